@@ -1,0 +1,157 @@
+// blend.cu — K5 per-tile front-to-back alpha compositing, sm_100a.
+//
+// Replaces the fixed-function rasteriser + fragment shader + ROP "under" blend of the reference:
+//   falloff / discard / premultiply   /root/reference/gsplat_plugin/shaders/GSplatShaderSource.h:304-312
+//   quad support (+-2 in eigen space) /root/reference/gsplat_plugin/shaders/GSplatShaderSource.h:168-188,277-282
+//   blend (ONE_MINUS_DST_ALPHA, ONE)  /root/reference/gsplat_plugin/src/GSplatRenderer.C:613-621
+//
+// One CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (one pixel per lane).  The
+// tile's depth-ordered instance list is staged through shared memory in batches of 256 records with
+// cp.async (LDGSTS) double buffering: thread t reads instance t's splat index and gathers its 48-byte
+// record as three 16-byte async copies.  Each warp then culls the batch against its own 8x4 block
+// 32 instances at a time (one instance per lane, conservative AABB test, ballot) and walks only the
+// surviving bits in order, so a small splat costs one warp pass instead of eight.  Transmittance
+// is kept per pixel in registers; a warp stops when all its pixels are saturated (T < eps) and the
+// CTA stops when all warps have (early-out: the reference has none).
+//
+// Per-pixel arithmetic is the spec of DESIGN.md §3 and oracle/gsplat_oracle.cpp shade(): explicit
+// fmaf where the spec says fmaf, nothing else contracted (TU built with -fmad=false), so coverage
+// decisions are bit-exact; only exp() differs from libm (MUFU.EX2), ~1e-7 relative.
+//
+// Algorithmic bytes: D_c * (4 + 48) + W*H*16 — HBM/L2-gather bound by design,
+// FP32-issue bound in practice.
+#include "common.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr int BL_THREADS = 256;
+constexpr int BL_BATCH   = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(BL_THREADS)
+blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
+             const uint2* __restrict__ ranges, float4* __restrict__ fb,
+             const __grid_constant__ FrameConsts F,
+             uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total)
+{
+    __shared__ __align__(16) Record srec[2][BL_BATCH];
+    __shared__ uint32_t s_consumed;
+
+    const int tile = blockIdx.x;
+    const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+    if (F.row_world > 1 && (ty % F.row_world) != F.row_rank) return;      // CTA-uniform
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx = tx * TILE + (warp & 1) * 8, by = ty * TILE + (warp >> 1) * 4;
+    const int px = bx + (lane & 7), py = by + (lane >> 3);
+    const bool inside = px < F.width && py < F.height;
+    const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+    // pixel-centre box of this warp's 8x4 block
+    const float wx_lo = (float)bx + 0.5f, wx_hi = (float)bx + 7.5f;
+    const float wy_lo = (float)by + 0.5f, wy_hi = (float)by + 3.5f;
+    const float eps = F.eps_t;
+
+    const uint2 range = ranges[tile];
+    const uint32_t start = range.x, len = range.y - range.x;
+    if (tid == 0) s_consumed = 0u;
+    __syncthreads();
+
+    float Cr = 0.0f, Cg = 0.0f, Cb = 0.0f, T = 1.0f;
+    bool done = !inside;
+    bool warp_done = __all_sync(0xffffffffu, done);
+    uint32_t warp_pos = 0;                       // instances this warp traversed when it saturated
+    const uint32_t nb = (len + BL_BATCH - 1) / BL_BATCH;
+
+    auto stage = [&](uint32_t b) {
+        const uint32_t k = b * BL_BATCH + tid;
+        if (k < len) {
+            const uint32_t ref = __ldg(inst + start + k);
+            const char* src = reinterpret_cast<const char*>(recs + ref);
+            char* dst = reinterpret_cast<char*>(&srec[b & 1][tid]);
+            cp_async16(dst, src); cp_async16(dst + 16, src + 16); cp_async16(dst + 32, src + 32);
+        }
+        cp_async_commit();
+    };
+
+    if (nb > 0) stage(0);
+    for (uint32_t b = 0; b < nb; ++b) {
+        if (b + 1 < nb) stage(b + 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const Record* buf = srec[b & 1];
+        const uint32_t count = min((uint32_t)BL_BATCH, len - b * BL_BATCH);
+        if (!warp_done) {
+            for (uint32_t c = 0; c < count && !warp_done; c += 32) {
+                const uint32_t my = c + lane;
+                bool ov = false;
+                if (my < count) {
+                    const float2 cc = *reinterpret_cast<const float2*>(&buf[my].cx);
+                    const uint32_t hp = buf[my].hpack;
+                    const float hx = __half2float(__ushort_as_half((unsigned short)(hp & 0xffffu)));
+                    const float hy = __half2float(__ushort_as_half((unsigned short)(hp >> 16)));
+                    ov = (cc.x - hx <= wx_hi) && (cc.x + hx >= wx_lo) && (cc.y - hy <= wy_hi) && (cc.y + hy >= wy_lo);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, ov);
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4* rp = reinterpret_cast<const float4*>(&buf[c + j]);
+                    const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                    if (!done) {
+                        const float dx = fpx - r0.x, dy = fpy - r0.y;
+                        const float qx = fmaf(dy, r0.w, dx * r0.z);
+                        const float qy = fmaf(dy, r1.y, dx * r1.x);
+                        const float pw = fmaf(qy, qy, qx * qx);
+                        if (fabsf(qx) <= 2.0f && fabsf(qy) <= 2.0f && pw <= r1.w) {
+                            const float A = fminf(r1.z * __expf(-pw), 1.0f);
+                            const float w = T * A;
+                            Cr = fmaf(w, r2.x, Cr); Cg = fmaf(w, r2.y, Cg); Cb = fmaf(w, r2.z, Cb);
+                            T = T - w;
+                            done = T < eps;
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, done)) {
+                        warp_done = true;
+                        warp_pos = b * BL_BATCH + c + (uint32_t)j + 1u;
+                        break;
+                    }
+                }
+            }
+        }
+        // barrier: everyone is finished with buf before it is refilled; also the CTA-wide early-out vote
+        if (__syncthreads_and(warp_done ? 1 : 0)) break;
+    }
+    cp_async_wait<0>();
+
+    if (inside) fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, 1.0f - T);
+
+    if (lane == 0) atomicMax(&s_consumed, warp_done ? warp_pos : len);
+    __syncthreads();
+    if (tid == 0) {
+        if (tile_consumed) tile_consumed[tile] = s_consumed;
+        if (consumed_total && s_consumed) atomicAdd(consumed_total, (unsigned long long)s_consumed);
+    }
+}
+
+}  // namespace
+
+void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
+                  FrameConsts fc, uint32_t* tile_consumed, unsigned long long* consumed_total,
+                  cudaStream_t s)
+{
+    const int tiles = fc.tiles_x * fc.tiles_y;
+    if (tiles <= 0) return;
+    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fc, tile_consumed, consumed_total);
+}
+
+}  // namespace gsb

@@ -1,0 +1,81 @@
+// common.cuh — shared device/host declarations for libgsplat_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstddef>
+
+namespace gsb {
+
+constexpr int      TILE       = 16;            // screen tile edge
+constexpr uint32_t KEY_CULLED = 0xFFFFFFFFu;   // depth key of a culled splat: sorts last
+constexpr int      NUM_SMS    = 148;           // B200
+
+// Per-frame constants handed to the kernels by value (fits the 4 KB kernel-parameter space).
+// Matrices are column-major: element (row r, col c) = m[c*4 + r].
+struct FrameConsts {
+    float view[16], proj[16], object[16], inv_object[16], obj_view[16];
+    float cam[3];
+    float origin[3];
+    float W, H;                 // glH_ScreenSize as floats
+    int   width, height;
+    int   tiles_x, tiles_y;
+    int   sh_order;             // effective order (0 when the packed set has no SH)
+    int   row_rank, row_world;  // tile-row ownership
+    float eps_t;                // transmittance early-out threshold
+};
+
+// 2-D record written by project and gathered by blend: 48 bytes, three 16-byte chunks.
+struct __align__(16) Record {
+    float cx, cy, m00, m01;
+    float m10, m11, alpha, pmax;
+    float r, g, b;
+    uint32_t hpack;             // half(hx) | half(hy) << 16, rounded toward +inf (conservative cull data)
+};
+static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
+
+// Packed, render-layout splat attributes (built by pack on active-set change):
+//   geomA[i] = (p.x, p.y, p.z, alpha)                         16 B
+//   geomB[i] = (scale h3 | orient h4 (x,y,z,w) | pad h1)      16 B
+//   col[k][i], k = 0..5: 48 halfs = Cd(3) then SH coefficient j channel c at 3+3j+c   6 x 16 B
+// Degree d needs halfs [0, 3 + 3*{0,3,8,15}) -> planes {1,2,4,6}.
+struct PackedSplats {
+    const float4* geomA;
+    const uint4*  geomB;
+    const uint4*  col[6];
+};
+
+// radix sort / scan primitives (radix_sort.cu, scan.cu)
+size_t   scan_scratch_bytes(size_t n);
+// exclusive scan of n uint32; out may alias in.  If total_dev != nullptr the 64-bit grand total is stored there.
+void     exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
+                            unsigned long long* total_dev, cudaStream_t s, int* launches);
+size_t   sort_scratch_bytes(size_t n);
+// Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit).  Ping-pongs between
+// (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
+                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* launches);
+
+// project.cu
+void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
+                 const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
+                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
+                 int planes, cudaStream_t s);
+void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
+                    uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
+                    unsigned long long* n_visible, cudaStream_t s);
+
+// binning.cu
+void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t n, FrameConsts fc,
+                        uint32_t* counts, cudaStream_t s);
+void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t n,
+                 FrameConsts fc, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
+                        cudaStream_t s);
+
+// blend.cu
+void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
+                  FrameConsts fc, uint32_t* tile_consumed, unsigned long long* consumed_total,
+                  cudaStream_t s);
+
+}  // namespace gsb

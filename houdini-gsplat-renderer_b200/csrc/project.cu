@@ -1,0 +1,346 @@
+// project.cu — K0 pack (active-set change) and K1 project + SH + depth key (every frame), sm_100a.
+//
+// K0 replaces the CPU texture packing of GSplatRenderer::generateRenderGeometry
+//    (/root/reference/gsplat_plugin/src/GSplatRenderer.C:448-505): the per-prim SoA arrays that
+//    registerUpdate received are re-laid into 16-byte planes so K1's loads are coalesced LDG.128.
+// K1 replaces, once per splat instead of once per vertex (the reference repeats it 6x):
+//    depth key                        src/GSplatRenderer.C:196-202
+//    centre + cull                    shaders/GSplatShaderSource.h:198-214, 277-282
+//    covariance chain + eigen axes    shaders/GSplatShaderCoreLib.h:10-93
+//    SH -> RGB                        shaders/GSplatShaderCoreLib.h:103-179, GSplatShaderSource.h:244-275
+//
+// The fp32 expression order below IS the spec and matches oracle/gsplat_oracle.cpp
+// operation for operation: this TU is compiled with -fmad=false, IEEE division and sqrt
+// (-prec-div=true -prec-sqrt=true, no fast-math), so keys, records and rectangles are bit-exact.
+// HBM-bound: 32 B read per submitted splat, +16..96 B colour per visible splat, 64 B written.
+#include "common.cuh"
+
+namespace gsb {
+
+namespace {
+
+#define MAT(M, r, c) ((M)[(c) * 4 + (r)])
+
+__device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+__device__ __forceinline__ float lo_h(uint32_t w) { return h2f((uint16_t)(w & 0xffffu)); }
+__device__ __forceinline__ float hi_h(uint32_t w) { return h2f((uint16_t)(w >> 16)); }
+
+// ln(x), x > 0, in double with + - * / only: the same sequence as oracle det_log() => same bits.
+__device__ __forceinline__ double det_log(double x)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    int k = (int)((u >> 52) & 0x7ffull) - 1023;
+    u = (u & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double m = __longlong_as_double((long long)u);
+    if (m > 1.4142135623730951) { m = m * 0.5; k = k + 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    double p = 1.0 / 19.0;
+    p = p * s2 + 1.0 / 17.0;
+    p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0;
+    p = p * s2 + 1.0 / 11.0;
+    p = p * s2 + 1.0 / 9.0;
+    p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0;
+    p = p * s2 + 1.0 / 3.0;
+    p = p * s2 + 1.0;
+    return (2.0 * s) * p + (double)k * 0.6931471805599453;
+}
+
+// ------------------------------------------------------------------------------------ K0 pack
+// One thread per splat of one registered prim.  Source layout = what registerUpdate receives
+// (R.h:34-47): pos f32x3, Cd h3, alpha f32, scale h3, orient h4 (x,y,z,w), SH 3 x half[16].
+__global__ void __launch_bounds__(256)
+pack_kernel(const float* __restrict__ pos, const uint16_t* __restrict__ cd, const float* __restrict__ alpha,
+            const uint16_t* __restrict__ scale, const uint16_t* __restrict__ orient,
+            const uint16_t* __restrict__ shx, const uint16_t* __restrict__ shy, const uint16_t* __restrict__ shz,
+            int64_t count, int64_t dst, float4* __restrict__ geomA, uint4* __restrict__ geomB,
+            uint4* __restrict__ c0, uint4* __restrict__ c1, uint4* __restrict__ c2,
+            uint4* __restrict__ c3, uint4* __restrict__ c4, uint4* __restrict__ c5, int planes)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t o = dst + i;
+    geomA[o] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], alpha[i]);
+    uint32_t s0 = scale[3 * i], s1 = scale[3 * i + 1], s2 = scale[3 * i + 2];
+    uint32_t q0 = orient[4 * i], q1 = orient[4 * i + 1], q2 = orient[4 * i + 2], q3 = orient[4 * i + 3];
+    geomB[o] = make_uint4(s0 | (s1 << 16), s2 | (q0 << 16), q1 | (q2 << 16), q3);
+    uint16_t h[48];
+    h[0] = cd[3 * i]; h[1] = cd[3 * i + 1]; h[2] = cd[3 * i + 2];
+    if (planes > 1) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) {
+            h[3 + 3 * j] = shx[16 * i + j]; h[4 + 3 * j] = shy[16 * i + j]; h[5 + 3 * j] = shz[16 * i + j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 3; j < 48; ++j) h[j] = 0;
+    }
+    uint4* cp[6] = { c0, c1, c2, c3, c4, c5 };
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        if (p < planes) {
+            uint4 w;
+            w.x = (uint32_t)h[8 * p + 0] | ((uint32_t)h[8 * p + 1] << 16);
+            w.y = (uint32_t)h[8 * p + 2] | ((uint32_t)h[8 * p + 3] << 16);
+            w.z = (uint32_t)h[8 * p + 4] | ((uint32_t)h[8 * p + 5] << 16);
+            w.w = (uint32_t)h[8 * p + 6] | ((uint32_t)h[8 * p + 7] << 16);
+            cp[p][o] = w;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K1 project
+constexpr float SH_C1   = 0.4886025f;
+constexpr float SH_C2_0 = 1.0925484f, SH_C2_1 = -1.0925484f, SH_C2_2 = 0.3153916f,
+                SH_C2_3 = -1.0925484f, SH_C2_4 = 0.5462742f;
+constexpr float SH_C3_0 = -0.5900436f, SH_C3_1 = 2.8906114f, SH_C3_2 = -0.4570458f,
+                SH_C3_3 = 0.3731763f, SH_C3_4 = -0.4570458f, SH_C3_5 = 1.4453057f,
+                SH_C3_6 = -0.5900436f;
+
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps, int64_t n,
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, Record* __restrict__ recs,
+               uint2* __restrict__ rects, unsigned long long* __restrict__ n_visible)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool vis = false;
+    if (i < n) {
+        const float4 ga = __ldg(ps.geomA + i);
+        const uint4  gb = __ldg(ps.geomB + i);
+        const float p[3] = { ga.x, ga.y, ga.z };
+        const float alpha = ga.w;
+        uint32_t key = KEY_CULLED;
+        uint2 rect = make_uint2(1u, 1u);          // x0=1,x1=0,y0=1,y1=0 : empty
+        Record rec;
+        do {
+            if (!(alpha >= 1.0f / 255.0f)) break;
+            float psx[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; psx[k] = t + F.origin[k]; }
+            float vc[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
+            const float fy = -vc[1];
+            float clip[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
+            const float cw = clip[3];
+            if (!(cw > 0.0f)) break;
+            if (!(clip[2] >= -cw && clip[2] <= cw)) break;
+            const float ndcx = clip[0] / cw;
+            const float ndcy = (-clip[1]) / cw;
+            const float cx = ((ndcx + 1.0f) * 0.5f) * F.W;
+            const float cy = ((ndcy + 1.0f) * 0.5f) * F.H;
+
+            const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
+            const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
+            float Rt[3][3];
+            Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
+            Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
+            Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
+            const float sc[3] = { sx, sy, sz };
+            float Mm[3][3], M2[3][3], S[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    M2[a][b] = (Mm[a][0] * MAT(F.object, b, 0) + Mm[a][1] * MAT(F.object, b, 1)) + Mm[a][2] * MAT(F.object, b, 2);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    S[a][b] = (M2[0][a] * M2[0][b] + M2[1][a] * M2[1][b]) + M2[2][a] * M2[2][b];
+                    S[b][a] = S[a][b];
+                }
+
+            float t[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                t[r] = ((MAT(F.view, r, 0) * psx[0] + MAT(F.view, r, 1) * psx[1]) + MAT(F.view, r, 2) * psx[2]) + MAT(F.view, r, 3);
+            const float aspect = MAT(F.proj, 0, 0) / MAT(F.proj, 1, 1);
+            const float tanFovX = 1.0f / MAT(F.proj, 0, 0);
+            const float tanFovY = 1.0f / (MAT(F.proj, 1, 1) * aspect);
+            const float limX = 1.3f * tanFovX, limY = 1.3f * tanFovY;
+            const float tz = t[2];
+            float rx = t[0] / tz; rx = fminf(fmaxf(rx, -limX), limX);
+            float ry = t[1] / tz; ry = fminf(fmaxf(ry, -limY), limY);
+            const float tx = rx * tz, ty = ry * tz;
+            const float focal = (F.W * MAT(F.proj, 0, 0)) / 2.0f;
+            const float j0 = focal / tz;
+            const float tz2 = tz * tz;
+            const float j2x = -((focal * tx) / tz2);
+            const float j2y = -((focal * ty) / tz2);
+            float A0[3], A1[3], B0[3], B1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                A0[k] = j0 * MAT(F.view, 0, k) + j2x * MAT(F.view, 2, k);
+                A1[k] = j0 * MAT(F.view, 1, k) + j2y * MAT(F.view, 2, k);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                B0[k] = (A0[0] * S[0][k] + A0[1] * S[1][k]) + A0[2] * S[2][k];
+                B1[k] = (A1[0] * S[0][k] + A1[1] * S[1][k]) + A1[2] * S[2][k];
+            }
+            const float c00 = (B0[0] * A0[0] + B0[1] * A0[1]) + B0[2] * A0[2];
+            const float c01 = (B0[0] * A1[0] + B0[1] * A1[1]) + B0[2] * A1[2];
+            const float c11 = (B1[0] * A1[0] + B1[1] * A1[1]) + B1[2] * A1[2];
+            const float a = c00 + 0.3f, b = c01, c = c11 + 0.3f;
+
+            const float mid = 0.5f * (a + c);
+            const float hd = (a - c) / 2.0f;
+            const float radius = sqrtf(hd * hd + b * b);
+            const float l1 = mid + radius;
+            const float l2 = fmaxf(mid - radius, 0.1f);
+            const float dvx = b, dvy = l1 - a;
+            const float len = sqrtf(dvx * dvx + dvy * dvy);
+            if (!(len > 0.0f) || !(len <= 3.0e38f)) break;
+            const float ex = dvx / len, ey = dvy / len;
+            const float s1 = fminf(sqrtf(2.0f * l1), 4096.0f);
+            const float s2 = fminf(sqrtf(2.0f * l2), 4096.0f);
+            if (!(s1 > 0.0f) || !(s2 > 0.0f)) break;
+            const float u1x = s1 * ex, u1y = s1 * ey;
+            const float u2x = -(s2 * ey), u2y = s2 * ex;
+
+            const float pmax = (float)det_log((double)alpha * 255.0);
+            if (!(pmax >= 0.0f)) break;
+
+            const float bxh = 2.0f * (fabsf(u1x) + fabsf(u2x));
+            const float byh = 2.0f * (fabsf(u1y) + fabsf(u2y));
+            const float rr = sqrtf(pmax);
+            const float exh = rr * sqrtf(u1x * u1x + u2x * u2x);
+            const float eyh = rr * sqrtf(u1y * u1y + u2y * u2y);
+            float hx = fminf(bxh, exh); hx = hx + (hx * 0.0001f + 0.01f);
+            float hy = fminf(byh, eyh); hy = hy + (hy * 0.0001f + 0.01f);
+            const float x0f = fmaxf(ceilf((cx - hx) - 0.5f), 0.0f);
+            const float x1f = fminf(floorf((cx + hx) - 0.5f), F.W - 1.0f);
+            const float y0f = fmaxf(ceilf((cy - hy) - 0.5f), 0.0f);
+            const float y1f = fminf(floorf((cy + hy) - 0.5f), F.H - 1.0f);
+            if (!(x0f <= x1f) || !(y0f <= y1f)) break;
+            const int x0 = (int)x0f, x1 = (int)x1f, y0 = (int)y0f, y1 = (int)y1f;
+            if (F.row_world > 1) {
+                bool any = false;
+                for (int tyy = y0 / TILE; tyy <= y1 / TILE && !any; ++tyy) any = (tyy % F.row_world) == F.row_rank;
+                if (!any) break;
+            }
+
+            float rgb[3];
+            {
+                const uint4 c0 = __ldg(ps.col[0] + i);
+                rgb[0] = lo_h(c0.x); rgb[1] = hi_h(c0.x); rgb[2] = lo_h(c0.y);
+                if (ORDER > 0) {
+                    // 48 halfs: Cd(3) then coefficient j channel ch at 3 + 3j + ch
+                    uint32_t w[24];
+                    w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
+                    constexpr int PLANES = ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6);
+#pragma unroll
+                    for (int pl = 1; pl < PLANES; ++pl) {
+                        const uint4 cc = __ldg(ps.col[pl] + i);
+                        w[4 * pl] = cc.x; w[4 * pl + 1] = cc.y; w[4 * pl + 2] = cc.z; w[4 * pl + 3] = cc.w;
+                    }
+                    const float wv[3] = { psx[0] - F.cam[0], psx[1] - F.cam[1], psx[2] - F.cam[2] };
+                    float ov[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        ov[r] = (MAT(F.inv_object, r, 0) * wv[0] + MAT(F.inv_object, r, 1) * wv[1]) + MAT(F.inv_object, r, 2) * wv[2];
+                    const float dl = sqrtf((ov[0] * ov[0] + ov[1] * ov[1]) + ov[2] * ov[2]);
+                    const float x = ov[0] / dl, y = ov[1] / dl, z = ov[2] / dl;
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        auto SH = [&](int j) -> float {      // coefficient j (0-based: sh1 = j 0)
+                            const int hidx = 3 + 3 * j + ch;
+                            const uint32_t word = w[hidx >> 1];
+                            return (hidx & 1) ? hi_h(word) : lo_h(word);
+                        };
+                        float res = rgb[ch];
+                        res = res + SH_C1 * (((-SH(0)) * y + SH(1) * z) - SH(2) * x);
+                        if (ORDER >= 2) {
+                            float t2 = (SH_C2_0 * xy) * SH(3);
+                            t2 = t2 + (SH_C2_1 * yz) * SH(4);
+                            t2 = t2 + (SH_C2_2 * ((2.0f * zz - xx) - yy)) * SH(5);
+                            t2 = t2 + (SH_C2_3 * xz) * SH(6);
+                            t2 = t2 + (SH_C2_4 * (xx - yy)) * SH(7);
+                            res = res + t2;
+                            if (ORDER >= 3) {
+                                float t3 = ((SH_C3_0 * y) * (3.0f * xx - yy)) * SH(8);
+                                t3 = t3 + ((SH_C3_1 * xy) * z) * SH(9);
+                                t3 = t3 + ((SH_C3_2 * y) * ((4.0f * zz - xx) - yy)) * SH(10);
+                                t3 = t3 + ((SH_C3_3 * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy)) * SH(11);
+                                t3 = t3 + ((SH_C3_4 * x) * ((4.0f * zz - xx) - yy)) * SH(12);
+                                t3 = t3 + ((SH_C3_5 * z) * (xx - yy)) * SH(13);
+                                t3 = t3 + ((SH_C3_6 * x) * (xx - 3.0f * yy)) * SH(14);
+                                res = res + t3;
+                            }
+                        }
+                        rgb[ch] = fmaxf(res, 0.0f);
+                    }
+                }
+            }
+
+            // depth key on the UNMODIFIED position (R.C:196-202, 454, 584)
+            const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            key = __float_as_uint(d2);
+            rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+            rec.cx = cx; rec.cy = cy;
+            rec.m00 = ex / s1; rec.m01 = ey / s1;
+            rec.m10 = (-ey) / s2; rec.m11 = ex / s2;
+            rec.alpha = alpha; rec.pmax = pmax;
+            rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
+            rec.hpack = (uint32_t)__half_as_ushort(__float2half_ru(hx)) |
+                        ((uint32_t)__half_as_ushort(__float2half_ru(hy)) << 16);
+            vis = true;
+        } while (false);
+
+        keys[i] = key;
+        vals[i] = (uint32_t)i;
+        rects[i] = rect;
+        if (vis) {
+            float4* o = reinterpret_cast<float4*>(recs + i);
+            o[0] = make_float4(rec.cx, rec.cy, rec.m00, rec.m01);
+            o[1] = make_float4(rec.m10, rec.m11, rec.alpha, rec.pmax);
+            o[2] = make_float4(rec.r, rec.g, rec.b, __uint_as_float(rec.hpack));
+        }
+    }
+    // one atomic per warp for V
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_visible, (unsigned long long)__popc(m));
+}
+
+}  // namespace
+
+void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
+                 const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
+                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
+                 int planes, cudaStream_t s)
+{
+    if (count <= 0) return;
+    unsigned grid = (unsigned)((count + 255) / 256);
+    pack_kernel<<<grid, 256, 0, s>>>(pos, cd_h, alpha, scale_h, orient_h, shx, shy, shz, count, dst_offset,
+                                     geomA, geomB, col[0], col[1], col[2], col[3], col[4], col[5], planes);
+}
+
+void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
+                    uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
+                    unsigned long long* n_visible, cudaStream_t s)
+{
+    if (n <= 0) return;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    switch (fc.sh_order) {
+    case 0:  project_kernel<0><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
+    case 1:  project_kernel<1><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
+    case 2:  project_kernel<2><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
+    default: project_kernel<3><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
+    }
+}
+
+}  // namespace gsb

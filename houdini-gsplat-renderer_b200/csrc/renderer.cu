@@ -1,0 +1,609 @@
+// renderer.cu — host side of libgsplat_b200.so: the C ABI of include/gsplat_b200.h and a C++ mirror
+// of the reference's GSplatRenderer registry / state machine
+// (/root/reference/gsplat_plugin/include/GSplatRenderer.h:29-131, src/GSplatRenderer.C:141-153,
+// 218-320, 322-378, 403-418, 534-563, 660-694).  What the reference does with GL textures, a CPU
+// argsort and one instanced draw is done here with CUDA launches on one stream:
+//   pack (on active-set change) | project+SH+key -> radix sort -> tile counts -> scan -> emit ->
+//   tile radix partition -> tile ranges -> blend | optional D2H.
+// No CPU fallback exists: every entry point fails with GSB_ERR_CUDA if the device is unusable.
+#include "common.cuh"
+#include "../../include/gsplat_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace gsb;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            std::ostringstream o_;                                                                \
+            o_ << #call << " failed: " << cudaGetErrorString(e_) << " (" << __FILE__ << ":" << __LINE__ << ")"; \
+            return fail(e_ == cudaErrorMemoryAllocation ? GSB_ERR_NOMEM : GSB_ERR_CUDA, o_.str()); \
+        }                                                                                         \
+    } while (0)
+
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;       // a little headroom so D jitter does not realloc every frame
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// One registered primitive (GSplatRegisterEntry, R.h:59-76).  Arrays are device copies.
+struct Entry {
+    uint64_t gdp = 0;
+    int64_t  version[4] = { 0, 0, 0, 0 };
+    int64_t  vtx0 = 0;
+    int64_t  count = 0;
+    float    origin[3] = { 0, 0, 0 };
+    bool     active = false;
+    int      age = -1, age_since_last_active = -1;
+    bool     has_sh = false;
+    DevBuf   pos, cd, alpha, scale, orient, shx, shy, shz;
+};
+
+enum { EV_START = 0, EV_PROJECT, EV_SORT, EV_BIN, EV_BLEND, EV_COPY, EV_COUNT };
+
+}  // namespace
+
+struct gsb_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+
+    // registry + state machine (names follow the reference's members)
+    std::map<std::string, std::unique_ptr<Entry>> registry;   // myRenderStateRegistry (ordered: deterministic iteration)
+    std::set<std::string> active_set;                         // myActiveRegistries
+    bool    render_enabled = true;                            // myIsRenderEnabled
+    bool    can_render = false;                               // myCanRender
+    bool    sh_present = false;                               // myIsShDataPresent
+    bool    explicit_cam_set = false;                         // myIsExplicitCameraPosSet
+    float   explicit_cam[3] = { 0, 0, 0 };
+    int     sh_order = 0;                                     // myShOrder
+    int64_t splat_count = 0;                                  // myGSplatCount
+    float   origin[3] = { 0, 0, 0 };                          // mySplatOrigin
+
+    // options
+    int64_t cap = GSB_REFERENCE_SPLAT_CAP;
+    float   eps_t = 1e-5f;
+    bool    stage_timing = false, keep_intermediates = false;
+
+    // packed render-layout attributes
+    DevBuf geomA, geomB, col[6];
+    int    planes = 1;
+
+    // per-frame device buffers
+    DevBuf keys[2], vals[2], keys_unsorted, recs, rects, counts, ikeys[2], ivals[2], ranges, tile_consumed, fb;
+    DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
+    unsigned long long* counters_h = nullptr;        // pinned mirror
+    int order_buf = 0, inst_buf = 0;
+    int64_t last_n = 0; uint64_t last_d = 0; int last_tiles = 0; int last_w = 0, last_h = 0;
+    float4* last_fb = nullptr;
+
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool ev_valid = false;
+    gsb_stats stats{};
+};
+
+namespace {
+
+std::string make_id(const gsb_prim_key& k)
+{
+    // same text the reference builds at R.C:241-243
+    std::ostringstream oss;
+    oss << std::hex << std::showbase << (uintptr_t)k.gdp << "__" << std::dec << k.vtx0 << "__"
+        << k.version[0] << "_" << k.version[1] << "_" << k.version[2] << "_" << k.version[3];
+    return oss.str();
+}
+
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s)
+{
+    CU(b.ensure(bytes ? bytes : 16));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    return GSB_OK;
+}
+
+// camera = (0,0,0,1) * inverse(view) in double, rounded to f32 (R.C:558-562): 4th column of the
+// inverse in column-vector convention.  Full adjugate, same formula as the oracle's.
+void camera_from_view(const float view[16], float cam[3])
+{
+    double m[16], a[16];
+    for (int i = 0; i < 16; ++i) m[i] = (double)view[i];
+    a[0] = m[5]*m[10]*m[15] - m[5]*m[11]*m[14] - m[9]*m[6]*m[15] + m[9]*m[7]*m[14] + m[13]*m[6]*m[11] - m[13]*m[7]*m[10];
+    a[4] = -m[4]*m[10]*m[15] + m[4]*m[11]*m[14] + m[8]*m[6]*m[15] - m[8]*m[7]*m[14] - m[12]*m[6]*m[11] + m[12]*m[7]*m[10];
+    a[8] = m[4]*m[9]*m[15] - m[4]*m[11]*m[13] - m[8]*m[5]*m[15] + m[8]*m[7]*m[13] + m[12]*m[5]*m[11] - m[12]*m[7]*m[9];
+    a[12] = -m[4]*m[9]*m[14] + m[4]*m[10]*m[13] + m[8]*m[5]*m[14] - m[8]*m[6]*m[13] - m[12]*m[5]*m[10] + m[12]*m[6]*m[9];
+    a[13] = m[0]*m[9]*m[14] - m[0]*m[10]*m[13] - m[8]*m[1]*m[14] + m[8]*m[2]*m[13] + m[12]*m[1]*m[10] - m[12]*m[2]*m[9];
+    a[14] = -m[0]*m[5]*m[14] + m[0]*m[6]*m[13] + m[4]*m[1]*m[14] - m[4]*m[2]*m[13] - m[12]*m[1]*m[6] + m[12]*m[2]*m[5];
+    double det = m[0]*a[0] + m[1]*a[4] + m[2]*a[8] + m[3]*a[12];
+    double r = 1.0 / det;
+    cam[0] = (float)(a[12] * r); cam[1] = (float)(a[13] * r); cam[2] = (float)(a[14] * r);
+}
+
+int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
+
+}  // namespace
+
+// ============================================================================== C ABI
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+const char* gsb_last_error(void) { return g_err.c_str(); }
+
+int gsb_create(int cuda_device, gsb_context** out)
+{
+    if (!out) return fail(GSB_ERR_INVALID, "gsb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cuda_device < 0 || cuda_device >= ndev) return fail(GSB_ERR_INVALID, "gsb_create: no such CUDA device");
+    CU(cudaSetDevice(cuda_device));
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major < 10)
+        return fail(GSB_ERR_CUDA, std::string("gsb_create: device is ") + prop.name +
+                                      " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                      "); this library contains sm_100a code only");
+    std::unique_ptr<gsb_context> c(new gsb_context);
+    c->device = cuda_device;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
+    CU(c->counters.ensure(64));
+    CU(cudaMallocHost(&c->counters_h, 64));
+    memset(c->counters_h, 0, 64);
+    *out = c.release();
+    return GSB_OK;
+}
+
+int gsb_destroy(gsb_context* ctx)
+{
+    if (!ctx) return GSB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+    cudaStream_t s = ctx->own_stream;
+    delete ctx;
+    if (s) cudaStreamDestroy(s);
+    return GSB_OK;
+}
+
+int gsb_set_stream(gsb_context* ctx, void* cuda_stream)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GSB_OK;
+}
+
+int gsb_synchronize(gsb_context* ctx)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSB_OK;
+}
+
+int gsb_set_option(gsb_context* ctx, int option, double value)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    switch (option) {
+    case GSB_OPT_SPLAT_CAP:
+        if (value < 0) return fail(GSB_ERR_INVALID, "GSB_OPT_SPLAT_CAP must be >= 0");
+        ctx->cap = (int64_t)value; return GSB_OK;
+    case GSB_OPT_EPS_T:
+        if (!(value >= 0.0 && value < 1.0)) return fail(GSB_ERR_INVALID, "GSB_OPT_EPS_T must be in [0,1)");
+        ctx->eps_t = (float)value; return GSB_OK;
+    case GSB_OPT_STAGE_TIMING: ctx->stage_timing = value != 0; return GSB_OK;
+    case GSB_OPT_KEEP_INTERMEDIATES: ctx->keep_intermediates = value != 0; return GSB_OK;
+    default: return fail(GSB_ERR_INVALID, "unknown option");
+    }
+}
+
+int gsb_registry_size(gsb_context* ctx) { return ctx ? (int)ctx->registry.size() : 0; }
+
+// ------------------------------------------------------------------ registerUpdate, R.C:218-291
+int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat_count, const float origin[3],
+                        const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
+                        const uint16_t* orient_h, const uint16_t* shx_h, const uint16_t* shy_h,
+                        const uint16_t* shz_h, char* id_out)
+{
+    if (!ctx || !key || !origin) return fail(GSB_ERR_INVALID, "gsb_register_update: NULL argument");
+    if (splat_count < 0 || splat_count > 0x7fffffffLL) return fail(GSB_ERR_INVALID, "gsb_register_update: bad splat_count");
+    if (splat_count > 0 && (!pos || !cd_h || !alpha || !scale_h || !orient_h))
+        return fail(GSB_ERR_INVALID, "gsb_register_update: NULL attribute array");
+    const bool has_sh = shx_h && shy_h && shz_h;
+    if (!has_sh && (shx_h || shy_h || shz_h))
+        return fail(GSB_ERR_INVALID, "gsb_register_update: shx/shy/shz must be all NULL or all non-NULL");
+    CU(cudaSetDevice(ctx->device));
+    const std::string id = make_id(*key);
+
+    // same gdp, different version -> erase (R.C:246-265)
+    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {
+        Entry& e = *it->second;
+        if (e.gdp == key->gdp && memcmp(e.version, key->version, sizeof e.version) != 0) it = ctx->registry.erase(it);
+        else ++it;
+    }
+    auto& slot = ctx->registry[id];
+    if (!slot) slot.reset(new Entry);
+    Entry& e = *slot;
+    e.gdp = key->gdp; e.vtx0 = key->vtx0; memcpy(e.version, key->version, sizeof e.version);
+    e.count = splat_count; memcpy(e.origin, origin, sizeof e.origin);
+    e.active = false; e.age = -1; e.age_since_last_active = -1;
+    e.has_sh = has_sh && splat_count > 0;
+    const size_t n = (size_t)splat_count;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = upload(e.pos, pos, n * 12, s))) return rc;
+    if ((rc = upload(e.cd, cd_h, n * 6, s))) return rc;
+    if ((rc = upload(e.alpha, alpha, n * 4, s))) return rc;
+    if ((rc = upload(e.scale, scale_h, n * 6, s))) return rc;
+    if ((rc = upload(e.orient, orient_h, n * 8, s))) return rc;
+    if (e.has_sh) {
+        if ((rc = upload(e.shx, shx_h, n * 32, s))) return rc;
+        if ((rc = upload(e.shy, shy_h, n * 32, s))) return rc;
+        if ((rc = upload(e.shz, shz_h, n * 32, s))) return rc;
+    }
+    CU(cudaStreamSynchronize(s));      // the caller's arrays are not borrowed past this call
+    // a re-registered id with new data must be re-packed even if the active set looks unchanged
+    ctx->active_set.erase(id);
+    if (id_out) { strncpy(id_out, id.c_str(), GSB_ID_MAX - 1); id_out[GSB_ID_MAX - 1] = 0; }
+    return GSB_OK;
+}
+
+int gsb_include_in_render_pass(gsb_context* ctx, const char* id)      // R.C:313-320
+{
+    if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
+    auto it = ctx->registry.find(id);
+    if (it == ctx->registry.end()) return GSB_OK;      // the reference silently ignores unknown ids
+    it->second->active = true;
+    return GSB_OK;
+}
+
+int gsb_flush_entries_for_matching_detail(gsb_context* ctx, const char* id)   // R.C:293-311
+{
+    if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
+    auto it = ctx->registry.find(id);
+    if (it == ctx->registry.end()) return GSB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint64_t gdp = it->second->gdp;
+    for (auto j = ctx->registry.begin(); j != ctx->registry.end();) {
+        if (j->second->gdp == gdp) j = ctx->registry.erase(j); else ++j;
+    }
+    return GSB_OK;
+}
+
+int gsb_set_rendering_enabled(gsb_context* ctx, int enabled)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    ctx->render_enabled = enabled != 0; return GSB_OK;
+}
+int gsb_set_explicit_camera_pos(gsb_context* ctx, const float pos[3])
+{
+    if (!ctx || !pos) return fail(GSB_ERR_INVALID, "NULL argument");
+    ctx->explicit_cam_set = true; memcpy(ctx->explicit_cam, pos, 12); return GSB_OK;
+}
+int gsb_set_spherical_harmonics_order(gsb_context* ctx, int sh_order)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    ctx->sh_order = sh_order; return GSB_OK;       // validation (0..3) is the caller's, GR_GSplat.C:444-457
+}
+
+// ------------------------------------------------------------------ generateRenderGeometry, R.C:322-532
+int gsb_generate_render_geometry(gsb_context* ctx)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    ctx->stats.repacked = 0;
+    // isRenderStateRegistryCurrent (R.C:141-153)
+    std::set<std::string> requested;
+    for (auto& kv : ctx->registry) if (kv.second->active) requested.insert(kv.first);
+    if (requested == ctx->active_set) return GSB_OK;
+
+    CU(cudaSetDevice(ctx->device));
+    const int64_t cap = ctx->cap > 0 ? ctx->cap : INT64_MAX;
+    ctx->active_set.clear();
+    ctx->can_render = false;
+    int64_t total = 0;
+    bool sh_all = true, cap_hit = false;
+    for (auto& kv : ctx->registry) {                       // R.C:344-358
+        Entry& e = *kv.second;
+        if (!cap_hit && e.active && e.count > 0) {
+            ctx->active_set.insert(kv.first);
+            total += e.count;
+            sh_all = sh_all && e.has_sh;                   // SH present iff every active prim has it
+        }
+        if (total >= cap) cap_hit = true;
+    }
+    if (!total) return GSB_OK;                             // R.C:360-363
+    ctx->splat_count = std::min(total, cap);
+    if (ctx->splat_count > 0x7fffffffLL) return fail(GSB_ERR_LIMIT, "more than 2^31-1 splats in the active set");
+    ctx->sh_present = sh_all;
+    ctx->planes = sh_all ? 6 : 1;
+
+    // origin = mean of the active prims' barycentres, fp32, iteration order = ascending id (R.C:403-418)
+    float o[3] = { 0, 0, 0 }; int clusters = 0;
+    for (auto& id : ctx->active_set) {
+        const Entry& e = *ctx->registry[id];
+        o[0] += e.origin[0]; o[1] += e.origin[1]; o[2] += e.origin[2]; ++clusters;
+    }
+    if (clusters > 0) { const float c = (float)clusters; o[0] /= c; o[1] /= c; o[2] /= c; }
+    memcpy(ctx->origin, o, sizeof o);
+
+    const size_t n = (size_t)ctx->splat_count;
+    CU(ctx->geomA.ensure(n * 16)); CU(ctx->geomB.ensure(n * 16));
+    for (int p = 0; p < ctx->planes; ++p) CU(ctx->col[p].ensure(n * 16));
+    uint4* cols[6];
+    for (int p = 0; p < 6; ++p) cols[p] = ctx->col[p].as<uint4>();
+    int64_t offset = 0;
+    for (auto& id : ctx->active_set) {                     // R.C:420-511
+        const Entry& e = *ctx->registry[id];
+        const int64_t left = ctx->splat_count - offset;
+        if (left <= 0) break;
+        const int64_t cnt = std::min(e.count, left);
+        launch_pack(e.pos.as<float>(), e.cd.as<uint16_t>(), e.alpha.as<float>(), e.scale.as<uint16_t>(),
+                    e.orient.as<uint16_t>(), e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(),
+                    cnt, offset, ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), cols, ctx->planes, ctx->stream);
+        offset += cnt;
+    }
+    CU(cudaGetLastError());
+    ctx->can_render = true;
+    ctx->stats.repacked = 1;
+    return GSB_OK;
+}
+
+// ------------------------------------------------------------------ render, R.C:534-658
+int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
+{
+    if (!ctx || !fr) return fail(GSB_ERR_INVALID, "gsb_render: NULL argument");
+    gsb_stats& st = ctx->stats;
+    st.rendered = 0; st.launches = 0;
+    if (!ctx->render_enabled || !ctx->can_render) return GSB_OK;          // R.C:536-539
+    bool any = false;
+    for (auto& kv : ctx->registry) any |= kv.second->active;
+    if (!any) return GSB_OK;                                             // R.C:541-549
+    if (fr->width < 1 || fr->height < 1 || fr->width > 65535 || fr->height > 65535)
+        return fail(GSB_ERR_LIMIT, "gsb_render: screen size must be 1..65535");
+    if (fr->row_world < 1 || fr->row_rank < 0 || fr->row_rank >= fr->row_world)
+        return fail(GSB_ERR_INVALID, "gsb_render: bad tile-row partition");
+    if (target && target->gl_texture != 0)
+        return fail(GSB_ERR_INVALID, "gsb_render: this build has no OpenGL; CUDA<->GL interop target unavailable");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+
+    FrameConsts fc{};
+    memcpy(fc.view, fr->view, 64); memcpy(fc.proj, fr->proj, 64); memcpy(fc.object, fr->object, 64);
+    memcpy(fc.inv_object, fr->inv_object, 64); memcpy(fc.obj_view, fr->obj_view, 64);
+    if (ctx->explicit_cam_set) memcpy(fc.cam, ctx->explicit_cam, 12);     // R.C:552-555
+    else camera_from_view(fr->view, fc.cam);                              // R.C:556-563
+    memcpy(fc.origin, ctx->origin, 12);
+    fc.width = fr->width; fc.height = fr->height; fc.W = (float)fr->width; fc.H = (float)fr->height;
+    fc.tiles_x = (fr->width + TILE - 1) / TILE; fc.tiles_y = (fr->height + TILE - 1) / TILE;
+    const bool do_sh = ctx->sh_order > 0 && ctx->sh_present;              // R.C:623
+    fc.sh_order = do_sh ? std::min(ctx->sh_order, 3) : 0;
+    fc.row_rank = fr->row_rank; fc.row_world = fr->row_world; fc.eps_t = ctx->eps_t;
+    const int num_tiles = fc.tiles_x * fc.tiles_y;
+    const int64_t n = ctx->splat_count;
+    const size_t  N = (size_t)n;
+
+    // buffers
+    for (int b = 0; b < 2; ++b) { CU(ctx->keys[b].ensure(N * 4)); CU(ctx->vals[b].ensure(N * 4)); }
+    CU(ctx->recs.ensure(N * sizeof(Record))); CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16));
+    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N))); CU(ctx->scan_scratch.ensure(scan_scratch_bytes(N)));
+    CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
+    if (ctx->keep_intermediates) CU(ctx->keys_unsorted.ensure(N * 4));
+    float4* fb = nullptr;
+    const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
+    if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
+    else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
+
+    unsigned long long* cnt = ctx->counters.as<unsigned long long>();
+    const bool tm = ctx->stage_timing;
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_START], s));
+    CU(cudaMemsetAsync(cnt, 0, 64, s));
+
+    // K1 project + SH + key
+    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(),
+                     { ctx->col[0].as<uint4>(), ctx->col[1].as<uint4>(), ctx->col[2].as<uint4>(),
+                       ctx->col[3].as<uint4>(), ctx->col[4].as<uint4>(), ctx->col[5].as<uint4>() } };
+    launch_project(fc, ps, n, ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), ctx->recs.as<Record>(),
+                   ctx->rects.as<uint2>(), cnt + 0, s);
+    st.launches += 1;
+    if (ctx->keep_intermediates)
+        CU(cudaMemcpyAsync(ctx->keys_unsorted.p, ctx->keys[0].p, N * 4, cudaMemcpyDeviceToDevice, s));
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
+
+    // K3 global depth sort (32-bit keys, stable)
+    ctx->order_buf = radix_sort_pairs(ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(),
+                                      ctx->keys[1].as<uint32_t>(), ctx->vals[1].as<uint32_t>(), N, 0, 32,
+                                      ctx->sort_scratch.p, s, &st.launches);
+    const uint32_t* order = ctx->vals[ctx->order_buf].as<uint32_t>();
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
+
+    // K4 binning: counts -> scan -> (D to host) -> emit -> stable tile partition -> ranges
+    launch_tile_counts(order, ctx->rects.as<uint2>(), n, fc, ctx->counts.as<uint32_t>(), s);
+    exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), N, ctx->scan_scratch.p, cnt + 1, s, &st.launches);
+    st.launches += 1;
+    CU(cudaMemcpyAsync(ctx->counters_h, cnt, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint64_t V = ctx->counters_h[0], D = ctx->counters_h[1];
+    if (D > 0x7fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^31-1 tile instances in one frame");
+    for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
+    CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)D)));
+    launch_emit(order, ctx->rects.as<uint2>(), ctx->counts.as<uint32_t>(), n, fc,
+                ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
+    st.launches += 1;
+    const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
+    ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
+                                     ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
+                                     ctx->sort_scratch.p, s, &st.launches);
+    launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
+    st.launches += (D ? 1 : 0);
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_BIN], s));
+
+    // K5 blend
+    if (fr->row_world > 1 || true) {
+        // un-owned rows (multi-GPU) and the consumed table start from zero
+        CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));
+    }
+    if (fr->row_world > 1) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));
+    launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fc,
+                 ctx->tile_consumed.as<uint32_t>(), cnt + 2, s);
+    st.launches += 1;
+    CU(cudaGetLastError());
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
+    CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 8, cudaMemcpyDeviceToHost, s));
+
+    if (target && target->host_rgba) {
+        CU(cudaMemcpyAsync(target->host_rgba, fb, fb_bytes, cudaMemcpyDeviceToHost, s));
+        if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
+        CU(cudaStreamSynchronize(s));
+    } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
+    ctx->ev_valid = tm;
+
+    ctx->last_n = n; ctx->last_d = D; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
+    ctx->last_fb = fb;
+    st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D;
+    st.sh_order_used = fc.sh_order; st.width = fr->width; st.height = fr->height;
+    st.tiles_x = fc.tiles_x; st.tiles_y = fc.tiles_y;
+    memcpy(st.camera, fc.cam, 12); memcpy(st.origin, fc.origin, 12);
+    return GSB_OK;
+}
+
+// ------------------------------------------------------------------ postRender, R.C:660-678
+int gsb_post_render(gsb_context* ctx)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    for (auto& kv : ctx->registry) {
+        Entry& e = *kv.second;
+        if (e.active) e.age_since_last_active = 0;
+        else if (e.age_since_last_active > -1) ++e.age_since_last_active;
+        e.active = false;
+        ++e.age;
+    }
+    ctx->explicit_cam_set = false;
+    return GSB_OK;
+}
+
+int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
+{
+    if (!ctx || !out) return fail(GSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    gsb_stats& st = ctx->stats;
+    if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[2];
+    st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = 0.0f;
+    if (st.rendered && ctx->ev_valid) {
+        cudaEventElapsedTime(&st.ms_project, ctx->ev[EV_START], ctx->ev[EV_PROJECT]);
+        cudaEventElapsedTime(&st.ms_sort, ctx->ev[EV_PROJECT], ctx->ev[EV_SORT]);
+        cudaEventElapsedTime(&st.ms_bin, ctx->ev[EV_SORT], ctx->ev[EV_BIN]);
+        cudaEventElapsedTime(&st.ms_blend, ctx->ev[EV_BIN], ctx->ev[EV_BLEND]);
+        cudaEventElapsedTime(&st.ms_copy, ctx->ev[EV_BLEND], ctx->ev[EV_COPY]);
+        cudaEventElapsedTime(&st.ms_total, ctx->ev[EV_START], ctx->ev[EV_COPY]);
+    }
+    *out = st;
+    return GSB_OK;
+}
+
+void* gsb_device_framebuffer(gsb_context* ctx) { return ctx ? (void*)ctx->last_fb : nullptr; }
+
+int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed)
+{
+    if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const void* src = nullptr; uint64_t need = 0;
+    const uint64_t n = (uint64_t)ctx->last_n, d = ctx->last_d, t = (uint64_t)ctx->last_tiles;
+    switch (which) {
+    case GSB_DBG_KEYS_UNSORTED: src = ctx->keys_unsorted.p; need = ctx->keep_intermediates ? n * 4 : 0; break;
+    case GSB_DBG_ORDER:         src = ctx->vals[ctx->order_buf].p; need = n * 4; break;
+    case GSB_DBG_KEYS_SORTED:   src = ctx->keys[ctx->order_buf].p; need = n * 4; break;
+    case GSB_DBG_RECORDS:       src = ctx->recs.p; need = n * sizeof(Record); break;
+    case GSB_DBG_RECTS:         src = ctx->rects.p; need = n * 8; break;
+    case GSB_DBG_TILE_RANGES:   src = ctx->ranges.p; need = t * 8; break;
+    case GSB_DBG_INSTANCES:     src = ctx->ivals[ctx->inst_buf].p; need = d * 4; break;
+    case GSB_DBG_FRAMEBUFFER:   src = ctx->last_fb; need = (uint64_t)ctx->last_w * ctx->last_h * 16; break;
+    case GSB_DBG_TILE_CONSUMED: src = ctx->tile_consumed.p; need = t * 4; break;
+    default: return fail(GSB_ERR_INVALID, "gsb_debug_fetch: unknown buffer");
+    }
+    if (bytes_needed) *bytes_needed = need;
+    if (dst && need) {
+        if (dst_bytes < need) return fail(GSB_ERR_INVALID, "gsb_debug_fetch: destination too small");
+        if (!src) return fail(GSB_ERR_INVALID, "gsb_debug_fetch: buffer not available");
+        CU(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    }
+    return GSB_OK;
+}
+
+int gsb_debug_sort_pairs(gsb_context* ctx, const uint32_t* keys, const uint32_t* vals, uint64_t n,
+                         int begin_bit, int end_bit, uint32_t* keys_out, uint32_t* vals_out)
+{
+    if (!ctx || (n && (!keys || !vals || !keys_out || !vals_out))) return fail(GSB_ERR_INVALID, "NULL argument");
+    if (begin_bit < 0 || end_bit > 32 || end_bit < begin_bit) return fail(GSB_ERR_INVALID, "bad bit range");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf k[2], v[2], scr;
+    for (int b = 0; b < 2; ++b) { CU(k[b].ensure(n * 4 + 16)); CU(v[b].ensure(n * 4 + 16)); }
+    CU(scr.ensure(sort_scratch_bytes(n)));
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(k[0].p, keys, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(v[0].p, vals, n * 4, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+    int r = radix_sort_pairs(k[0].as<uint32_t>(), v[0].as<uint32_t>(), k[1].as<uint32_t>(), v[1].as<uint32_t>(), n,
+                             begin_bit, end_bit, scr.p, s, &launches);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keys_out, k[r].p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(vals_out, v[r].p, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return GSB_OK;
+}
+
+int gsb_debug_exclusive_scan(gsb_context* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* total)
+{
+    if (!ctx || (n && (!in || !out))) return fail(GSB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf a, b, scr, tot;
+    CU(a.ensure(n * 4 + 16)); CU(b.ensure(n * 4 + 16)); CU(scr.ensure(scan_scratch_bytes(n))); CU(tot.ensure(16));
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(a.p, in, n * 4, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+    exclusive_scan_u32(a.as<uint32_t>(), b.as<uint32_t>(), n, scr.p, tot.as<unsigned long long>(), s, &launches);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, b.p, n * 4, cudaMemcpyDeviceToHost, s));
+    unsigned long long t = 0;
+    CU(cudaMemcpyAsync(&t, tot.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (total) *total = t;
+    return GSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+/* gsplat_b200.h — C ABI of libgsplat_b200.so: the B200-native replacement for the
+ * splat -> framebuffer hot path of rubendhz/houdini-gsplat-renderer (plugin v1.4.1).
+ *
+ * Every entry point below replaces one member of the reference's `GSplatRenderer` singleton
+ * (reference paths relative to /root/reference/gsplat_plugin); the HDK shim keeps the reference's
+ * class names and forwards 1:1 (INTEGRATION.md shows the binding).  Plain pointers and sizes only:
+ * no C++/torch types cross this boundary, nothing throws, every call returns a status code and
+ * leaves a message for gsb_last_error().  One caller thread per context (the reference is not
+ * thread-safe either, include/GSplatRenderer.h:29-32); one context per GPU / process.
+ *
+ * Conventions: matrices are 16 floats, column-major, column-vector convention (OpenGL), i.e.
+ * exactly the glH_* builtins the reference's GLSL reads (shaders/GSplatShaderSource.h:153-159).
+ * Framebuffers are RGBA32F, premultiplied alpha, row 0 = bottom scanline (GL texture order).
+ * Half-precision inputs are IEEE binary16 bit patterns in uint16_t (UT_Vector3H / fpreal16).
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSB_API __attribute__((visibility("default")))
+#else
+#define GSB_API
+#endif
+
+#define GSB_ABI_VERSION 1
+#define GSB_TILE 16                       /* screen tile edge in pixels */
+#define GSB_REFERENCE_SPLAT_CAP 8388607   /* GSPLAT_COUNT_MAX - 1, include/GSplatRenderer.h:26, src/GSplatRenderer.C:336 */
+#define GSB_ID_MAX 128                    /* bytes for a registry id string incl. NUL */
+
+typedef struct gsb_context gsb_context;
+
+enum gsb_status {
+    GSB_OK = 0,
+    GSB_ERR_INVALID = 1,     /* bad argument */
+    GSB_ERR_CUDA = 2,        /* CUDA runtime error (message in gsb_last_error) */
+    GSB_ERR_NOMEM = 3,
+    GSB_ERR_NOT_FOUND = 4,   /* unknown registry id */
+    GSB_ERR_LIMIT = 5        /* more than 2^31 tile instances, screen > 65535 px, ... */
+};
+
+/* Identity of one GSplat primitive, the fields the reference hashes into its registry id
+ * "<gdp ptr hex>__<vtx0>__<v0>_<v1>_<v2>_<v3>" (src/GSplatRenderer.C:241-243). */
+typedef struct gsb_prim_key {
+    uint64_t gdp;            /* GU_Detail pointer value */
+    int64_t  vtx0;           /* GA_Offset of the prim's first vertex */
+    int64_t  version[4];     /* RE_CacheVersion elements 0..3 */
+} gsb_prim_key;
+
+/* Per-redraw inputs the reference reads from RE_Render and the glH_* uniforms
+ * (src/GSplatRenderer.C:558-562; shaders/GSplatShaderSource.h:153-159). */
+typedef struct gsb_frame {
+    float   view[16];        /* glH_ViewMatrix      (also r->getMatrix(), R.C:558) */
+    float   proj[16];        /* glH_ProjectMatrix   */
+    float   object[16];      /* glH_ObjectMatrix    */
+    float   inv_object[16];  /* glH_InvObjectMatrix */
+    float   obj_view[16];    /* glH_ObjViewMatrix   */
+    int32_t width, height;   /* glH_ScreenSize      */
+    int32_t is_object_level; /* DM_SceneHookData::disp_options->isObjectLevel() (DM_GSplatHook.C:34) */
+    int32_t row_rank;        /* multi-GPU: this context blends tile rows ty with ty % row_world == row_rank */
+    int32_t row_world;       /* 1 = whole frame */
+    int32_t reserved[3];
+} gsb_frame;
+
+/* Where the finished frame goes.  All optional; with everything NULL the frame stays in the
+ * library-owned device buffer (gsb_device_framebuffer). */
+typedef struct gsb_target {
+    void*    device_rgba;    /* caller-owned device buffer, width*height*16 bytes; NULL = library buffer */
+    void*    host_rgba;      /* if non-NULL the frame is copied here (D2H inside the call, call returns when done) */
+    uint32_t gl_texture;     /* CUDA<->GL interop target (RGBA32F GL_TEXTURE_2D); must be 0 in builds without GL */
+    uint32_t flags;          /* reserved, 0 */
+} gsb_target;
+
+typedef struct gsb_stats {
+    int64_t n_submitted;     /* N: splats in the packed active set */
+    int64_t n_visible;       /* V: survive cull */
+    int64_t n_instances;     /* D: tile instances emitted */
+    int64_t n_consumed;      /* D_c: instances traversed before every pixel of their tile saturated */
+    int32_t rendered;        /* 1 if the last gsb_render drew, 0 if it early-returned like R.C:536-549 */
+    int32_t repacked;        /* 1 if the last gsb_generate_render_geometry rebuilt the packed set */
+    int32_t sh_order_used;   /* GSplatShOrder actually bound (0 if no SH data, R.C:623,628) */
+    int32_t width, height;
+    int32_t tiles_x, tiles_y;
+    int32_t launches;        /* kernels launched by the last gsb_render */
+    float   camera[3];       /* WorldSpaceCameraPos used for keys and SH */
+    float   origin[3];       /* GSplatOrigin (mean of barycentres, R.C:403-418) */
+    /* device time per stage of the last gsb_render, CUDA events on the library stream;
+     * valid when GSB_OPT_STAGE_TIMING is on (gsb_get_stats synchronises) */
+    float   ms_project, ms_sort, ms_bin, ms_blend, ms_copy, ms_total;
+} gsb_stats;
+
+enum gsb_option {
+    GSB_OPT_SPLAT_CAP = 1,       /* max splats packed; default GSB_REFERENCE_SPLAT_CAP; 0 = unlimited */
+    GSB_OPT_EPS_T = 2,           /* transmittance early-out threshold; default 1e-5; 0 = never stop (reference) */
+    GSB_OPT_STAGE_TIMING = 3,    /* record per-stage CUDA events (default 0) */
+    GSB_OPT_KEEP_INTERMEDIATES = 4 /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
+};
+
+enum gsb_debug_buffer {
+    GSB_DBG_KEYS_UNSORTED = 0,   /* uint32[N]  depth keys in submission order (needs KEEP_INTERMEDIATES) */
+    GSB_DBG_ORDER = 1,           /* uint32[N]  splat index by depth rank (culled splats last) */
+    GSB_DBG_RECORDS = 2,         /* 48 B x N   2-D records by splat index (valid where visible) */
+    GSB_DBG_RECTS = 3,           /* uint16[4] x N  inclusive pixel rectangle x0,x1,y0,y1 (x0>x1 = culled) */
+    GSB_DBG_TILE_RANGES = 4,     /* uint32[2] x tiles  [start,end) into the instance list */
+    GSB_DBG_INSTANCES = 5,       /* uint32[D]  splat index per tile instance, tile-major, depth order inside */
+    GSB_DBG_FRAMEBUFFER = 6,     /* float[4] x W x H */
+    GSB_DBG_KEYS_SORTED = 7,     /* uint32[N] */
+    GSB_DBG_TILE_CONSUMED = 8    /* uint32 x tiles  instances traversed per tile */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+GSB_API int  gsb_abi_version(void);
+GSB_API int  gsb_create(int cuda_device, gsb_context** out);   /* replaces GSplatRenderer::getInstance(), R.h:29-32 */
+GSB_API int  gsb_destroy(gsb_context* ctx);
+GSB_API const char* gsb_last_error(void);                      /* thread-local, never NULL */
+
+/* ---- the reference's public surface, include/GSplatRenderer.h:34-56 ---------------------- */
+
+/* GSplatRenderer::registerUpdate (R.h:34-47, R.C:218-291).  Copies the arrays to the device
+ * immediately (the reference keeps raw pointers, R.C:277-284; this ABI never borrows host memory).
+ * Evicts entries of the same gdp with a different version (R.C:246-265).  shx/shy/shz may be NULL
+ * together (no SH data).  id_out receives the registry id string (GSB_ID_MAX bytes). */
+GSB_API int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat_count,
+                        const float origin[3],
+                        const float*    pos,        /* [count][3]  UT_Vector3Array  */
+                        const uint16_t* cd_h,       /* [count][3]  UT_Vector3HArray */
+                        const float*    alpha,      /* [count]     UT_FloatArray    */
+                        const uint16_t* scale_h,    /* [count][3]  UT_Vector3HArray */
+                        const uint16_t* orient_h,   /* [count][4]  UT_Vector4HArray (x,y,z,w) */
+                        const uint16_t* shx_h,      /* [count][16] MyUT_Matrix4HArray, coeff j at (j/4, j%4) */
+                        const uint16_t* shy_h,
+                        const uint16_t* shz_h,
+                        char* id_out);
+
+GSB_API int gsb_include_in_render_pass(gsb_context* ctx, const char* id);              /* R.C:313-320 */
+GSB_API int gsb_flush_entries_for_matching_detail(gsb_context* ctx, const char* id);   /* R.C:293-311 */
+GSB_API int gsb_generate_render_geometry(gsb_context* ctx);                            /* R.C:322-532 */
+GSB_API int gsb_render(gsb_context* ctx, const gsb_frame* frame, const gsb_target* target); /* R.C:534-658 */
+GSB_API int gsb_post_render(gsb_context* ctx);                                         /* R.C:660-678 */
+GSB_API int gsb_set_rendering_enabled(gsb_context* ctx, int enabled);                  /* R.C:680-683 */
+GSB_API int gsb_set_explicit_camera_pos(gsb_context* ctx, const float pos[3]);         /* R.C:685-689 */
+GSB_API int gsb_set_spherical_harmonics_order(gsb_context* ctx, int sh_order);         /* R.C:691-694 */
+
+/* ---- additions the reference has no equivalent for -------------------------------------- */
+GSB_API int   gsb_set_option(gsb_context* ctx, int option, double value);
+GSB_API int   gsb_get_stats(gsb_context* ctx, gsb_stats* out);
+GSB_API int   gsb_set_stream(gsb_context* ctx, void* cuda_stream);   /* run on a caller stream (NULL = library stream) */
+GSB_API int   gsb_synchronize(gsb_context* ctx);
+GSB_API void* gsb_device_framebuffer(gsb_context* ctx);              /* device pointer of the last library-owned frame */
+GSB_API int   gsb_registry_size(gsb_context* ctx);                   /* live registry entries */
+
+/* Test hooks: copy an intermediate device buffer to the host.  *bytes_needed is always set;
+ * the copy happens only if dst != NULL and dst_bytes >= needed. */
+GSB_API int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed);
+/* Stand-alone exercisers for the device primitives (stable LSD radix sort on [begin_bit,end_bit),
+ * exclusive scan), host buffers in and out. */
+GSB_API int gsb_debug_sort_pairs(gsb_context* ctx, const uint32_t* keys, const uint32_t* vals, uint64_t n,
+                         int begin_bit, int end_bit, uint32_t* keys_out, uint32_t* vals_out);
+GSB_API int gsb_debug_exclusive_scan(gsb_context* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */
