@@ -220,6 +220,7 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
     switch (option) {
     case GSB_OPT_SPLAT_CAP:
         if (value < 0) return fail(GSB_ERR_INVALID, "GSB_OPT_SPLAT_CAP must be >= 0");
+        if (ctx->cap != (int64_t)value) ctx->active_set.clear();     // force a re-pack under the new budget
         ctx->cap = (int64_t)value; return GSB_OK;
     case GSB_OPT_EPS_T:
         if (!(value >= 0.0 && value < 1.0)) return fail(GSB_ERR_INVALID, "GSB_OPT_EPS_T must be in [0,1)");
@@ -472,10 +473,8 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BIN], s));
 
     // K5 blend
-    if (fr->row_world > 1 || true) {
-        // un-owned rows (multi-GPU) and the consumed table start from zero
-        CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));
-    }
+    // the consumed table and (multi-GPU) the rows this rank does not own start from zero
+    CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));
     if (fr->row_world > 1) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));
     launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fc,
                  ctx->tile_consumed.as<uint32_t>(), cnt + 2, s);
