@@ -75,6 +75,14 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to start; do not open the timed region before it is sampling."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
+
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -236,14 +244,17 @@ def run_ours(args):
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms, acc, cnt
 
+    # clocks are sampled (100 ms period) from before the warm-up to the end of the second timed region: the GPU is
+    # under the same load throughout, so short timed regions still get a meaningful median
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler: sampler.wait_first_sample()
     for i in range(max(3, args.warmup)):
         step(i, False)
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, acc, cnt = timed(args.steps, False, True)
-    clocks = sampler.stop() if sampler else None
     for i in range(2):
         step(i, True)
     ms_e2e, _, _ = timed(args.steps, True, False)
+    clocks = sampler.stop() if sampler else None
 
     K = args.steps
     ms_step = ms_dev / K

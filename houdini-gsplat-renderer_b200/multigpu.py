@@ -1,0 +1,35 @@
+"""Screen-tile partition across the GPUs of one box, one process per GPU.
+
+Tiles are independent (a pixel depends only on the ordered list of splats covering it), so the path
+shards by interleaved 16-scanline tile rows: rank g owns tile rows ty with ty % G == g.  Every rank
+holds all splat attributes, culls to its rows, sorts / bins / blends only those, and writes zeros to
+rows it does not own.  The only exchange step is the framebuffer combine below: one NCCL reduction per
+frame onto the display rank (exact, because every pixel is non-zero on exactly one rank: x + 0 == x).
+The reference has no multi-GPU path at all.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TILE = 16
+
+
+def owned_tile_rows(height: int, rank: int, world: int) -> list[int]:
+    tiles_y = (height + TILE - 1) // TILE
+    return [ty for ty in range(tiles_y) if ty % world == rank]
+
+
+def owned_scanlines(height: int, rank: int, world: int) -> np.ndarray:
+    """bool[height]: scanlines (bottom-up, GL order) this rank renders."""
+    y = np.arange(height)
+    return ((y // TILE) % world) == rank
+
+
+def combine_on_root(fb, rank: int, world: int, root: int = 0, group=None):
+    """fb: [H,W,4] float32 torch tensor holding this rank's rows (zeros elsewhere).  After the call the
+    root holds the whole frame.  NCCL on GPUs (NVLink 5 / NVSwitch), gloo in the CPU tests."""
+    if world == 1:
+        return fb
+    import torch.distributed as dist
+    dist.reduce(fb, dst=root, op=dist.ReduceOp.SUM, group=group)
+    return fb
