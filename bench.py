@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="20M_sh3_1080p")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth-chunks", type=int, default=0, help="0 = library default (auto)")
     return ap.parse_args()
 
 
@@ -188,6 +189,7 @@ def run_ours(args):
     r = R.GSplatRenderer(local)
     r.set_option(R.OPT_SPLAT_CAP, 0)          # the reference's 2^23-1 cap lifted for the 20 M configs
     r.set_option(R.OPT_STAGE_TIMING, 1)
+    r.set_option(R.OPT_DEPTH_CHUNKS, args.depth_chunks)
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
     r.setSphericalHarmonicsOrder(sh_order)
@@ -227,7 +229,7 @@ def run_ours(args):
 
     def timed(K, to_host, collect):
         acc = {k: 0.0 for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_copy")}
-        cnt = {"n_visible": 0, "n_instances": 0, "n_consumed": 0, "launches": 0}
+        cnt = {"n_visible": 0, "n_instances": 0, "n_consumed": 0, "launches": 0, "depth_chunks": 0}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -263,7 +265,7 @@ def run_ours(args):
     e2e_val = N / (e2e_ms * 1e-3) / 1e6
 
     if world > 1:   # stage times / counters: sum counters over ranks, max stage times
-        t = torch.tensor([cnt["n_visible"], cnt["n_instances"], cnt["n_consumed"], cnt["launches"]], dtype=torch.float64, device="cuda")
+        t = torch.tensor([cnt[k] for k in cnt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t); cnt = dict(zip(cnt.keys(), [int(x) for x in t.tolist()]))
         t = torch.tensor([acc[k] for k in acc], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX); acc = dict(zip(acc.keys(), t.tolist()))
@@ -296,7 +298,7 @@ def run_ours(args):
                    "camera": "orbit 1 deg/frame" if w["orbit"] else "static", "tile": 16, "eps_t": 1e-5,
                    "splat_cap": "lifted (reference caps at 8388607)", "parallelism": f"tile-row interleave x{world}",
                    "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (N * 128 / 1e9),
-                   "full_pipeline_every_frame": True},
+                   "full_pipeline_every_frame": True, "depth_chunks": cnt["depth_chunks"] / K / world},
         "e2e": {"value": e2e_val, "unit": "Msplats/s", "fps": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 352, "d2h_bytes_per_step": frame_bytes,
                 "note": "gsb_render with host target: gsb_frame in, RGBA32F frame to pinned host memory; geometry resident "

@@ -20,42 +20,47 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
     return t;
 }
 
-__device__ __forceinline__ int owned_rows(const TileRect& t, int rank, int world)
-{
-    if (world <= 1) return t.ty1 - t.ty0 + 1;
-    int c = 0;
-    for (int ty = t.ty0; ty <= t.ty1; ++ty) c += (ty % world) == rank;
-    return c;
-}
-
-// counts[r] = number of owned tiles touched by the splat of depth rank r (0 for culled splats)
+// counts[k] = number of live tiles touched by the splat of depth rank r0 + k (0 for culled splats).
+// A tile is live if this rank owns its row and it is not yet saturated (tile_done, set by the blend
+// of an earlier depth chunk): instances behind a saturated tile can never change a pixel.
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects, int64_t n,
-                  int row_rank, int row_world, uint32_t* __restrict__ counts)
+tile_count_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects, int64_t r0, int64_t n,
+                  int tiles_x, int row_rank, int row_world, const uint32_t* __restrict__ tile_done,
+                  uint32_t* __restrict__ counts)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t i = __ldg(order + r);
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t i = __ldg(order + r0 + k);
     const TileRect t = tile_rect(__ldg(rects + i));
-    counts[r] = t.empty ? 0u : (uint32_t)((t.tx1 - t.tx0 + 1) * owned_rows(t, row_rank, row_world));
+    uint32_t c = 0;
+    if (!t.empty) {
+        for (int ty = t.ty0; ty <= t.ty1; ++ty) {
+            if (row_world > 1 && (ty % row_world) != row_rank) continue;
+            if (tile_done) { for (int tx = t.tx0; tx <= t.tx1; ++tx) c += __ldg(tile_done + ty * tiles_x + tx) == 0u; }
+            else c += (uint32_t)(t.tx1 - t.tx0 + 1);
+        }
+    }
+    counts[k] = c;
 }
 
-// instance (tile id, splat index) pairs at offsets[r] .., rows ascending then columns ascending
+// instance (tile id, splat index) pairs at offsets[k] .., rows ascending then columns ascending
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects,
-            const uint32_t* __restrict__ offsets, int64_t n, int tiles_x, int row_rank, int row_world,
-            uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
+            const uint32_t* __restrict__ offsets, int64_t r0, int64_t n, int tiles_x, int row_rank, int row_world,
+            const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t i = __ldg(order + r);
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t i = __ldg(order + r0 + k);
     const TileRect t = tile_rect(__ldg(rects + i));
     if (t.empty) return;
-    size_t o = offsets[r];
+    size_t o = offsets[k];
     for (int ty = t.ty0; ty <= t.ty1; ++ty) {
         if (row_world > 1 && (ty % row_world) != row_rank) continue;
         for (int tx = t.tx0; tx <= t.tx1; ++tx) {
-            inst_keys[o] = (uint32_t)(ty * tiles_x + tx);
+            const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
+            if (tile_done && __ldg(tile_done + tile) != 0u) continue;
+            inst_keys[o] = tile;
             inst_vals[o] = i;
             ++o;
         }
@@ -75,19 +80,20 @@ tile_range_kernel(const uint32_t* __restrict__ ids, uint64_t d, uint2* __restric
 
 }  // namespace
 
-void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t n, FrameConsts fc,
-                        uint32_t* counts, cudaStream_t s)
+void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t r0, int64_t n, FrameConsts fc,
+                        const uint32_t* tile_done, uint32_t* counts, cudaStream_t s)
 {
     if (n <= 0) return;
-    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, n, fc.row_rank, fc.row_world, counts);
+    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, r0, n, fc.tiles_x, fc.row_rank,
+                                                                 fc.row_world, tile_done, counts);
 }
 
-void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t n,
-                 FrameConsts fc, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
+void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t r0, int64_t n,
+                 FrameConsts fc, const uint32_t* tile_done, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
 {
     if (n <= 0) return;
-    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, offsets, n, fc.tiles_x,
-                                                           fc.row_rank, fc.row_world, inst_keys, inst_vals);
+    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, offsets, r0, n, fc.tiles_x,
+                                                           fc.row_rank, fc.row_world, tile_done, inst_keys, inst_vals);
 }
 
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,

@@ -41,7 +41,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __global__ void __launch_bounds__(BL_THREADS)
 blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
              const uint2* __restrict__ ranges, float4* __restrict__ fb,
-             const __grid_constant__ FrameConsts F,
+             const __grid_constant__ FrameConsts F, const int first, const int last,
+             uint32_t* __restrict__ tile_done,
              uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total)
 {
     __shared__ __align__(16) Record srec[2][BL_BATCH];
@@ -50,6 +51,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     const int tile = blockIdx.x;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
     if (F.row_world > 1 && (ty % F.row_world) != F.row_rank) return;      // CTA-uniform
+    if (!first && tile_done[tile] != 0u) return;                          // saturated and finalised in an earlier chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bx = tx * TILE + (warp & 1) * 8, by = ty * TILE + (warp >> 1) * 4;
@@ -63,11 +65,16 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
     const uint2 range = ranges[tile];
     const uint32_t start = range.x, len = range.y - range.x;
+    if (!first && !last && len == 0u) return;                             // nothing to add in this chunk
     if (tid == 0) s_consumed = 0u;
     __syncthreads();
 
     float Cr = 0.0f, Cg = 0.0f, Cb = 0.0f, T = 1.0f;
-    bool done = !inside;
+    if (!first && inside) {                                               // between chunks fb holds (C, T)
+        const float4 st = fb[(size_t)py * F.width + px];
+        Cr = st.x; Cg = st.y; Cb = st.z; T = st.w;
+    }
+    bool done = !inside || (T < eps);
     bool warp_done = __all_sync(0xffffffffu, done);
     uint32_t warp_pos = 0;                       // instances this warp traversed when it saturated
     const uint32_t nb = (len + BL_BATCH - 1) / BL_BATCH;
@@ -133,12 +140,12 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     }
     cp_async_wait<0>();
 
-    if (inside) fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, 1.0f - T);
-
     if (lane == 0) atomicMax(&s_consumed, warp_done ? warp_pos : len);
-    __syncthreads();
+    const bool tile_saturated = __syncthreads_and(warp_done ? 1 : 0) != 0;   // also orders the atomicMax
+    if (inside) fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, (tile_saturated || last) ? 1.0f - T : T);
     if (tid == 0) {
-        if (tile_consumed) tile_consumed[tile] = s_consumed;
+        if (tile_saturated) tile_done[tile] = 1u;
+        if (tile_consumed) tile_consumed[tile] += s_consumed;
         if (consumed_total && s_consumed) atomicAdd(consumed_total, (unsigned long long)s_consumed);
     }
 }
@@ -146,12 +153,13 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 }  // namespace
 
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
-                  FrameConsts fc, uint32_t* tile_consumed, unsigned long long* consumed_total,
-                  cudaStream_t s)
+                  FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
+                  unsigned long long* consumed_total, cudaStream_t s)
 {
     const int tiles = fc.tiles_x * fc.tiles_y;
     if (tiles <= 0) return;
-    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fc, tile_consumed, consumed_total);
+    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fc, first, last, tile_done,
+                                              tile_consumed, consumed_total);
 }
 
 }  // namespace gsb

@@ -66,16 +66,20 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     unsigned long long* n_visible, cudaStream_t s);
 
 // binning.cu
-void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t n, FrameConsts fc,
-                        uint32_t* counts, cudaStream_t s);
-void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t n,
-                 FrameConsts fc, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
+// ranks [r0, r0+n) of the depth order; tile_done (may be NULL) = per-tile saturation flags
+void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t r0, int64_t n, FrameConsts fc,
+                        const uint32_t* tile_done, uint32_t* counts, cudaStream_t s);
+void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t r0, int64_t n,
+                 FrameConsts fc, const uint32_t* tile_done, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
                         cudaStream_t s);
 
 // blend.cu
+// One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
+// chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done;
+// last: every remaining tile is finalised.
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
-                  FrameConsts fc, uint32_t* tile_consumed, unsigned long long* consumed_total,
-                  cudaStream_t s);
+                  FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
+                  unsigned long long* consumed_total, cudaStream_t s);
 
 }  // namespace gsb

@@ -95,13 +95,14 @@ struct gsb_context {
     int64_t cap = GSB_REFERENCE_SPLAT_CAP;
     float   eps_t = 1e-5f;
     bool    stage_timing = false, keep_intermediates = false;
+    int     depth_chunks = 0;                                 // 0 = auto
 
     // packed render-layout attributes
     DevBuf geomA, geomB, col[6];
     int    planes = 1;
 
     // per-frame device buffers
-    DevBuf keys[2], vals[2], keys_unsorted, recs, rects, counts, ikeys[2], ivals[2], ranges, tile_consumed, fb;
+    DevBuf keys[2], vals[2], keys_unsorted, recs, rects, counts, ikeys[2], ivals[2], ranges, tile_consumed, tile_done, fb;
     DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
     unsigned long long* counters_h = nullptr;        // pinned mirror
     int order_buf = 0, inst_buf = 0;
@@ -109,6 +110,8 @@ struct gsb_context {
     float4* last_fb = nullptr;
 
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t evc[16][3] = {};                     // per depth chunk: start, after binning, after blend
+    int evc_chunks = 0;
     bool ev_valid = false;
     gsb_stats stats{};
 };
@@ -178,6 +181,7 @@ int gsb_create(int cuda_device, gsb_context** out)
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 16; ++i) for (int j = 0; j < 3; ++j) CU(cudaEventCreate(&c->evc[i][j]));
     CU(c->counters.ensure(64));
     CU(cudaMallocHost(&c->counters_h, 64));
     memset(c->counters_h, 0, 64);
@@ -191,6 +195,7 @@ int gsb_destroy(gsb_context* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; ++i) for (int j = 0; j < 3; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
     cudaStream_t s = ctx->own_stream;
     delete ctx;
@@ -227,6 +232,9 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
         ctx->eps_t = (float)value; return GSB_OK;
     case GSB_OPT_STAGE_TIMING: ctx->stage_timing = value != 0; return GSB_OK;
     case GSB_OPT_KEEP_INTERMEDIATES: ctx->keep_intermediates = value != 0; return GSB_OK;
+    case GSB_OPT_DEPTH_CHUNKS:
+        if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_DEPTH_CHUNKS must be 0 (auto) .. 16");
+        ctx->depth_chunks = (int)value; return GSB_OK;
     default: return fail(GSB_ERR_INVALID, "unknown option");
     }
 }
@@ -422,6 +430,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     CU(ctx->recs.ensure(N * sizeof(Record))); CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16));
     CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N))); CU(ctx->scan_scratch.ensure(scan_scratch_bytes(N)));
     CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
+    CU(ctx->tile_done.ensure((size_t)num_tiles * 4));
     if (ctx->keep_intermediates) CU(ctx->keys_unsorted.ensure(N * 4));
     float4* fb = nullptr;
     const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
@@ -451,35 +460,55 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const uint32_t* order = ctx->vals[ctx->order_buf].as<uint32_t>();
     if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
 
-    // K4 binning: counts -> scan -> (D to host) -> emit -> stable tile partition -> ranges
-    launch_tile_counts(order, ctx->rects.as<uint2>(), n, fc, ctx->counts.as<uint32_t>(), s);
-    exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), N, ctx->scan_scratch.p, cnt + 1, s, &st.launches);
-    st.launches += 1;
-    CU(cudaMemcpyAsync(ctx->counters_h, cnt, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const uint64_t V = ctx->counters_h[0], D = ctx->counters_h[1];
-    if (D > 0x7fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^31-1 tile instances in one frame");
-    for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
-    CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)D)));
-    launch_emit(order, ctx->rects.as<uint2>(), ctx->counts.as<uint32_t>(), n, fc,
-                ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
-    st.launches += 1;
+    // K4 + K5, in depth chunks.  Ranks [r0, r1) of the global depth order are binned and blended, tiles whose pixels
+    // all saturated are flagged, and later (deeper) chunks no longer emit instances into flagged tiles.  The per-pixel
+    // sequence of blended instances is unchanged, so the frame is bit-identical to the single-chunk result.
+    uint32_t* tile_done = ctx->tile_done.as<uint32_t>();
+    CU(cudaMemsetAsync(tile_done, 0, (size_t)num_tiles * 4, s));
+    CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));     // accumulates over chunks
+    if (fr->row_world > 1) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));             // rows this rank does not own stay zero
+    int nchunks = ctx->depth_chunks;
+    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 5 : 1;                // auto
+    nchunks = std::min(nchunks, 16);
+    // geometric boundaries: the first chunk is N / 2^(nchunks), every further chunk doubles the covered depth range
+    int64_t bounds[17]; bounds[0] = 0;
+    for (int c = 1; c <= nchunks; ++c) {
+        bounds[c] = (c == nchunks) ? n : std::max<int64_t>(1, (int64_t)(((double)n * (double)((1ll << c) - 1)) / (double)(1ll << nchunks)));
+        bounds[c] = std::min(bounds[c], n);
+    }
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
-    ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
-                                     ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
-                                     ctx->sort_scratch.p, s, &st.launches);
-    launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
-    st.launches += (D ? 1 : 0);
-    if (tm) CU(cudaEventRecord(ctx->ev[EV_BIN], s));
-
-    // K5 blend
-    // the consumed table and (multi-GPU) the rows this rank does not own start from zero
-    CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));
-    if (fr->row_world > 1) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));
-    launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fc,
-                 ctx->tile_consumed.as<uint32_t>(), cnt + 2, s);
-    st.launches += 1;
+    uint64_t D_total = 0, V = 0, D = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t r0 = bounds[c], cn = bounds[c + 1] - bounds[c];
+        const bool first = (c == 0), last = (c == nchunks - 1);
+        if (tm) CU(cudaEventRecord(ctx->evc[c][0], s));
+        launch_tile_counts(order, ctx->rects.as<uint2>(), r0, cn, fc, first ? nullptr : tile_done, ctx->counts.as<uint32_t>(), s);
+        exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), (size_t)cn, ctx->scan_scratch.p, cnt + 1, s, &st.launches);
+        st.launches += 1;
+        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        V = ctx->counters_h[0]; D = ctx->counters_h[1];
+        if (D > 0x7fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^31-1 tile instances in one depth chunk");
+        D_total += D;
+        for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
+        CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)D)));
+        launch_emit(order, ctx->rects.as<uint2>(), ctx->counts.as<uint32_t>(), r0, cn, fc, first ? nullptr : tile_done,
+                    ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
+        st.launches += 1;
+        ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
+                                         ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
+                                         ctx->sort_scratch.p, s, &st.launches);
+        launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
+        st.launches += (D ? 1 : 0);
+        if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
+        launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fc,
+                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 2, s);
+        st.launches += 1;
+        if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+    }
     CU(cudaGetLastError());
+    ctx->evc_chunks = nchunks;
+    D = D_total;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
     CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 8, cudaMemcpyDeviceToHost, s));
 
@@ -492,6 +521,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
 
     ctx->last_n = n; ctx->last_d = D; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
     ctx->last_fb = fb;
+    st.depth_chunks = nchunks;
     st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D;
     st.sh_order_used = fc.sh_order; st.width = fr->width; st.height = fr->height;
     st.tiles_x = fc.tiles_x; st.tiles_y = fc.tiles_y;
@@ -525,8 +555,11 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
     if (st.rendered && ctx->ev_valid) {
         cudaEventElapsedTime(&st.ms_project, ctx->ev[EV_START], ctx->ev[EV_PROJECT]);
         cudaEventElapsedTime(&st.ms_sort, ctx->ev[EV_PROJECT], ctx->ev[EV_SORT]);
-        cudaEventElapsedTime(&st.ms_bin, ctx->ev[EV_SORT], ctx->ev[EV_BIN]);
-        cudaEventElapsedTime(&st.ms_blend, ctx->ev[EV_BIN], ctx->ev[EV_BLEND]);
+        for (int c = 0; c < ctx->evc_chunks; ++c) {                        // summed over depth chunks
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ctx->evc[c][0], ctx->evc[c][1]); cudaEventElapsedTime(&b, ctx->evc[c][1], ctx->evc[c][2]);
+            st.ms_bin += a; st.ms_blend += b;
+        }
         cudaEventElapsedTime(&st.ms_copy, ctx->ev[EV_BLEND], ctx->ev[EV_COPY]);
         cudaEventElapsedTime(&st.ms_total, ctx->ev[EV_START], ctx->ev[EV_COPY]);
     }

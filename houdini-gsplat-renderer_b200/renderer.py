@@ -19,7 +19,7 @@ LIB_PATH = HERE / "libgsplat_b200.so"
 ID_MAX = 128
 REFERENCE_SPLAT_CAP = 8388607
 
-OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES = 1, 2, 3, 4
+OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS = 1, 2, 3, 4, 5
 (DBG_KEYS_UNSORTED, DBG_ORDER, DBG_RECORDS, DBG_RECTS, DBG_TILE_RANGES, DBG_INSTANCES,
  DBG_FRAMEBUFFER, DBG_KEYS_SORTED, DBG_TILE_CONSUMED) = range(9)
 
@@ -62,6 +62,7 @@ class StatsC(C.Structure):
                 ("n_consumed", C.c_int64), ("rendered", C.c_int32), ("repacked", C.c_int32),
                 ("sh_order_used", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("launches", C.c_int32),
+                ("depth_chunks", C.c_int32), ("reserved0", C.c_int32),
                 ("camera", C.c_float * 3), ("origin", C.c_float * 3),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float),
                 ("ms_blend", C.c_float), ("ms_copy", C.c_float), ("ms_total", C.c_float)]

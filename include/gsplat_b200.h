@@ -80,7 +80,7 @@ typedef struct gsb_target {
 typedef struct gsb_stats {
     int64_t n_submitted;     /* N: splats in the packed active set */
     int64_t n_visible;       /* V: survive cull */
-    int64_t n_instances;     /* D: tile instances emitted */
+    int64_t n_instances;     /* D: tile instances emitted (summed over depth chunks; saturated tiles receive none) */
     int64_t n_consumed;      /* D_c: instances traversed before every pixel of their tile saturated */
     int32_t rendered;        /* 1 if the last gsb_render drew, 0 if it early-returned like R.C:536-549 */
     int32_t repacked;        /* 1 if the last gsb_generate_render_geometry rebuilt the packed set */
@@ -88,6 +88,8 @@ typedef struct gsb_stats {
     int32_t width, height;
     int32_t tiles_x, tiles_y;
     int32_t launches;        /* kernels launched by the last gsb_render */
+    int32_t depth_chunks;    /* depth chunks the last frame was binned/blended in */
+    int32_t reserved0;
     float   camera[3];       /* WorldSpaceCameraPos used for keys and SH */
     float   origin[3];       /* GSplatOrigin (mean of barycentres, R.C:403-418) */
     /* device time per stage of the last gsb_render, CUDA events on the library stream;
@@ -99,7 +101,9 @@ enum gsb_option {
     GSB_OPT_SPLAT_CAP = 1,       /* max splats packed; default GSB_REFERENCE_SPLAT_CAP; 0 = unlimited */
     GSB_OPT_EPS_T = 2,           /* transmittance early-out threshold; default 1e-5; 0 = never stop (reference) */
     GSB_OPT_STAGE_TIMING = 3,    /* record per-stage CUDA events (default 0) */
-    GSB_OPT_KEEP_INTERMEDIATES = 4 /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
+    GSB_OPT_KEEP_INTERMEDIATES = 4, /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
+    GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
+                                    chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };
 
 enum gsb_debug_buffer {
@@ -107,8 +111,8 @@ enum gsb_debug_buffer {
     GSB_DBG_ORDER = 1,           /* uint32[N]  splat index by depth rank (culled splats last) */
     GSB_DBG_RECORDS = 2,         /* 48 B x N   2-D records by splat index (valid where visible) */
     GSB_DBG_RECTS = 3,           /* uint16[4] x N  inclusive pixel rectangle x0,x1,y0,y1 (x0>x1 = culled) */
-    GSB_DBG_TILE_RANGES = 4,     /* uint32[2] x tiles  [start,end) into the instance list */
-    GSB_DBG_INSTANCES = 5,       /* uint32[D]  splat index per tile instance, tile-major, depth order inside */
+    GSB_DBG_TILE_RANGES = 4,     /* uint32[2] x tiles  [start,end) into the instance list (last depth chunk) */
+    GSB_DBG_INSTANCES = 5,       /* uint32[D]  splat index per tile instance, tile-major, depth order inside (last chunk) */
     GSB_DBG_FRAMEBUFFER = 6,     /* float[4] x W x H */
     GSB_DBG_KEYS_SORTED = 7,     /* uint32[N] */
     GSB_DBG_TILE_CONSUMED = 8    /* uint32 x tiles  instances traversed per tile */

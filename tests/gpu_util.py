@@ -5,11 +5,12 @@ from houdini_gsplat_renderer_b200 import renderer as R
 
 
 def gpu_pipeline(cloud, frame, sh_order, eps_t=1e-5, row_rank=0, row_world=1, cap=0, renderer=None,
-                 explicit_cam=None, origin=None):
+                 explicit_cam=None, origin=None, depth_chunks=1):
     r = renderer or R.GSplatRenderer(0)
     r.set_option(R.OPT_KEEP_INTERMEDIATES, 1)
     r.set_option(R.OPT_SPLAT_CAP, cap)
     r.set_option(R.OPT_EPS_T, eps_t)
+    r.set_option(R.OPT_DEPTH_CHUNKS, depth_chunks)     # 1 = single pass: the fetched tile lists are the full lists
     rid = r.registerUpdate(0x7f00dead0000, (1, 2, 3, 4), 0, cloud, origin=origin)
     r.includeInRenderPass(rid)
     r.setSphericalHarmonicsOrder(sh_order)

@@ -97,6 +97,31 @@ def test_tile_row_partition_reassembles_bit_exactly(oracle, scene):
     assert np.array_equal(acc, full["rgba"])
 
 
+@pytest.mark.parametrize("chunks", [2, 5, 16])
+def test_depth_chunks_leave_the_frame_bit_identical(oracle, scene, chunks):
+    """Depth-chunked binning drops instances behind saturated tiles; the per-pixel sequence of blended instances is
+    unchanged, so frame, per-tile consumed counts and D_c equal the single-pass result bit for bit (and the oracle)."""
+    O, S = oracle, scene
+    cl = S.make_cloud(150_000, 404, sh=True, scale_mult=2.5)
+    fr, F = _frame(O, S, cl, 488, 270, 52.0, 3)
+    one = gpu_pipeline(cl, fr, 3, depth_chunks=1)
+    many = gpu_pipeline(cl, fr, 3, depth_chunks=chunks)
+    assert many["stats"]["depth_chunks"] == chunks
+    assert np.array_equal(one["rgba"], many["rgba"])
+    assert np.array_equal(one["consumed"], many["consumed"])
+    assert one["stats"]["n_consumed"] == many["stats"]["n_consumed"]
+    assert many["stats"]["n_consumed"] <= many["stats"]["n_instances"] < one["stats"]["n_instances"]
+    o = O.pipeline(F, cl)
+    assert np.abs(many["rgba"] - o["rgba"]).max() <= 2e-5
+    # also with tile-row sharding and without early-out
+    a = gpu_pipeline(cl, fr, 3, depth_chunks=chunks, row_rank=1, row_world=3)
+    b = gpu_pipeline(cl, fr, 3, depth_chunks=1, row_rank=1, row_world=3)
+    assert np.array_equal(a["rgba"], b["rgba"])
+    c = gpu_pipeline(cl, fr, 3, depth_chunks=chunks, eps_t=0.0)
+    d = gpu_pipeline(cl, fr, 3, depth_chunks=1, eps_t=0.0)
+    assert np.array_equal(c["rgba"], d["rgba"]) and c["stats"]["n_instances"] == d["stats"]["n_instances"]
+
+
 def test_full_size_properties_1M_1080p(scene):
     """BASELINE config 2 size (1M splats, SH 0, 1080p) through size-independent properties: sorted keys,
     order is a permutation, tile lists are depth ordered, ranges partition D, alpha in [0,1], idempotence."""
