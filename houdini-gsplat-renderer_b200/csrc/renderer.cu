@@ -508,6 +508,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     }
     CU(cudaGetLastError());
     ctx->evc_chunks = nchunks;
+    const uint64_t D_last = D;      // the instance buffers hold the last chunk only
     D = D_total;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
     CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 8, cudaMemcpyDeviceToHost, s));
@@ -519,7 +520,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
     ctx->ev_valid = tm;
 
-    ctx->last_n = n; ctx->last_d = D; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
+    ctx->last_n = n; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
     ctx->last_fb = fb;
     st.depth_chunks = nchunks;
     st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D;
