@@ -52,9 +52,10 @@ void     exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* s
                             unsigned long long* total_dev, cudaStream_t s, int* launches);
 size_t   sort_scratch_bytes(size_t n);
 // Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit).  Ping-pongs between
-// (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+// (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).  n must be < 2^30.
+// *error_flag (device, may be NULL) is set to 1 if a bounded look-back spin ever times out.
 int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                          int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* launches);
+                          int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches);
 
 // project.cu
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,

@@ -1,4 +1,4 @@
-// radix_sort.cu — stable LSD radix sort of (uint32 key, uint32 value) pairs, sm_100a.
+// radix_sort.cu — stable LSD radix sort of (uint32 key, uint32 value) pairs, sm_100a, onesweep style.
 //
 // Replaces the reference's CPU argsort (tbb::parallel_sort through an index indirection,
 // /root/reference/gsplat_plugin/src/GSplatRenderer.C:206-208) for the depth order, and performs the
@@ -6,84 +6,136 @@
 // (non-negative floats order as uint32).  LSD + stable ranking => ties keep ascending input order,
 // which is the tie rule the spec fixes.
 //
-// Per pass (<= 8 bits): digit histogram per 4096-element block -> exclusive scan of the
-// [digit][block] table -> rank + reorder in shared memory + coalesced scatter.
-// HBM-bound integer work: 4 B (histogram read) + 16 B (scatter read+write) per element per pass.
-// Ranking inside a warp uses match.any so equal digits (the common case for the top byte of a
-// depth key, or the low bits of a tile id) cost one shared-memory update per distinct digit.
+// Structure (after Adinets & Merrill's Onesweep): ONE upfront kernel builds the global digit histogram
+// of every pass from a single read of the keys; then one kernel per <= 8-bit pass ranks a 4096-key tile,
+// obtains the tile's per-digit global offset by decoupled look-back over the preceding tiles, reorders the
+// tile in shared memory and scatters it coalesced.  Per pass each element is read once and written once:
+// 16 B/element/pass + 4 B for the histogram (68 B per element for 4 passes).
+//
+// Safety: tiles take their index from an atomic ticket, so a tile only ever waits on tiles that already
+// started; every spin is bounded and raises an error flag instead of hanging the GPU.
+//
+// Ranking inside a warp needs, per key, the mask of lanes holding the same digit.  match.any does that in one
+// instruction but runs on the ADU pipe at ~2 cycles per DISTINCT value (ncu r01: ADU 97 % busy, 62 cycles per
+// warp for random digits), so the mask is built from one vote.ballot per digit bit instead (<= 8 ballots + LOP3).
 #include "common.cuh"
 
 namespace gsb {
 
 namespace {
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_ITEMS   = 16;
+constexpr int RS_ITEMS   = 8;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096
 constexpr int RS_RADIX   = 256;
+constexpr int RS_MAX_PASSES = 4;
+
+constexpr uint32_t LB_AGG  = 0x40000000u;   // tile aggregate available
+constexpr uint32_t LB_INCL = 0x80000000u;   // inclusive prefix available
+constexpr uint32_t LB_MASK = 0x3FFFFFFFu;   // counts < 2^30
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+struct PassPlan { int shift[RS_MAX_PASSES]; int bits[RS_MAX_PASSES]; int passes; };
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
 }
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p)
+{
+    uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-// element index of item j of this thread: warp-striped inside the warp's contiguous 512-element chunk
+// lanes of the warp whose digit equals this lane's digit (0 for invalid lanes); nbits = digit width of the pass
+__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid, int nbits)
+{
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < nbits) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+    }
+    return valid ? peers : 0u;
+}
+
+// element index of item j of this thread: warp-striped inside the warp's contiguous 256-element chunk
 __device__ __forceinline__ size_t item_index(size_t base, int warp, int lane, int j)
 {
     return base + (size_t)warp * (32 * RS_ITEMS) + (size_t)j * 32 + lane;
 }
 
+// ---- upfront: global digit histograms of all passes, one read of the keys --------------------------------
+// hist layout: [pass][256].  Persistent CTAs, shared-memory REDs, one global RED per non-zero bin per CTA.
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t mask, int nbins,
-               uint32_t* __restrict__ block_hist, unsigned num_blocks)
+os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t cnt[RS_WARPS][RS_RADIX];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0u;
+    __shared__ uint32_t h[RS_MAX_PASSES][RS_RADIX];
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&h[0][0])[i] = 0u;
     __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_TILE;
-    uint32_t k[RS_ITEMS];
+    const size_t stride = (size_t)gridDim.x * RS_THREADS;
+    for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = __ldg(keys + i);
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        size_t idx = item_index(base, warp, lane, j);
-        k[j] = (idx < n) ? __ldg(keys + idx) : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        size_t idx = item_index(base, warp, lane, j);
-        bool valid = idx < n;
-        uint32_t d = (k[j] >> shift) & mask;
-        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
-        if (valid && lane == (__ffs(peers) - 1)) cnt[warp][d] += __popc(peers);   // one lane per distinct digit
-        __syncwarp();
+        for (int p = 0; p < RS_MAX_PASSES; ++p)
+            if (p < plan.passes) atomicAdd(&h[p][(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
     }
     __syncthreads();
-    if ((int)threadIdx.x < nbins) {
-        uint32_t t = 0;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) t += cnt[w][threadIdx.x];
-        block_hist[(size_t)threadIdx.x * num_blocks + blockIdx.x] = t;
+    for (int i = threadIdx.x; i < plan.passes * RS_RADIX; i += RS_THREADS) {
+        const uint32_t c = (&h[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-                  int shift, uint32_t mask, int nbins,
-                  const uint32_t* __restrict__ block_offsets, unsigned num_blocks)
+// exclusive scan of each pass's 256 bins, in place (one CTA of 256 threads per pass)
+__global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t cnt[RS_WARPS][RS_RADIX];     // per-warp digit counts -> warp-exclusive offsets
-    __shared__ uint32_t local_base[RS_RADIX];        // exclusive scan of block digit totals
-    __shared__ uint32_t global_delta[RS_RADIX];      // block_offsets[d][block] - local_base[d]
+    __shared__ uint32_t wtot[RS_RADIX / 32];
+    uint32_t* h = hist + (size_t)blockIdx.x * RS_RADIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = h[threadIdx.x];
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < RS_RADIX / 32; ++w) woff += (w < warp) ? wtot[w] : 0u;
+    h[threadIdx.x] = woff + inc - v;
+}
+
+// ---- one pass ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
+               int shift, int nbits, const uint32_t* __restrict__ digit_base,
+               uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag)
+{
+    __shared__ uint16_t cnt[RS_WARPS][RS_RADIX];     // per-warp digit counts -> warp-exclusive offsets (<= 4096)
+    __shared__ uint32_t local_base[RS_RADIX];        // exclusive scan of the tile's digit totals
+    __shared__ uint32_t global_delta[RS_RADIX];      // global offset of digit d for this tile - local_base[d]
     __shared__ uint32_t wtot[RS_WARPS];
+    __shared__ uint32_t s_tile;
     __shared__ uint32_t sk[RS_TILE];
     __shared__ uint32_t sv[RS_TILE];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbins = 1 << nbits;
+    const uint32_t mask = (uint32_t)nbins - 1u;
     const unsigned lt = lanemask_lt();
-    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0u;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
 
-    const size_t base = (size_t)blockIdx.x * RS_TILE;
+    const size_t base = (size_t)tile * RS_TILE;
     const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
     uint32_t k[RS_ITEMS], v[RS_ITEMS];
     uint16_t rank[RS_ITEMS];
@@ -94,7 +146,6 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
         k[j] = valid ? __ldg(keys_in + idx) : 0u;
         v[j] = valid ? __ldg(vals_in + idx) : 0u;
     }
-    __syncthreads();
 
     // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
 #pragma unroll
@@ -102,22 +153,39 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
         size_t idx = item_index(base, warp, lane, j);
         bool valid = idx < n;
         uint32_t d = (k[j] >> shift) & mask;
-        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0xFFFFFFFFu);
+        unsigned peers = match_digit(d, valid, nbits);
         uint32_t pre = valid ? cnt[warp][d] : 0u;
         __syncwarp();
-        if (valid && lane == (__ffs(peers) - 1)) cnt[warp][d] = pre + __popc(peers);
+        if (valid && lane == (__ffs(peers) - 1)) cnt[warp][d] = (uint16_t)(pre + __popc(peers));
         __syncwarp();
         rank[j] = (uint16_t)(pre + __popc(peers & lt));
     }
     __syncthreads();
 
-    // thread d: exclusive prefix over warps for digit d, block total for d
-    uint32_t total = 0;
+    // thread d: exclusive prefix over warps for digit d, tile total for d; publish, look back
+    uint32_t total = 0, excl = 0;
     if ((int)threadIdx.x < nbins) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = total; total += c; }
+        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
+        uint32_t* mine = lookback + (size_t)tile * RS_RADIX + threadIdx.x;
+        st_volatile(mine, total | (tile == 0 ? LB_INCL : LB_AGG));
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint32_t* p = lookback + (size_t)t * RS_RADIX + threadIdx.x;
+                uint32_t val, spins = 0;
+                while (((val = ld_volatile(p)) & (LB_AGG | LB_INCL)) == 0u) {
+                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); val = LB_INCL; break; }
+                    __nanosleep(20);
+                }
+                excl += val & LB_MASK;
+                if ((val & LB_INCL) || t == 0) break;
+                --t;
+            }
+            st_volatile(mine, ((excl + total) & LB_MASK) | LB_INCL);
+        }
     }
-    // exclusive scan of the 256 digit totals across the block
+    // exclusive scan of the digit totals across the block
     uint32_t inc = total;
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
@@ -129,7 +197,7 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     if ((int)threadIdx.x < nbins) {
         uint32_t lb = woff + inc - total;
         local_base[threadIdx.x] = lb;
-        global_delta[threadIdx.x] = block_offsets[(size_t)threadIdx.x * num_blocks + blockIdx.x] - lb;
+        global_delta[threadIdx.x] = digit_base[threadIdx.x] + excl - lb;
     }
     __syncthreads();
 
@@ -159,37 +227,47 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
 
 static inline size_t rs_blocks(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
+// scratch layout: [hist 4*256 u32][tickets 4 u32][error flag ...][pad to 256 B][lookback passes * blocks * 256 u32]
+static inline size_t os_header_bytes() { return ((RS_MAX_PASSES * RS_RADIX + 8) * sizeof(uint32_t) + 255) & ~size_t(255); }
+
 size_t sort_scratch_bytes(size_t n)
 {
-    size_t table = rs_blocks(n) * RS_RADIX;
-    return ((table * sizeof(uint32_t) + 255) & ~size_t(255)) + scan_scratch_bytes(table) + 256;
+    return os_header_bytes() + (size_t)RS_MAX_PASSES * rs_blocks(n) * RS_RADIX * sizeof(uint32_t) + 256;
 }
 
 int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                     int begin_bit, int end_bit, void* scratch, cudaStream_t s, int* launches)
+                     int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches)
 {
     if (n == 0 || end_bit <= begin_bit) return 0;
     const unsigned nb = (unsigned)rs_blocks(n);
-    uint32_t* table = static_cast<uint32_t*>(scratch);
-    void* scan_scr = static_cast<char*>(scratch) + ((((size_t)nb * RS_RADIX) * sizeof(uint32_t) + 255) & ~size_t(255));
+    PassPlan plan{};
     int bits_left = end_bit - begin_bit;
-    int passes = (bits_left + 7) / 8;
-    int shift = begin_bit, cur = 0;
+    plan.passes = (bits_left + 7) / 8;
+    int shift = begin_bit;
+    for (int p = 0; p < plan.passes; ++p) {
+        int b = (bits_left + (plan.passes - p) - 1) / (plan.passes - p);
+        plan.shift[p] = shift; plan.bits[p] = b; shift += b; bits_left -= b;
+    }
+    uint32_t* hist = static_cast<uint32_t*>(scratch);
+    uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
+    if (!error_flag) error_flag = tickets + RS_MAX_PASSES;      // nobody looks: still a valid sink
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + os_header_bytes());
+    const size_t lb_pass = (size_t)nb * RS_RADIX;
+    cudaMemsetAsync(scratch, 0, os_header_bytes() + (size_t)plan.passes * lb_pass * sizeof(uint32_t), s);
+    const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
+    os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n, plan, hist);
+    os_scan_hist_kernel<<<plan.passes, RS_RADIX, 0, s>>>(hist);
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
-    for (int p = 0; p < passes; ++p) {
-        int b = (bits_left + (passes - p) - 1) / (passes - p);
-        int nbins = 1 << b;
-        uint32_t mask = (uint32_t)nbins - 1u;
-        rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(kin, n, shift, mask, nbins, table, nb);
-        if (launches) *launches += 1;
-        exclusive_scan_u32(table, table, (size_t)nbins * nb, scan_scr, nullptr, s, launches);
-        rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, nbins, table, nb);
-        if (launches) *launches += 1;
+    int cur = 0;
+    for (int p = 0; p < plan.passes; ++p) {
+        os_pass_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, plan.shift[p], plan.bits[p],
+                                                 hist + p * RS_RADIX, lookback + (size_t)p * lb_pass, tickets + p, error_flag);
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
-        cur ^= 1; shift += b; bits_left -= b;
+        cur ^= 1;
     }
+    if (launches) *launches += 2 + plan.passes;
     return cur;
 }
 

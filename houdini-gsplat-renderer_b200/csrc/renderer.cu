@@ -248,7 +248,7 @@ int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat
                         const uint16_t* shz_h, char* id_out)
 {
     if (!ctx || !key || !origin) return fail(GSB_ERR_INVALID, "gsb_register_update: NULL argument");
-    if (splat_count < 0 || splat_count > 0x7fffffffLL) return fail(GSB_ERR_INVALID, "gsb_register_update: bad splat_count");
+    if (splat_count < 0 || splat_count > 0x3fffffffLL) return fail(GSB_ERR_INVALID, "gsb_register_update: bad splat_count");
     if (splat_count > 0 && (!pos || !cd_h || !alpha || !scale_h || !orient_h))
         return fail(GSB_ERR_INVALID, "gsb_register_update: NULL attribute array");
     const bool has_sh = shx_h && shy_h && shz_h;
@@ -356,7 +356,7 @@ int gsb_generate_render_geometry(gsb_context* ctx)
     }
     if (!total) return GSB_OK;                             // R.C:360-363
     ctx->splat_count = std::min(total, cap);
-    if (ctx->splat_count > 0x7fffffffLL) return fail(GSB_ERR_LIMIT, "more than 2^31-1 splats in the active set");
+    if (ctx->splat_count > 0x3fffffffLL) return fail(GSB_ERR_LIMIT, "more than 2^30-1 splats in the active set");
     ctx->sh_present = sh_all;
     ctx->planes = sh_all ? 6 : 1;
 
@@ -456,7 +456,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     // K3 global depth sort (32-bit keys, stable)
     ctx->order_buf = radix_sort_pairs(ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(),
                                       ctx->keys[1].as<uint32_t>(), ctx->vals[1].as<uint32_t>(), N, 0, 32,
-                                      ctx->sort_scratch.p, s, &st.launches);
+                                      ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
     const uint32_t* order = ctx->vals[ctx->order_buf].as<uint32_t>();
     if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
 
@@ -488,7 +488,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         CU(cudaMemcpyAsync(ctx->counters_h, cnt, 16, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         V = ctx->counters_h[0]; D = ctx->counters_h[1];
-        if (D > 0x7fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^31-1 tile instances in one depth chunk");
+        if (D > 0x3fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^30-1 tile instances in one depth chunk");
         D_total += D;
         for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
         CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)D)));
@@ -497,7 +497,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         st.launches += 1;
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
-                                         ctx->sort_scratch.p, s, &st.launches);
+                                         ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
@@ -511,7 +511,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const uint64_t D_last = D;      // the instance buffers hold the last chunk only
     D = D_total;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
-    CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
 
     if (target && target->host_rgba) {
         CU(cudaMemcpyAsync(target->host_rgba, fb, fb_bytes, cudaMemcpyDeviceToHost, s));
@@ -552,6 +552,8 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
     CU(cudaStreamSynchronize(ctx->stream));
     gsb_stats& st = ctx->stats;
     if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[2];
+    if (st.rendered && ctx->counters_h[3] != 0ull)
+        return fail(GSB_ERR_CUDA, "radix sort look-back timed out (internal error); the last frame is invalid");
     st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = 0.0f;
     if (st.rendered && ctx->ev_valid) {
         cudaEventElapsedTime(&st.ms_project, ctx->ev[EV_START], ctx->ev[EV_PROJECT]);
@@ -612,7 +614,7 @@ int gsb_debug_sort_pairs(gsb_context* ctx, const uint32_t* keys, const uint32_t*
     CU(cudaMemcpyAsync(v[0].p, vals, n * 4, cudaMemcpyHostToDevice, s));
     int launches = 0;
     int r = radix_sort_pairs(k[0].as<uint32_t>(), v[0].as<uint32_t>(), k[1].as<uint32_t>(), v[1].as<uint32_t>(), n,
-                             begin_bit, end_bit, scr.p, s, &launches);
+                             begin_bit, end_bit, scr.p, nullptr, s, &launches);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(keys_out, k[r].p, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(vals_out, v[r].p, n * 4, cudaMemcpyDeviceToHost, s));
