@@ -276,11 +276,14 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     V, D, Dc = cnt["n_visible"] / K, cnt["n_instances"] / K, cnt["n_consumed"] / K
-    color_bytes = {0: 16, 1: 32, 2: 64, 3: 96}[sh_order]
+    # algorithmic (compulsory) bytes per frame, SURVEY.md §8d formulas; R = 48-byte record; counters from gsb_stats.
+    # N is replicated on every rank (each rank culls all splats), V/D/D_c are summed over ranks.
+    sh_bytes = {0: 0, 1: 18, 2: 48, 3: 90}[sh_order]
+    tile_passes = max(1, -(-max(1, (((W + 15) // 16) * ((H + 15) // 16) - 1).bit_length()) // 8))
     stage_bytes = {
-        "project": N * 32 * world + V * (color_bytes + 4 + 4 + 8 + RECORD_BYTES) + (N * world - V) * 16,
-        "sort": N * world * 4 * (4 + 16 + 0),            # 4 passes x (hist read 4 + scatter read 8 + write 8)
-        "bin": N * world * (4 + 8 + 4) + N * world * 12 + D * 8 + 2 * D * 20 + D * 4,
+        "project": N * world * 30 + V * (6 + sh_bytes) + V * (4 + 4 + RECORD_BYTES + 4),
+        "sort": 68 * V,                                   # 32-bit key + 32-bit payload, 4 passes of 8 bits
+        "bin": V * 8 + D * 8 + tile_passes * D * 16 + ((W + 15) // 16) * ((H + 15) // 16) * 8,
         "blend": Dc * (4 + RECORD_BYTES) + (W * H * 16),
     }
     stage_ms = {"project": acc["ms_project"] / K, "sort": acc["ms_sort"] / K, "bin": acc["ms_bin"] / K, "blend": acc["ms_blend"] / K}

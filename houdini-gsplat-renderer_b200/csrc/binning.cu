@@ -21,17 +21,17 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
 }
 
 // counts[k] = number of live tiles touched by the splat of depth rank r0 + k (0 for culled splats).
+// rects_sorted is in depth order (gathered by the last pass of the depth sort), so this is a coalesced stream.
 // A tile is live if this rank owns its row and it is not yet saturated (tile_done, set by the blend
 // of an earlier depth chunk): instances behind a saturated tile can never change a pixel.
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects, int64_t r0, int64_t n,
+tile_count_kernel(const uint2* __restrict__ rects_sorted, int64_t r0, int64_t n,
                   int tiles_x, int row_rank, int row_world, const uint32_t* __restrict__ tile_done,
                   uint32_t* __restrict__ counts)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t i = __ldg(order + r0 + k);
-    const TileRect t = tile_rect(__ldg(rects + i));
+    const TileRect t = tile_rect(__ldg(rects_sorted + r0 + k));
     uint32_t c = 0;
     if (!t.empty) {
         for (int ty = t.ty0; ty <= t.ty1; ++ty) {
@@ -45,16 +45,19 @@ tile_count_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ 
 
 // instance (tile id, splat index) pairs at offsets[k] .., rows ascending then columns ascending
 __global__ void __launch_bounds__(256)
-emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects,
-            const uint32_t* __restrict__ offsets, int64_t r0, int64_t n, int tiles_x, int row_rank, int row_world,
+emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects_sorted,
+            const uint32_t* __restrict__ offsets, const unsigned long long* __restrict__ total,
+            int64_t r0, int64_t n, int tiles_x, int row_rank, int row_world,
             const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    const uint32_t o0 = offsets[k];
+    const uint32_t o1 = (k + 1 < n) ? offsets[k + 1] : (uint32_t)(*total);
+    if (o1 == o0) return;                                    // culled, or every tile it touches is saturated
     const uint32_t i = __ldg(order + r0 + k);
-    const TileRect t = tile_rect(__ldg(rects + i));
-    if (t.empty) return;
-    size_t o = offsets[k];
+    const TileRect t = tile_rect(__ldg(rects_sorted + r0 + k));
+    size_t o = o0;
     for (int ty = t.ty0; ty <= t.ty1; ++ty) {
         if (row_world > 1 && (ty % row_world) != row_rank) continue;
         for (int tx = t.tx0; tx <= t.tx1; ++tx) {
@@ -80,19 +83,20 @@ tile_range_kernel(const uint32_t* __restrict__ ids, uint64_t d, uint2* __restric
 
 }  // namespace
 
-void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t r0, int64_t n, FrameConsts fc,
+void launch_tile_counts(const uint2* rects_sorted, int64_t r0, int64_t n, FrameConsts fc,
                         const uint32_t* tile_done, uint32_t* counts, cudaStream_t s)
 {
     if (n <= 0) return;
-    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, r0, n, fc.tiles_x, fc.row_rank,
+    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rects_sorted, r0, n, fc.tiles_x, fc.row_rank,
                                                                  fc.row_world, tile_done, counts);
 }
 
-void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t r0, int64_t n,
-                 FrameConsts fc, const uint32_t* tile_done, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
+void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_t* offsets,
+                 const unsigned long long* total, int64_t r0, int64_t n, FrameConsts fc, const uint32_t* tile_done,
+                 uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
 {
     if (n <= 0) return;
-    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects, offsets, r0, n, fc.tiles_x,
+    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects_sorted, offsets, total, r0, n, fc.tiles_x,
                                                            fc.row_rank, fc.row_world, tile_done, inst_keys, inst_vals);
 }
 

@@ -43,7 +43,8 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
              const uint2* __restrict__ ranges, float4* __restrict__ fb,
              const __grid_constant__ FrameConsts F, const int first, const int last,
              uint32_t* __restrict__ tile_done,
-             uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total)
+             uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total,
+             unsigned long long* __restrict__ done_tiles)
 {
     __shared__ __align__(16) Record srec[2][BL_BATCH];
     __shared__ uint32_t s_consumed;
@@ -144,7 +145,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     const bool tile_saturated = __syncthreads_and(warp_done ? 1 : 0) != 0;   // also orders the atomicMax
     if (inside) fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, (tile_saturated || last) ? 1.0f - T : T);
     if (tid == 0) {
-        if (tile_saturated) tile_done[tile] = 1u;
+        if (tile_saturated) { tile_done[tile] = 1u; atomicAdd(done_tiles, 1ull); }
         if (tile_consumed) tile_consumed[tile] += s_consumed;
         if (consumed_total && s_consumed) atomicAdd(consumed_total, (unsigned long long)s_consumed);
     }
@@ -154,12 +155,12 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
-                  unsigned long long* consumed_total, cudaStream_t s)
+                  unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s)
 {
     const int tiles = fc.tiles_x * fc.tiles_y;
     if (tiles <= 0) return;
     blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fc, first, last, tile_done,
-                                              tile_consumed, consumed_total);
+                                              tile_consumed, consumed_total, done_tiles);
 }
 
 }  // namespace gsb

@@ -54,33 +54,42 @@ size_t   sort_scratch_bytes(size_t n);
 // Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit).  Ping-pongs between
 // (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).  n must be < 2^30.
 // *error_flag (device, may be NULL) is set to 1 if a bounded look-back spin ever times out.
+// If gather_src != NULL the last pass also writes gather_dst[sorted position] = gather_src[value] (8-byte items).
 int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                          int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches);
+                          int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
+                          const uint2* gather_src = nullptr, uint2* gather_dst = nullptr,
+                          uint32_t key_min = 0u, uint32_t key_span = 0xFFFFFFFFu);
+// The sort orders by min(key - key_min, key_span) (order-preserving for keys in [key_min, key_min + key_span),
+// everything above collapses onto key_span); pass end_bit = sort_key_bits(key_span) to sort only the bits that vary.
+int      sort_key_bits(uint32_t key_span);
 
 // project.cu
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
                  int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
                  int planes, cudaStream_t s);
+// K1: keys (culled -> KEY_CULLED), vals = splat index, rects (x0>x1 = culled), records, *n_visible += V
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
                     unsigned long long* n_visible, cudaStream_t s);
 
 // binning.cu
-// ranks [r0, r0+n) of the depth order; tile_done (may be NULL) = per-tile saturation flags
-void launch_tile_counts(const uint32_t* order, const uint2* rects, int64_t r0, int64_t n, FrameConsts fc,
+// ranks [r0, r0+n) of the depth order; rects_sorted in depth order; tile_done (may be NULL) = saturation flags
+void launch_tile_counts(const uint2* rects_sorted, int64_t r0, int64_t n, FrameConsts fc,
                         const uint32_t* tile_done, uint32_t* counts, cudaStream_t s);
-void launch_emit(const uint32_t* order, const uint2* rects, const uint32_t* offsets, int64_t r0, int64_t n,
-                 FrameConsts fc, const uint32_t* tile_done, uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
+// offsets = exclusive scan of the tile counts, *total = its grand total (device)
+void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_t* offsets,
+                 const unsigned long long* total, int64_t r0, int64_t n, FrameConsts fc, const uint32_t* tile_done,
+                 uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
                         cudaStream_t s);
 
 // blend.cu
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
 // chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done;
-// last: every remaining tile is finalised.
+// last: every remaining tile is finalised.  *done_tiles counts the tiles flagged so far (early termination).
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
-                  unsigned long long* consumed_total, cudaStream_t s);
+                  unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s);
 
 }  // namespace gsb

@@ -99,6 +99,199 @@ constexpr float SH_C3_0 = -0.5900436f, SH_C3_1 = 2.8906114f, SH_C3_2 = -0.457045
                 SH_C3_3 = 0.3731763f, SH_C3_4 = -0.4570458f, SH_C3_5 = 1.4453057f,
                 SH_C3_6 = -0.5900436f;
 
+// Geometry of one projected splat: everything the record needs except the colour.
+struct Geom {
+    float cx, cy, m00, m01, m10, m11, pmax, hx, hy;
+    int   x0, x1, y0, y1;
+    float psx[3];            // shader-side position (P - origin) + origin
+};
+
+// Centre, cull, covariance chain, eigen axes, discard radius, pixel rectangle.  Returns false if culled.
+// The expression order is the spec; oracle/gsplat_oracle.cpp project_one() is its twin.
+__device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p[3], const float alpha,
+                                             const uint4 gb, Geom& g)
+{
+    if (!(alpha >= 1.0f / 255.0f)) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; g.psx[k] = t + F.origin[k]; }
+    const float* psx = g.psx;
+    float vc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
+    const float fy = -vc[1];
+    float clip[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
+    const float cw = clip[3];
+    if (!(cw > 0.0f)) return false;
+    if (!(clip[2] >= -cw && clip[2] <= cw)) return false;
+    const float ndcx = clip[0] / cw;
+    const float ndcy = (-clip[1]) / cw;
+    const float cx = ((ndcx + 1.0f) * 0.5f) * F.W;
+    const float cy = ((ndcy + 1.0f) * 0.5f) * F.H;
+
+    const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
+    const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
+    float Rt[3][3];
+    Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
+    Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
+    Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float sc[3] = { sx, sy, sz };
+    float Mm[3][3], M2[3][3], S[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            M2[a][b] = (Mm[a][0] * MAT(F.object, b, 0) + Mm[a][1] * MAT(F.object, b, 1)) + Mm[a][2] * MAT(F.object, b, 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            S[a][b] = (M2[0][a] * M2[0][b] + M2[1][a] * M2[1][b]) + M2[2][a] * M2[2][b];
+            S[b][a] = S[a][b];
+        }
+
+    float t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        t[r] = ((MAT(F.view, r, 0) * psx[0] + MAT(F.view, r, 1) * psx[1]) + MAT(F.view, r, 2) * psx[2]) + MAT(F.view, r, 3);
+    const float aspect = MAT(F.proj, 0, 0) / MAT(F.proj, 1, 1);
+    const float tanFovX = 1.0f / MAT(F.proj, 0, 0);
+    const float tanFovY = 1.0f / (MAT(F.proj, 1, 1) * aspect);
+    const float limX = 1.3f * tanFovX, limY = 1.3f * tanFovY;
+    const float tz = t[2];
+    float rx = t[0] / tz; rx = fminf(fmaxf(rx, -limX), limX);
+    float ry = t[1] / tz; ry = fminf(fmaxf(ry, -limY), limY);
+    const float tx = rx * tz, ty = ry * tz;
+    const float focal = (F.W * MAT(F.proj, 0, 0)) / 2.0f;
+    const float j0 = focal / tz;
+    const float tz2 = tz * tz;
+    const float j2x = -((focal * tx) / tz2);
+    const float j2y = -((focal * ty) / tz2);
+    float A0[3], A1[3], B0[3], B1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        A0[k] = j0 * MAT(F.view, 0, k) + j2x * MAT(F.view, 2, k);
+        A1[k] = j0 * MAT(F.view, 1, k) + j2y * MAT(F.view, 2, k);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        B0[k] = (A0[0] * S[0][k] + A0[1] * S[1][k]) + A0[2] * S[2][k];
+        B1[k] = (A1[0] * S[0][k] + A1[1] * S[1][k]) + A1[2] * S[2][k];
+    }
+    const float c00 = (B0[0] * A0[0] + B0[1] * A0[1]) + B0[2] * A0[2];
+    const float c01 = (B0[0] * A1[0] + B0[1] * A1[1]) + B0[2] * A1[2];
+    const float c11 = (B1[0] * A1[0] + B1[1] * A1[1]) + B1[2] * A1[2];
+    const float a = c00 + 0.3f, b = c01, c = c11 + 0.3f;
+
+    const float mid = 0.5f * (a + c);
+    const float hd = (a - c) / 2.0f;
+    const float radius = sqrtf(hd * hd + b * b);
+    const float l1 = mid + radius;
+    const float l2 = fmaxf(mid - radius, 0.1f);
+    const float dvx = b, dvy = l1 - a;
+    const float len = sqrtf(dvx * dvx + dvy * dvy);
+    if (!(len > 0.0f) || !(len <= 3.0e38f)) return false;
+    const float ex = dvx / len, ey = dvy / len;
+    const float s1 = fminf(sqrtf(2.0f * l1), 4096.0f);
+    const float s2 = fminf(sqrtf(2.0f * l2), 4096.0f);
+    if (!(s1 > 0.0f) || !(s2 > 0.0f)) return false;
+    const float u1x = s1 * ex, u1y = s1 * ey;
+    const float u2x = -(s2 * ey), u2y = s2 * ex;
+
+    const float pmax = (float)det_log((double)alpha * 255.0);
+    if (!(pmax >= 0.0f)) return false;
+
+    const float bxh = 2.0f * (fabsf(u1x) + fabsf(u2x));
+    const float byh = 2.0f * (fabsf(u1y) + fabsf(u2y));
+    const float rr = sqrtf(pmax);
+    const float exh = rr * sqrtf(u1x * u1x + u2x * u2x);
+    const float eyh = rr * sqrtf(u1y * u1y + u2y * u2y);
+    float hx = fminf(bxh, exh); hx = hx + (hx * 0.0001f + 0.01f);
+    float hy = fminf(byh, eyh); hy = hy + (hy * 0.0001f + 0.01f);
+    const float x0f = fmaxf(ceilf((cx - hx) - 0.5f), 0.0f);
+    const float x1f = fminf(floorf((cx + hx) - 0.5f), F.W - 1.0f);
+    const float y0f = fmaxf(ceilf((cy - hy) - 0.5f), 0.0f);
+    const float y1f = fminf(floorf((cy + hy) - 0.5f), F.H - 1.0f);
+    if (!(x0f <= x1f) || !(y0f <= y1f)) return false;
+    g.x0 = (int)x0f; g.x1 = (int)x1f; g.y0 = (int)y0f; g.y1 = (int)y1f;
+    if (F.row_world > 1) {
+        bool any = false;
+        for (int tyy = g.y0 / TILE; tyy <= g.y1 / TILE && !any; ++tyy) any = (tyy % F.row_world) == F.row_rank;
+        if (!any) return false;
+    }
+    g.cx = cx; g.cy = cy;
+    g.m00 = ex / s1; g.m01 = ey / s1;
+    g.m10 = (-ey) / s2; g.m11 = ex / s2;
+    g.pmax = pmax; g.hx = hx; g.hy = hy;
+    return true;
+}
+
+// SH -> RGB for splat i (SRC.h:224,244-275; LIB.h:117-179), term order of LIB.h:148-174
+template <int ORDER>
+__device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedSplats& ps, const int64_t i,
+                                             const float psx[3], float rgb[3])
+{
+    const uint4 c0 = __ldg(ps.col[0] + i);
+    rgb[0] = lo_h(c0.x); rgb[1] = hi_h(c0.x); rgb[2] = lo_h(c0.y);
+    if (ORDER > 0) {
+        // 48 halfs: Cd(3) then coefficient j channel ch at 3 + 3j + ch
+        uint32_t w[24];
+        w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
+        constexpr int PLANES = ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6);
+#pragma unroll
+        for (int pl = 1; pl < PLANES; ++pl) {
+            const uint4 cc = __ldg(ps.col[pl] + i);
+            w[4 * pl] = cc.x; w[4 * pl + 1] = cc.y; w[4 * pl + 2] = cc.z; w[4 * pl + 3] = cc.w;
+        }
+        const float wv[3] = { psx[0] - F.cam[0], psx[1] - F.cam[1], psx[2] - F.cam[2] };
+        float ov[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            ov[r] = (MAT(F.inv_object, r, 0) * wv[0] + MAT(F.inv_object, r, 1) * wv[1]) + MAT(F.inv_object, r, 2) * wv[2];
+        const float dl = sqrtf((ov[0] * ov[0] + ov[1] * ov[1]) + ov[2] * ov[2]);
+        const float x = ov[0] / dl, y = ov[1] / dl, z = ov[2] / dl;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            auto SH = [&](int j) -> float {      // coefficient j (0-based: sh1 = j 0)
+                const int hidx = 3 + 3 * j + ch;
+                const uint32_t word = w[hidx >> 1];
+                return (hidx & 1) ? hi_h(word) : lo_h(word);
+            };
+            float res = rgb[ch];
+            res = res + SH_C1 * (((-SH(0)) * y + SH(1) * z) - SH(2) * x);
+            if (ORDER >= 2) {
+                float t2 = (SH_C2_0 * xy) * SH(3);
+                t2 = t2 + (SH_C2_1 * yz) * SH(4);
+                t2 = t2 + (SH_C2_2 * ((2.0f * zz - xx) - yy)) * SH(5);
+                t2 = t2 + (SH_C2_3 * xz) * SH(6);
+                t2 = t2 + (SH_C2_4 * (xx - yy)) * SH(7);
+                res = res + t2;
+                if (ORDER >= 3) {
+                    float t3 = ((SH_C3_0 * y) * (3.0f * xx - yy)) * SH(8);
+                    t3 = t3 + ((SH_C3_1 * xy) * z) * SH(9);
+                    t3 = t3 + ((SH_C3_2 * y) * ((4.0f * zz - xx) - yy)) * SH(10);
+                    t3 = t3 + ((SH_C3_3 * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy)) * SH(11);
+                    t3 = t3 + ((SH_C3_4 * x) * ((4.0f * zz - xx) - yy)) * SH(12);
+                    t3 = t3 + ((SH_C3_5 * z) * (xx - yy)) * SH(13);
+                    t3 = t3 + ((SH_C3_6 * x) * (xx - 3.0f * yy)) * SH(14);
+                    res = res + t3;
+                }
+            }
+            rgb[ch] = fmaxf(res, 0.0f);
+        }
+    }
+}
+
+// ---- K1: one thread per submitted splat.  Everything is a coalesced stream (random-sector gathers of a lazy
+// per-emitted-splat variant measured slower on B200: r01, 3.75 vs 3.42 ms/frame).
 template <int ORDER>
 __global__ void __launch_bounds__(256)
 project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps, int64_t n,
@@ -111,208 +304,30 @@ project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ Pa
         const float4 ga = __ldg(ps.geomA + i);
         const uint4  gb = __ldg(ps.geomB + i);
         const float p[3] = { ga.x, ga.y, ga.z };
-        const float alpha = ga.w;
+        Geom g;
+        vis = project_geom(F, p, ga.w, gb, g);
         uint32_t key = KEY_CULLED;
         uint2 rect = make_uint2(1u, 1u);          // x0=1,x1=0,y0=1,y1=0 : empty
-        Record rec;
-        do {
-            if (!(alpha >= 1.0f / 255.0f)) break;
-            float psx[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; psx[k] = t + F.origin[k]; }
-            float vc[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
-            const float fy = -vc[1];
-            float clip[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
-            const float cw = clip[3];
-            if (!(cw > 0.0f)) break;
-            if (!(clip[2] >= -cw && clip[2] <= cw)) break;
-            const float ndcx = clip[0] / cw;
-            const float ndcy = (-clip[1]) / cw;
-            const float cx = ((ndcx + 1.0f) * 0.5f) * F.W;
-            const float cy = ((ndcy + 1.0f) * 0.5f) * F.H;
-
-            const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
-            const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
-            float Rt[3][3];
-            Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
-            Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
-            Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
-            const float sc[3] = { sx, sy, sz };
-            float Mm[3][3], M2[3][3], S[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b)
-                    M2[a][b] = (Mm[a][0] * MAT(F.object, b, 0) + Mm[a][1] * MAT(F.object, b, 1)) + Mm[a][2] * MAT(F.object, b, 2);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = a; b < 3; ++b) {
-                    S[a][b] = (M2[0][a] * M2[0][b] + M2[1][a] * M2[1][b]) + M2[2][a] * M2[2][b];
-                    S[b][a] = S[a][b];
-                }
-
-            float t[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                t[r] = ((MAT(F.view, r, 0) * psx[0] + MAT(F.view, r, 1) * psx[1]) + MAT(F.view, r, 2) * psx[2]) + MAT(F.view, r, 3);
-            const float aspect = MAT(F.proj, 0, 0) / MAT(F.proj, 1, 1);
-            const float tanFovX = 1.0f / MAT(F.proj, 0, 0);
-            const float tanFovY = 1.0f / (MAT(F.proj, 1, 1) * aspect);
-            const float limX = 1.3f * tanFovX, limY = 1.3f * tanFovY;
-            const float tz = t[2];
-            float rx = t[0] / tz; rx = fminf(fmaxf(rx, -limX), limX);
-            float ry = t[1] / tz; ry = fminf(fmaxf(ry, -limY), limY);
-            const float tx = rx * tz, ty = ry * tz;
-            const float focal = (F.W * MAT(F.proj, 0, 0)) / 2.0f;
-            const float j0 = focal / tz;
-            const float tz2 = tz * tz;
-            const float j2x = -((focal * tx) / tz2);
-            const float j2y = -((focal * ty) / tz2);
-            float A0[3], A1[3], B0[3], B1[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                A0[k] = j0 * MAT(F.view, 0, k) + j2x * MAT(F.view, 2, k);
-                A1[k] = j0 * MAT(F.view, 1, k) + j2y * MAT(F.view, 2, k);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                B0[k] = (A0[0] * S[0][k] + A0[1] * S[1][k]) + A0[2] * S[2][k];
-                B1[k] = (A1[0] * S[0][k] + A1[1] * S[1][k]) + A1[2] * S[2][k];
-            }
-            const float c00 = (B0[0] * A0[0] + B0[1] * A0[1]) + B0[2] * A0[2];
-            const float c01 = (B0[0] * A1[0] + B0[1] * A1[1]) + B0[2] * A1[2];
-            const float c11 = (B1[0] * A1[0] + B1[1] * A1[1]) + B1[2] * A1[2];
-            const float a = c00 + 0.3f, b = c01, c = c11 + 0.3f;
-
-            const float mid = 0.5f * (a + c);
-            const float hd = (a - c) / 2.0f;
-            const float radius = sqrtf(hd * hd + b * b);
-            const float l1 = mid + radius;
-            const float l2 = fmaxf(mid - radius, 0.1f);
-            const float dvx = b, dvy = l1 - a;
-            const float len = sqrtf(dvx * dvx + dvy * dvy);
-            if (!(len > 0.0f) || !(len <= 3.0e38f)) break;
-            const float ex = dvx / len, ey = dvy / len;
-            const float s1 = fminf(sqrtf(2.0f * l1), 4096.0f);
-            const float s2 = fminf(sqrtf(2.0f * l2), 4096.0f);
-            if (!(s1 > 0.0f) || !(s2 > 0.0f)) break;
-            const float u1x = s1 * ex, u1y = s1 * ey;
-            const float u2x = -(s2 * ey), u2y = s2 * ex;
-
-            const float pmax = (float)det_log((double)alpha * 255.0);
-            if (!(pmax >= 0.0f)) break;
-
-            const float bxh = 2.0f * (fabsf(u1x) + fabsf(u2x));
-            const float byh = 2.0f * (fabsf(u1y) + fabsf(u2y));
-            const float rr = sqrtf(pmax);
-            const float exh = rr * sqrtf(u1x * u1x + u2x * u2x);
-            const float eyh = rr * sqrtf(u1y * u1y + u2y * u2y);
-            float hx = fminf(bxh, exh); hx = hx + (hx * 0.0001f + 0.01f);
-            float hy = fminf(byh, eyh); hy = hy + (hy * 0.0001f + 0.01f);
-            const float x0f = fmaxf(ceilf((cx - hx) - 0.5f), 0.0f);
-            const float x1f = fminf(floorf((cx + hx) - 0.5f), F.W - 1.0f);
-            const float y0f = fmaxf(ceilf((cy - hy) - 0.5f), 0.0f);
-            const float y1f = fminf(floorf((cy + hy) - 0.5f), F.H - 1.0f);
-            if (!(x0f <= x1f) || !(y0f <= y1f)) break;
-            const int x0 = (int)x0f, x1 = (int)x1f, y0 = (int)y0f, y1 = (int)y1f;
-            if (F.row_world > 1) {
-                bool any = false;
-                for (int tyy = y0 / TILE; tyy <= y1 / TILE && !any; ++tyy) any = (tyy % F.row_world) == F.row_rank;
-                if (!any) break;
-            }
-
+        if (vis) {
             float rgb[3];
-            {
-                const uint4 c0 = __ldg(ps.col[0] + i);
-                rgb[0] = lo_h(c0.x); rgb[1] = hi_h(c0.x); rgb[2] = lo_h(c0.y);
-                if (ORDER > 0) {
-                    // 48 halfs: Cd(3) then coefficient j channel ch at 3 + 3j + ch
-                    uint32_t w[24];
-                    w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
-                    constexpr int PLANES = ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6);
-#pragma unroll
-                    for (int pl = 1; pl < PLANES; ++pl) {
-                        const uint4 cc = __ldg(ps.col[pl] + i);
-                        w[4 * pl] = cc.x; w[4 * pl + 1] = cc.y; w[4 * pl + 2] = cc.z; w[4 * pl + 3] = cc.w;
-                    }
-                    const float wv[3] = { psx[0] - F.cam[0], psx[1] - F.cam[1], psx[2] - F.cam[2] };
-                    float ov[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        ov[r] = (MAT(F.inv_object, r, 0) * wv[0] + MAT(F.inv_object, r, 1) * wv[1]) + MAT(F.inv_object, r, 2) * wv[2];
-                    const float dl = sqrtf((ov[0] * ov[0] + ov[1] * ov[1]) + ov[2] * ov[2]);
-                    const float x = ov[0] / dl, y = ov[1] / dl, z = ov[2] / dl;
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        auto SH = [&](int j) -> float {      // coefficient j (0-based: sh1 = j 0)
-                            const int hidx = 3 + 3 * j + ch;
-                            const uint32_t word = w[hidx >> 1];
-                            return (hidx & 1) ? hi_h(word) : lo_h(word);
-                        };
-                        float res = rgb[ch];
-                        res = res + SH_C1 * (((-SH(0)) * y + SH(1) * z) - SH(2) * x);
-                        if (ORDER >= 2) {
-                            float t2 = (SH_C2_0 * xy) * SH(3);
-                            t2 = t2 + (SH_C2_1 * yz) * SH(4);
-                            t2 = t2 + (SH_C2_2 * ((2.0f * zz - xx) - yy)) * SH(5);
-                            t2 = t2 + (SH_C2_3 * xz) * SH(6);
-                            t2 = t2 + (SH_C2_4 * (xx - yy)) * SH(7);
-                            res = res + t2;
-                            if (ORDER >= 3) {
-                                float t3 = ((SH_C3_0 * y) * (3.0f * xx - yy)) * SH(8);
-                                t3 = t3 + ((SH_C3_1 * xy) * z) * SH(9);
-                                t3 = t3 + ((SH_C3_2 * y) * ((4.0f * zz - xx) - yy)) * SH(10);
-                                t3 = t3 + ((SH_C3_3 * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy)) * SH(11);
-                                t3 = t3 + ((SH_C3_4 * x) * ((4.0f * zz - xx) - yy)) * SH(12);
-                                t3 = t3 + ((SH_C3_5 * z) * (xx - yy)) * SH(13);
-                                t3 = t3 + ((SH_C3_6 * x) * (xx - 3.0f * yy)) * SH(14);
-                                res = res + t3;
-                            }
-                        }
-                        rgb[ch] = fmaxf(res, 0.0f);
-                    }
-                }
-            }
-
+            shade_colour<ORDER>(F, ps, i, g.psx, rgb);
             // depth key on the UNMODIFIED position (R.C:196-202, 454, 584)
             const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
             const float d2 = dx * dx + dy * dy + dz * dz;
             key = __float_as_uint(d2);
-            rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
-            rec.cx = cx; rec.cy = cy;
-            rec.m00 = ex / s1; rec.m01 = ey / s1;
-            rec.m10 = (-ey) / s2; rec.m11 = ex / s2;
-            rec.alpha = alpha; rec.pmax = pmax;
-            rec.r = rgb[0]; rec.g = rgb[1]; rec.b = rgb[2];
-            rec.hpack = (uint32_t)__half_as_ushort(__float2half_ru(hx)) |
-                        ((uint32_t)__half_as_ushort(__float2half_ru(hy)) << 16);
-            vis = true;
-        } while (false);
-
+            rect = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
+            const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
+                                   ((uint32_t)__half_as_ushort(__float2half_ru(g.hy)) << 16);
+            float4* out = reinterpret_cast<float4*>(recs + i);
+            out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
+            out[1] = make_float4(g.m10, g.m11, ga.w, g.pmax);
+            out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
+        }
         keys[i] = key;
         vals[i] = (uint32_t)i;
         rects[i] = rect;
-        if (vis) {
-            float4* o = reinterpret_cast<float4*>(recs + i);
-            o[0] = make_float4(rec.cx, rec.cy, rec.m00, rec.m01);
-            o[1] = make_float4(rec.m10, rec.m11, rec.alpha, rec.pmax);
-            o[2] = make_float4(rec.r, rec.g, rec.b, __uint_as_float(rec.hpack));
-        }
     }
-    // one atomic per warp for V
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    const unsigned m = __ballot_sync(0xffffffffu, vis);      // one atomic per warp for V
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_visible, (unsigned long long)__popc(m));
 }
 

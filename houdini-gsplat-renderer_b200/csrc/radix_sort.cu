@@ -27,15 +27,30 @@ constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int RS_ITEMS   = 8;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096
-constexpr int RS_RADIX   = 256;
+constexpr int RS_MAXBITS = 9;
+constexpr int RS_RADIX   = 1 << RS_MAXBITS;         // up to 512 bins per pass
 constexpr int RS_MAX_PASSES = 4;
+constexpr int LB_WIN     = 16;                      // predecessors inspected per look-back step (independent loads)
 
 constexpr uint32_t LB_AGG  = 0x40000000u;   // tile aggregate available
 constexpr uint32_t LB_INCL = 0x80000000u;   // inclusive prefix available
 constexpr uint32_t LB_MASK = 0x3FFFFFFFu;   // counts < 2^30
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
-struct PassPlan { int shift[RS_MAX_PASSES]; int bits[RS_MAX_PASSES]; int passes; };
+struct PassPlan { int shift[RS_MAX_PASSES]; int bits[RS_MAX_PASSES]; int passes; uint32_t key_min, key_span; };
+
+// dynamic shared memory of os_pass_kernel
+struct PassSmem {
+    uint16_t cnt[RS_WARPS][RS_RADIX];   // per-warp digit counts -> warp-exclusive offsets (<= 4096)
+    uint32_t local_base[RS_RADIX];      // exclusive scan of the tile's digit totals
+    uint32_t global_delta[RS_RADIX];    // global offset of digit d for this tile - local_base[d]
+    uint32_t tot[RS_RADIX];             // tile total per digit
+    uint32_t excl[RS_RADIX];            // look-back result per digit
+    uint32_t wtot[RS_WARPS];
+    uint32_t tile;
+    uint32_t sk[RS_TILE];
+    uint32_t sv[RS_TILE];
+};
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -50,17 +65,24 @@ __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v)
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Order-preserving key compression: keys below key_min + key_span keep their order after subtracting key_min,
+// everything at or above (the culled sentinel 0xFFFFFFFF) collapses onto key_span, the largest value.
+// key_min = 0, key_span = 0xFFFFFFFF is the identity.
+__device__ __forceinline__ uint32_t squeeze(uint32_t key, uint32_t key_min, uint32_t key_span)
+{
+    return min(key - key_min, key_span);
+}
+
 // lanes of the warp whose digit equals this lane's digit (0 for invalid lanes); nbits = digit width of the pass
-__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid, int nbits)
+template <int NBITS>
+__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid)
 {
     unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        if (b < nbits) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
-        }
+    for (int b = 0; b < NBITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
     }
     return valid ? peers : 0u;
 }
@@ -72,7 +94,7 @@ __device__ __forceinline__ size_t item_index(size_t base, int warp, int lane, in
 }
 
 // ---- upfront: global digit histograms of all passes, one read of the keys --------------------------------
-// hist layout: [pass][256].  Persistent CTAs, shared-memory REDs, one global RED per non-zero bin per CTA.
+// hist layout: [pass][RS_RADIX].  Persistent CTAs, shared-memory REDs, one global RED per non-zero bin per CTA.
 __global__ void __launch_bounds__(RS_THREADS)
 os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint32_t* __restrict__ hist)
 {
@@ -81,7 +103,7 @@ os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint3
     __syncthreads();
     const size_t stride = (size_t)gridDim.x * RS_THREADS;
     for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = __ldg(keys + i);
+        const uint32_t k = squeeze(__ldg(keys + i), plan.key_min, plan.key_span);
 #pragma unroll
         for (int p = 0; p < RS_MAX_PASSES; ++p)
             if (p < plan.passes) atomicAdd(&h[p][(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u)], 1u);
@@ -93,7 +115,7 @@ os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint3
     }
 }
 
-// exclusive scan of each pass's 256 bins, in place (one CTA of 256 threads per pass)
+// exclusive scan of each pass's RS_RADIX bins, in place (one CTA of RS_RADIX threads per pass)
 __global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t wtot[RS_RADIX / 32];
@@ -112,28 +134,27 @@ __global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __rest
 }
 
 // ---- one pass ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS)
+// lookback layout: [tile][nbins]: a tile publishes one coalesced row; a look-back step reads LB_WIN rows.
+template <int NBITS>
+__global__ void __launch_bounds__(RS_THREADS, 2)
 os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-               int shift, int nbits, const uint32_t* __restrict__ digit_base,
-               uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag)
+               int shift, uint32_t key_min, uint32_t key_span, const uint32_t* __restrict__ digit_base,
+               uint32_t* __restrict__ lookback, unsigned num_tiles, uint32_t* __restrict__ ticket,
+               uint32_t* __restrict__ error_flag,
+               const uint2* __restrict__ gather_src, uint2* __restrict__ gather_dst)
 {
-    __shared__ uint16_t cnt[RS_WARPS][RS_RADIX];     // per-warp digit counts -> warp-exclusive offsets (<= 4096)
-    __shared__ uint32_t local_base[RS_RADIX];        // exclusive scan of the tile's digit totals
-    __shared__ uint32_t global_delta[RS_RADIX];      // global offset of digit d for this tile - local_base[d]
-    __shared__ uint32_t wtot[RS_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t sk[RS_TILE];
-    __shared__ uint32_t sv[RS_TILE];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nbins = 1 << nbits;
-    const uint32_t mask = (uint32_t)nbins - 1u;
+    constexpr int nbins = 1 << NBITS;
+    constexpr uint32_t mask = (uint32_t)nbins - 1u;
     const unsigned lt = lanemask_lt();
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = sm.tile;
 
     const size_t base = (size_t)tile * RS_TILE;
     const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
@@ -152,74 +173,96 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     for (int j = 0; j < RS_ITEMS; ++j) {
         size_t idx = item_index(base, warp, lane, j);
         bool valid = idx < n;
-        uint32_t d = (k[j] >> shift) & mask;
-        unsigned peers = match_digit(d, valid, nbits);
-        uint32_t pre = valid ? cnt[warp][d] : 0u;
+        uint32_t d = (squeeze(k[j], key_min, key_span) >> shift) & mask;
+        unsigned peers = match_digit<NBITS>(d, valid);
+        uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
         __syncwarp();
-        if (valid && lane == (__ffs(peers) - 1)) cnt[warp][d] = (uint16_t)(pre + __popc(peers));
+        if (valid && lane == (__ffs(peers) - 1)) sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers));
         __syncwarp();
         rank[j] = (uint16_t)(pre + __popc(peers & lt));
     }
     __syncthreads();
 
-    // thread d: exclusive prefix over warps for digit d, tile total for d; publish, look back
-    uint32_t total = 0, excl = 0;
+    // thread d: exclusive prefix over warps for digit d, tile total for d; publish the aggregate
+    uint32_t total = 0;
     if ((int)threadIdx.x < nbins) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
-        uint32_t* mine = lookback + (size_t)tile * RS_RADIX + threadIdx.x;
-        st_volatile(mine, total | (tile == 0 ? LB_INCL : LB_AGG));
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t* p = lookback + (size_t)t * RS_RADIX + threadIdx.x;
-                uint32_t val, spins = 0;
-                while (((val = ld_volatile(p)) & (LB_AGG | LB_INCL)) == 0u) {
-                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); val = LB_INCL; break; }
-                    __nanosleep(20);
-                }
-                excl += val & LB_MASK;
-                if ((val & LB_INCL) || t == 0) break;
-                --t;
-            }
-            st_volatile(mine, ((excl + total) & LB_MASK) | LB_INCL);
-        }
+        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = sm.cnt[w][threadIdx.x]; sm.cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
+        sm.tot[threadIdx.x] = total;
+        st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, total | (tile == 0 ? LB_INCL : LB_AGG));
+        if (tile == 0) sm.excl[threadIdx.x] = 0u;
     }
     // exclusive scan of the digit totals across the block
     uint32_t inc = total;
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
-    if (lane == 31) wtot[warp] = inc;
+    if (lane == 31) sm.wtot[warp] = inc;
     __syncthreads();
     uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? wtot[w] : 0u;
-    if ((int)threadIdx.x < nbins) {
-        uint32_t lb = woff + inc - total;
-        local_base[threadIdx.x] = lb;
-        global_delta[threadIdx.x] = digit_base[threadIdx.x] + excl - lb;
-    }
+    for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
+    if ((int)threadIdx.x < nbins) sm.local_base[threadIdx.x] = woff + inc - total;
     __syncthreads();
 
-    // reorder through shared memory so each digit's run is contiguous
+    // reorder through shared memory so each digit's run is contiguous (needs no global information, and lets the
+    // key/value/rank registers die before the look-back)
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         size_t idx = item_index(base, warp, lane, j);
         if (idx < n) {
-            uint32_t d = (k[j] >> shift) & mask;
-            uint32_t lp = local_base[d] + cnt[warp][d] + rank[j];
-            sk[lp] = k[j]; sv[lp] = v[j];
+            uint32_t d = (squeeze(k[j], key_min, key_span) >> shift) & mask;
+            uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
+            sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
         }
     }
+
+    // Decoupled look-back, one thread per digit, LB_WIN predecessors per step: the LB_WIN volatile loads of a step are
+    // independent (one L2 round trip), rows of the [tile][digit] table are read coalesced across the warp.  With a window
+    // this wide the chain of not-yet-inclusive predecessors stays shorter than one window (equilibrium: resident tiles x
+    // round trip / (window x tile time) < 1); a narrow or serial walk lets it grow to the number of resident tiles.
+    if (tile > 0 && (int)threadIdx.x < nbins) {
+        const uint32_t* col = lookback + threadIdx.x;
+        uint32_t excl = 0, spins = 0;
+        int t = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t val[LB_WIN];
+#pragma unroll
+            for (int j = 0; j < LB_WIN; ++j)
+                val[j] = (t - j >= 0) ? ld_volatile(col + (size_t)(t - j) * nbins) : LB_INCL;
+            int used = 0;
+            bool blocked = false;
+#pragma unroll
+            for (int j = 0; j < LB_WIN; ++j) {
+                if (!done && !blocked) {
+                    if ((val[j] & (LB_AGG | LB_INCL)) == 0u) blocked = true;          // not published yet: retry from here
+                    else { excl += val[j] & LB_MASK; ++used; done = (val[j] & LB_INCL) != 0u; }
+                }
+            }
+            t -= used;
+            if (blocked) {
+                if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); break; }
+                __nanosleep(20);
+            }
+        }
+        sm.excl[threadIdx.x] = excl;
+        st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, ((excl + total) & LB_MASK) | LB_INCL);
+    }
     __syncthreads();
+    if ((int)threadIdx.x < nbins)
+        sm.global_delta[threadIdx.x] = digit_base[threadIdx.x] + sm.excl[threadIdx.x] - sm.local_base[threadIdx.x];
+    __syncthreads();
+
 #pragma unroll
     for (int t = 0; t < RS_ITEMS; ++t) {
         uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
         if (i < tile_count) {
-            uint32_t key = sk[i];
-            uint32_t d = (key >> shift) & mask;
-            size_t o = (size_t)(global_delta[d] + i);
-            keys_out[o] = key; vals_out[o] = sv[i];
+            uint32_t key = sm.sk[i];
+            uint32_t d = (squeeze(key, key_min, key_span) >> shift) & mask;
+            size_t o = (size_t)(sm.global_delta[d] + i);
+            const uint32_t val = sm.sv[i];
+            keys_out[o] = key; vals_out[o] = val;
+            if (gather_src) gather_dst[o] = __ldg(gather_src + val);     // last pass: payload into sorted order
         }
     }
 }
@@ -227,22 +270,38 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
 
 static inline size_t rs_blocks(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
-// scratch layout: [hist 4*256 u32][tickets 4 u32][error flag ...][pad to 256 B][lookback passes * blocks * 256 u32]
+// scratch layout: [hist 4*512 u32][tickets 4 u32][error flag ...][pad to 256 B][lookback passes * 512 * blocks u32]
 static inline size_t os_header_bytes() { return ((RS_MAX_PASSES * RS_RADIX + 8) * sizeof(uint32_t) + 255) & ~size_t(255); }
 
 size_t sort_scratch_bytes(size_t n)
 {
-    return os_header_bytes() + (size_t)RS_MAX_PASSES * rs_blocks(n) * RS_RADIX * sizeof(uint32_t) + 256;
+    return os_header_bytes() + (size_t)RS_MAX_PASSES * rs_blocks(n) * (RS_RADIX / 2) * sizeof(uint32_t) * 2 + 256;
+}
+
+int sort_key_bits(uint32_t key_span)
+{
+    int b = 0; while (b < 32 && (key_span >> b) != 0u) ++b; return b < 1 ? 1 : b;
 }
 
 int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                     int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches)
+                     int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
+                     const uint2* gather_src, uint2* gather_dst, uint32_t key_min, uint32_t key_span)
 {
     if (n == 0 || end_bit <= begin_bit) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
+        GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
+        GSB_SET_ATTR(8); GSB_SET_ATTR(9);
+#undef GSB_SET_ATTR
+        attr_set = true;
+    }
     const unsigned nb = (unsigned)rs_blocks(n);
     PassPlan plan{};
+    plan.key_min = key_min; plan.key_span = key_span;
     int bits_left = end_bit - begin_bit;
-    plan.passes = (bits_left + 7) / 8;
+    const int p8 = (bits_left + 7) / 8, p9 = (bits_left + 8) / 9;
+    plan.passes = p9 < p8 ? p9 : p8;          // 9-bit digits only when they save a whole pass
     int shift = begin_bit;
     for (int p = 0; p < plan.passes; ++p) {
         int b = (bits_left + (plan.passes - p) - 1) / (plan.passes - p);
@@ -252,16 +311,22 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
     if (!error_flag) error_flag = tickets + RS_MAX_PASSES;      // nobody looks: still a valid sink
     uint32_t* lookback = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + os_header_bytes());
-    const size_t lb_pass = (size_t)nb * RS_RADIX;
-    cudaMemsetAsync(scratch, 0, os_header_bytes() + (size_t)plan.passes * lb_pass * sizeof(uint32_t), s);
+    size_t lb_off[RS_MAX_PASSES + 1]; lb_off[0] = 0;
+    for (int p = 0; p < plan.passes; ++p) lb_off[p + 1] = lb_off[p] + ((size_t)nb << plan.bits[p]);
+    cudaMemsetAsync(scratch, 0, os_header_bytes() + lb_off[plan.passes] * sizeof(uint32_t), s);
     const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
     os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n, plan, hist);
     os_scan_hist_kernel<<<plan.passes, RS_RADIX, 0, s>>>(hist);
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
-        os_pass_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, plan.shift[p], plan.bits[p],
-                                                 hist + p * RS_RADIX, lookback + (size_t)p * lb_pass, tickets + p, error_flag);
+        const uint2* gsrc = (p == plan.passes - 1) ? gather_src : nullptr;
+#define GSB_PASS(B) case B: os_pass_kernel<B><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, plan.shift[p], \
+                        key_min, key_span, hist + p * RS_RADIX, lookback + lb_off[p], nb, tickets + p, error_flag, gsrc, gather_dst); break
+        switch (plan.bits[p]) {
+            GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
+        }
+#undef GSB_PASS
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

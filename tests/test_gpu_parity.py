@@ -62,6 +62,13 @@ def test_edge_cases_big_splats_behind_camera_and_offscreen(oracle, scene):
     o = O.pipeline(F, cl)
     g = gpu_pipeline(cl, fr, 3)
     assert_stage_parity(O, g, o, cl.n)
+    # non-finite positions: the depth-key range bound is disabled (full 32-bit sort), NaN splats are culled
+    cl.pos[100:105] = np.float32(np.nan); cl.pos[105:108, 1] = np.float32(np.inf)
+    fr, F = _frame(O, S, cl, 256, 144, 0.0, 3)
+    F.origin[:] = [0.0, 0.0, 0.0]
+    o = O.pipeline(F, cl)
+    g = gpu_pipeline(cl, fr, 3, origin=(0.0, 0.0, 0.0))
+    assert_stage_parity(O, g, o, cl.n)
 
 
 def test_explicit_camera_and_object_matrix(oracle, scene):

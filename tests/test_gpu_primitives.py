@@ -34,11 +34,15 @@ def test_exclusive_scan_64bit_total(rdr):
     (100_003, 0, 32, "rand"), (1_000_000, 0, 32, "float"), (1_000_000, 0, 32, "dups"),
     (300_000, 0, 13, "tiles"), (300_000, 0, 17, "tiles"), (50_000, 0, 1, "rand"), (2_500_000, 0, 32, "float"),
     (200_000, 0, 32, "same"),
+    (400_000, 0, 17, "tiles"), (1_000_000, 0, 25, "rand"), (700_001, 0, 27, "rand"), (9000, 0, 9, "rand"),   # 9-bit digits
+    (6_000_000, 0, 26, "rand"),
 ])
 def test_radix_sort_is_stable(rdr, n, lo, hi, kind):
     rng = np.random.default_rng(n + hi)
     if kind == "rand":
         k = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+        if hi < 32:
+            k &= np.uint32((1 << hi) - 1)
     elif kind == "float":       # depth keys: bits of non-negative floats in a narrow exponent range
         k = (rng.random(n, dtype=np.float32) * 20 + 1.5).view(np.uint32)
     elif kind == "dups":
