@@ -26,7 +26,7 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
 // of an earlier depth chunk): instances behind a saturated tile can never change a pixel.
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const uint2* __restrict__ rects_sorted, int64_t r0, int64_t n,
-                  int tiles_x, int row_rank, int row_world, const uint32_t* __restrict__ tile_done,
+                  int tiles_x, int row_rank, int row_world, int row_group, const uint32_t* __restrict__ tile_done,
                   uint32_t* __restrict__ counts)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,7 +35,7 @@ tile_count_kernel(const uint2* __restrict__ rects_sorted, int64_t r0, int64_t n,
     uint32_t c = 0;
     if (!t.empty) {
         for (int ty = t.ty0; ty <= t.ty1; ++ty) {
-            if (row_world > 1 && (ty % row_world) != row_rank) continue;
+            if (!owns_row(ty, row_rank, row_world, row_group)) continue;
             if (tile_done) { for (int tx = t.tx0; tx <= t.tx1; ++tx) c += __ldg(tile_done + ty * tiles_x + tx) == 0u; }
             else c += (uint32_t)(t.tx1 - t.tx0 + 1);
         }
@@ -47,7 +47,7 @@ tile_count_kernel(const uint2* __restrict__ rects_sorted, int64_t r0, int64_t n,
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects_sorted,
             const uint32_t* __restrict__ offsets, const unsigned long long* __restrict__ total,
-            int64_t r0, int64_t n, int tiles_x, int row_rank, int row_world,
+            int64_t r0, int64_t n, int tiles_x, int row_rank, int row_world, int row_group,
             const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +59,7 @@ emit_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ rects_
     const TileRect t = tile_rect(__ldg(rects_sorted + r0 + k));
     size_t o = o0;
     for (int ty = t.ty0; ty <= t.ty1; ++ty) {
-        if (row_world > 1 && (ty % row_world) != row_rank) continue;
+        if (!owns_row(ty, row_rank, row_world, row_group)) continue;
         for (int tx = t.tx0; tx <= t.tx1; ++tx) {
             const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
             if (tile_done && __ldg(tile_done + tile) != 0u) continue;
@@ -88,7 +88,7 @@ void launch_tile_counts(const uint2* rects_sorted, int64_t r0, int64_t n, FrameC
 {
     if (n <= 0) return;
     tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rects_sorted, r0, n, fc.tiles_x, fc.row_rank,
-                                                                 fc.row_world, tile_done, counts);
+                                                                 fc.row_world, fc.row_group, tile_done, counts);
 }
 
 void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_t* offsets,
@@ -97,7 +97,7 @@ void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_
 {
     if (n <= 0) return;
     emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, rects_sorted, offsets, total, r0, n, fc.tiles_x,
-                                                           fc.row_rank, fc.row_world, tile_done, inst_keys, inst_vals);
+                                                           fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals);
 }
 
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,

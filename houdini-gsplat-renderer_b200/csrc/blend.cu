@@ -40,7 +40,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void __launch_bounds__(BL_THREADS)
 blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
-             const uint2* __restrict__ ranges, float4* __restrict__ fb,
+             const uint2* __restrict__ ranges, float4* __restrict__ fb, float4* __restrict__ fb_final,
              const __grid_constant__ FrameConsts F, const int first, const int last,
              uint32_t* __restrict__ tile_done,
              uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total,
@@ -51,7 +51,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
     const int tile = blockIdx.x;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
-    if (F.row_world > 1 && (ty % F.row_world) != F.row_rank) return;      // CTA-uniform
+    if (!owns_row(ty, F.row_rank, F.row_world, F.row_group)) return;      // CTA-uniform
     if (!first && tile_done[tile] != 0u) return;                          // saturated and finalised in an earlier chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -143,7 +143,11 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
     if (lane == 0) atomicMax(&s_consumed, warp_done ? warp_pos : len);
     const bool tile_saturated = __syncthreads_and(warp_done ? 1 : 0) != 0;   // also orders the atomicMax
-    if (inside) fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, (tile_saturated || last) ? 1.0f - T : T);
+    if (inside) {
+        // finished tiles go to the final frame (possibly peer memory over NVLink), unfinished ones keep (C, T) locally
+        if (tile_saturated || last) fb_final[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, 1.0f - T);
+        else fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, T);
+    }
     if (tid == 0) {
         if (tile_saturated) { tile_done[tile] = 1u; atomicAdd(done_tiles, 1ull); }
         if (tile_consumed) tile_consumed[tile] += s_consumed;
@@ -153,13 +157,13 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
 }  // namespace
 
-void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
+void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
                   unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s)
 {
     const int tiles = fc.tiles_x * fc.tiles_y;
     if (tiles <= 0) return;
-    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fc, first, last, tile_done,
+    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last, tile_done,
                                               tile_consumed, consumed_total, done_tiles);
 }
 

@@ -21,7 +21,8 @@ struct FrameConsts {
     int   width, height;
     int   tiles_x, tiles_y;
     int   sh_order;             // effective order (0 when the packed set has no SH)
-    int   row_rank, row_world;  // tile-row ownership
+    int   row_rank, row_world;  // tile-row ownership: row ty is owned iff (ty / row_group) % row_world == row_rank
+    int   row_group;
     float eps_t;                // transmittance early-out threshold
 };
 
@@ -69,9 +70,13 @@ void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, con
                  int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
                  int planes, cudaStream_t s);
 // K1: keys (culled -> KEY_CULLED), vals = splat index, rects (x0>x1 = culled), records, *n_visible += V
+// vis_flags (may be NULL): 1/0 per splat, the input of launch_compact's scan
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
-                    unsigned long long* n_visible, cudaStream_t s);
+                    unsigned long long* n_visible, uint32_t* vis_flags, cudaStream_t s);
+// order-preserving compaction of the surviving (key, index) pairs; positions = exclusive scan of vis_flags
+void launch_compact(const uint32_t* keys, const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
+                    cudaStream_t s);
 
 // binning.cu
 // ranks [r0, r0+n) of the depth order; rects_sorted in depth order; tile_done (may be NULL) = saturation flags
@@ -87,9 +92,15 @@ void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* rang
 // blend.cu
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
 // chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done;
-// last: every remaining tile is finalised.  *done_tiles counts the tiles flagged so far (early termination).
-void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb,
+// last: every remaining tile is finalised.  Finalised tiles are stored to fb_final (NULL = fb; may be peer memory).  *done_tiles counts the tiles flagged so far (early termination).
+void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
                   unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s);
+
+// tile-row ownership rule shared by every kernel
+__host__ __device__ __forceinline__ bool owns_row(int ty, int rank, int world, int group)
+{
+    return world <= 1 || ((ty / group) % world) == rank;
+}
 
 }  // namespace gsb

@@ -223,7 +223,7 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     g.x0 = (int)x0f; g.x1 = (int)x1f; g.y0 = (int)y0f; g.y1 = (int)y1f;
     if (F.row_world > 1) {
         bool any = false;
-        for (int tyy = g.y0 / TILE; tyy <= g.y1 / TILE && !any; ++tyy) any = (tyy % F.row_world) == F.row_rank;
+        for (int tyy = g.y0 / TILE; tyy <= g.y1 / TILE && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
         if (!any) return false;
     }
     g.cx = cx; g.cy = cy;
@@ -296,7 +296,8 @@ template <int ORDER>
 __global__ void __launch_bounds__(256)
 project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps, int64_t n,
                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, Record* __restrict__ recs,
-               uint2* __restrict__ rects, unsigned long long* __restrict__ n_visible)
+               uint2* __restrict__ rects, unsigned long long* __restrict__ n_visible,
+               uint32_t* __restrict__ vis_flags)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
@@ -326,6 +327,7 @@ project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ Pa
         keys[i] = key;
         vals[i] = (uint32_t)i;
         rects[i] = rect;
+        if (vis_flags) vis_flags[i] = vis ? 1u : 0u;         // input of the survivor compaction (multi-GPU shards)
     }
     const unsigned m = __ballot_sync(0xffffffffu, vis);      // one atomic per warp for V
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_visible, (unsigned long long)__popc(m));
@@ -346,16 +348,36 @@ void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, con
 
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
-                    unsigned long long* n_visible, cudaStream_t s)
+                    unsigned long long* n_visible, uint32_t* vis_flags, cudaStream_t s)
 {
     if (n <= 0) return;
     unsigned grid = (unsigned)((n + 255) / 256);
     switch (fc.sh_order) {
-    case 0:  project_kernel<0><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
-    case 1:  project_kernel<1><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
-    case 2:  project_kernel<2><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
-    default: project_kernel<3><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible); break;
+    case 0:  project_kernel<0><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
+    case 1:  project_kernel<1><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
+    case 2:  project_kernel<2><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
+    default: project_kernel<3><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
     }
+}
+
+namespace {
+// survivors keep their relative (index) order: positions = exclusive scan of the visibility flags
+__global__ void __launch_bounds__(256)
+compact_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ positions, int64_t n,
+               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = __ldg(keys + i);
+    if (k != KEY_CULLED) { const uint32_t p = __ldg(positions + i); keys_out[p] = k; vals_out[p] = (uint32_t)i; }
+}
+}  // namespace
+
+void launch_compact(const uint32_t* keys, const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
+                    cudaStream_t s)
+{
+    if (n <= 0) return;
+    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, positions, n, keys_out, vals_out);
 }
 
 }  // namespace gsb

@@ -100,6 +100,7 @@ struct gsb_context {
     float   eps_t = 1e-5f;
     bool    stage_timing = false, keep_intermediates = false;
     int     depth_chunks = 0;                                 // 0 = auto
+    int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
     DevBuf geomA, geomB, col[6];
@@ -107,10 +108,11 @@ struct gsb_context {
 
     // per-frame device buffers
     DevBuf keys[2], vals[2], keys_unsorted, recs, rects, rects_sorted, counts, ikeys[2], ivals[2], ranges, tile_consumed, tile_done, fb;
+    DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
     unsigned long long* counters_h = nullptr;        // pinned mirror
     int order_buf = 0, inst_buf = 0;
-    int64_t last_n = 0; uint64_t last_d = 0; int last_tiles = 0; int last_w = 0, last_h = 0;
+    int64_t last_n = 0, last_sorted = 0; uint64_t last_d = 0; int last_tiles = 0; int last_w = 0, last_h = 0;
     float4* last_fb = nullptr;
 
     cudaEvent_t ev[EV_COUNT] = {};
@@ -236,6 +238,9 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
         ctx->eps_t = (float)value; return GSB_OK;
     case GSB_OPT_STAGE_TIMING: ctx->stage_timing = value != 0; return GSB_OK;
     case GSB_OPT_KEEP_INTERMEDIATES: ctx->keep_intermediates = value != 0; return GSB_OK;
+    case GSB_OPT_COMPACT:
+        if (value < 0 || value > 2) return fail(GSB_ERR_INVALID, "GSB_OPT_COMPACT must be 0 (auto), 1 (always) or 2 (never)");
+        ctx->compact_mode = (int)value; return GSB_OK;
     case GSB_OPT_DEPTH_CHUNKS:
         if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_DEPTH_CHUNKS must be 0 (auto) .. 16");
         ctx->depth_chunks = (int)value; return GSB_OK;
@@ -434,6 +439,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         return fail(GSB_ERR_LIMIT, "gsb_render: screen size must be 1..65535");
     if (fr->row_world < 1 || fr->row_rank < 0 || fr->row_rank >= fr->row_world)
         return fail(GSB_ERR_INVALID, "gsb_render: bad tile-row partition");
+    if (fr->row_group < 0) return fail(GSB_ERR_INVALID, "gsb_render: row_group must be >= 0");
     if (target && target->gl_texture != 0)
         return fail(GSB_ERR_INVALID, "gsb_render: this build has no OpenGL; CUDA<->GL interop target unavailable");
     CU(cudaSetDevice(ctx->device));
@@ -449,7 +455,8 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     fc.tiles_x = (fr->width + TILE - 1) / TILE; fc.tiles_y = (fr->height + TILE - 1) / TILE;
     const bool do_sh = ctx->sh_order > 0 && ctx->sh_present;              // R.C:623
     fc.sh_order = do_sh ? std::min(ctx->sh_order, 3) : 0;
-    fc.row_rank = fr->row_rank; fc.row_world = fr->row_world; fc.eps_t = ctx->eps_t;
+    fc.row_rank = fr->row_rank; fc.row_world = fr->row_world; fc.row_group = fr->row_group > 1 ? fr->row_group : 1;
+    fc.eps_t = ctx->eps_t;
     const int num_tiles = fc.tiles_x * fc.tiles_y;
     const int64_t n = ctx->splat_count;
     const size_t  N = (size_t)n;
@@ -465,6 +472,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
     if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
     else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
+    float4* fb_final = (target && target->final_rgba) ? static_cast<float4*>(target->final_rgba) : fb;
 
     unsigned long long* cnt = ctx->counters.as<unsigned long long>();
     const bool tm = ctx->stage_timing;
@@ -475,11 +483,27 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(),
                      { ctx->col[0].as<uint4>(), ctx->col[1].as<uint4>(), ctx->col[2].as<uint4>(),
                        ctx->col[3].as<uint4>(), ctx->col[4].as<uint4>(), ctx->col[5].as<uint4>() } };
+    // A row-partitioned frame (multi-GPU) culls most splats on every rank: compact the survivors (order preserving,
+    // so the tie rule "ascending index" still holds) and sort / bin only V instead of N.
+    const bool compact = ctx->compact_mode == 1 || (ctx->compact_mode == 0 && fr->row_world > 1);
     launch_project(fc, ps, n, ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), ctx->recs.as<Record>(),
-                   ctx->rects.as<uint2>(), cnt + 0, s);
+                   ctx->rects.as<uint2>(), cnt + 0, compact ? ctx->counts.as<uint32_t>() : nullptr, s);
     st.launches += 1;
     if (ctx->keep_intermediates)
         CU(cudaMemcpyAsync(ctx->keys_unsorted.p, ctx->keys[0].p, N * 4, cudaMemcpyDeviceToDevice, s));
+    int64_t n_sort = n;                 // elements that go through the depth sort and the binning
+    int src = 0;                        // which (keys, vals) pair holds the sort input
+    if (compact) {
+        exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), N, ctx->scan_scratch.p, nullptr, s, &st.launches);
+        launch_compact(ctx->keys[0].as<uint32_t>(), ctx->counts.as<uint32_t>(), n, ctx->keys[1].as<uint32_t>(),
+                       ctx->vals[1].as<uint32_t>(), s);
+        st.launches += 1;
+        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        n_sort = (int64_t)ctx->counters_h[0];
+        src = 1;
+    }
+    const size_t NS = (size_t)n_sort;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
 
     // K3 global depth sort (stable).  Every key is the fp32 bit pattern of a squared distance from the camera to a point
@@ -502,8 +526,8 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         }
     }
     const int key_bits = sort_key_bits(key_span);
-    ctx->order_buf = radix_sort_pairs(ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(),
-                                      ctx->keys[1].as<uint32_t>(), ctx->vals[1].as<uint32_t>(), N, 0, key_bits,
+    ctx->order_buf = src ^ radix_sort_pairs(ctx->keys[src].as<uint32_t>(), ctx->vals[src].as<uint32_t>(),
+                                      ctx->keys[src ^ 1].as<uint32_t>(), ctx->vals[src ^ 1].as<uint32_t>(), NS, 0, key_bits,
                                       ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches,
                                       ctx->rects.as<uint2>(), ctx->rects_sorted.as<uint2>(), key_min, key_span);
     const uint32_t* order = ctx->vals[ctx->order_buf].as<uint32_t>();
@@ -515,20 +539,20 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     uint32_t* tile_done = ctx->tile_done.as<uint32_t>();
     CU(cudaMemsetAsync(tile_done, 0, (size_t)num_tiles * 4, s));
     CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));     // accumulates over chunks
-    if (fr->row_world > 1) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));             // rows this rank does not own stay zero
+    if (fr->row_world > 1 && fb_final == fb) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));   // rows this rank does not own stay zero
     int nchunks = ctx->depth_chunks;
-    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 5 : 1;                // auto
+    if (nchunks <= 0) nchunks = (n_sort >= (int64_t)2000000) ? 3 : 1;           // auto (r01 sweep: 3-4 best at 20 M, 1 at 1 M)
     nchunks = std::min(nchunks, 16);
     // geometric boundaries: the first chunk is N / 2^(nchunks), every further chunk doubles the covered depth range
     int64_t bounds[17]; bounds[0] = 0;
     for (int c = 1; c <= nchunks; ++c) {
-        bounds[c] = (c == nchunks) ? n : std::max<int64_t>(1, (int64_t)(((double)n * (double)((1ll << c) - 1)) / (double)(1ll << nchunks)));
-        bounds[c] = std::min(bounds[c], n);
+        bounds[c] = (c == nchunks) ? n_sort : std::max<int64_t>(1, (int64_t)(((double)n_sort * (double)((1ll << c) - 1)) / (double)(1ll << nchunks)));
+        bounds[c] = std::min(bounds[c], n_sort);
     }
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
     // tiles this rank owns: when all of them are saturated no deeper splat can change a pixel and the frame is done
     int owned_rows = 0;
-    for (int ty = 0; ty < fc.tiles_y; ++ty) owned_rows += (fr->row_world <= 1) || (ty % fr->row_world) == fr->row_rank;
+    for (int ty = 0; ty < fc.tiles_y; ++ty) owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
     const uint64_t owned_tiles = (uint64_t)owned_rows * (uint64_t)fc.tiles_x;
     uint64_t D_total = 0, V = 0, D = 0;
     int chunks_run = 0;
@@ -565,7 +589,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
-        launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fc,
+        launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fb_final, fc,
                      first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 2, cnt + 4, s);
         st.launches += 1;
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
@@ -579,14 +603,14 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
 
     if (target && target->host_rgba) {
-        CU(cudaMemcpyAsync(target->host_rgba, fb, fb_bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
         if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
         CU(cudaStreamSynchronize(s));
     } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
     ctx->ev_valid = tm;
 
-    ctx->last_n = n; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
-    ctx->last_fb = fb;
+    ctx->last_n = n; ctx->last_sorted = n_sort; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
+    ctx->last_fb = fb_final;
     st.depth_chunks = nchunks;
     st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D;
     st.sh_order_used = fc.sh_order; st.width = fr->width; st.height = fr->height;
@@ -637,6 +661,49 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
 
 void* gsb_device_framebuffer(gsb_context* ctx) { return ctx ? (void*)ctx->last_fb : nullptr; }
 
+int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height, unsigned char handle_out[GSB_IPC_HANDLE_BYTES],
+                         void** local_ptr_out)
+{
+    if (!ctx || !handle_out || !local_ptr_out || width < 1 || height < 1) return fail(GSB_ERR_INVALID, "gsb_ipc_export_frame: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GSB_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->shared_frame.ensure((size_t)width * height * 16));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->shared_frame.p));
+    memcpy(handle_out, &h, GSB_IPC_HANDLE_BYTES);
+    *local_ptr_out = ctx->shared_frame.p;
+    return GSB_OK;
+}
+
+int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYTES], void** peer_ptr_out)
+{
+    if (!ctx || !handle || !peer_ptr_out) return fail(GSB_ERR_INVALID, "gsb_ipc_open: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h; memcpy(&h, handle, GSB_IPC_HANDLE_BYTES);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));     // maps the peer GPU's memory (NVLink P2P)
+    *peer_ptr_out = p;
+    return GSB_OK;
+}
+
+int gsb_ipc_close(gsb_context* ctx, void* peer_ptr)
+{
+    if (!ctx || !peer_ptr) return fail(GSB_ERR_INVALID, "gsb_ipc_close: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaIpcCloseMemHandle(peer_ptr));
+    return GSB_OK;
+}
+
+int gsb_copy_to_host(gsb_context* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes)
+{
+    if (!ctx || !device_ptr || !host_ptr) return fail(GSB_ERR_INVALID, "gsb_copy_to_host: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(host_ptr, device_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GSB_OK;
+}
+
 int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed)
 {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
@@ -646,8 +713,8 @@ int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, 
     const uint64_t n = (uint64_t)ctx->last_n, d = ctx->last_d, t = (uint64_t)ctx->last_tiles;
     switch (which) {
     case GSB_DBG_KEYS_UNSORTED: src = ctx->keys_unsorted.p; need = ctx->keep_intermediates ? n * 4 : 0; break;
-    case GSB_DBG_ORDER:         src = ctx->vals[ctx->order_buf].p; need = n * 4; break;
-    case GSB_DBG_KEYS_SORTED:   src = ctx->keys[ctx->order_buf].p; need = n * 4; break;
+    case GSB_DBG_ORDER:         src = ctx->vals[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
+    case GSB_DBG_KEYS_SORTED:   src = ctx->keys[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
     case GSB_DBG_RECORDS:       src = ctx->recs.p; need = n * sizeof(Record); break;
     case GSB_DBG_RECTS:         src = ctx->rects.p; need = n * 8; break;
     case GSB_DBG_TILE_RANGES:   src = ctx->ranges.p; need = t * 8; break;

@@ -19,7 +19,7 @@ LIB_PATH = HERE / "libgsplat_b200.so"
 ID_MAX = 128
 REFERENCE_SPLAT_CAP = 8388607
 
-OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS = 1, 2, 3, 4, 5
+OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS, OPT_COMPACT = 1, 2, 3, 4, 5, 6
 (DBG_KEYS_UNSORTED, DBG_ORDER, DBG_RECORDS, DBG_RECTS, DBG_TILE_RANGES, DBG_INSTANCES,
  DBG_FRAMEBUFFER, DBG_KEYS_SORTED, DBG_TILE_CONSUMED) = range(9)
 
@@ -34,7 +34,8 @@ EXPORTS = ["gsb_abi_version", "gsb_create", "gsb_destroy", "gsb_last_error", "gs
            "gsb_generate_render_geometry", "gsb_render", "gsb_post_render", "gsb_set_rendering_enabled",
            "gsb_set_explicit_camera_pos", "gsb_set_spherical_harmonics_order", "gsb_set_option",
            "gsb_get_stats", "gsb_set_stream", "gsb_synchronize", "gsb_device_framebuffer",
-           "gsb_registry_size", "gsb_debug_fetch", "gsb_debug_sort_pairs", "gsb_debug_exclusive_scan"]
+           "gsb_registry_size", "gsb_debug_fetch", "gsb_debug_sort_pairs", "gsb_debug_exclusive_scan",
+           "gsb_ipc_export_frame", "gsb_ipc_open", "gsb_ipc_close", "gsb_copy_to_host"]
 
 
 class GsbError(RuntimeError):
@@ -49,12 +50,13 @@ class FrameC(C.Structure):
     _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("object", C.c_float * 16),
                 ("inv_object", C.c_float * 16), ("obj_view", C.c_float * 16),
                 ("width", C.c_int32), ("height", C.c_int32), ("is_object_level", C.c_int32),
-                ("row_rank", C.c_int32), ("row_world", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("row_rank", C.c_int32), ("row_world", C.c_int32), ("row_group", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class TargetC(C.Structure):
     _fields_ = [("device_rgba", C.c_void_p), ("host_rgba", C.c_void_p),
-                ("gl_texture", C.c_uint32), ("flags", C.c_uint32)]
+                ("gl_texture", C.c_uint32), ("flags", C.c_uint32), ("final_rgba", C.c_void_p)]
 
 
 class StatsC(C.Structure):
@@ -99,6 +101,10 @@ def load_library() -> C.CDLL:
         lib.gsb_set_rendering_enabled.argtypes = [C.c_void_p, C.c_int]
         lib.gsb_set_spherical_harmonics_order.argtypes = [C.c_void_p, C.c_int]
         lib.gsb_set_explicit_camera_pos.argtypes = [C.c_void_p, C.c_void_p]
+        lib.gsb_ipc_export_frame.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.gsb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.gsb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+        lib.gsb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = lib
     return _lib
 
@@ -107,13 +113,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def frame_to_c(frame, row_rank: int = 0, row_world: int = 1) -> FrameC:
+def frame_to_c(frame, row_rank: int = 0, row_world: int = 1, row_group: int = 1) -> FrameC:
     f = FrameC()
     for name in ("view", "proj", "object", "inv_object", "obj_view"):
         getattr(f, name)[:] = np.asarray(getattr(frame, name), np.float32).reshape(16).tolist()
     f.width, f.height = int(frame.width), int(frame.height)
     f.is_object_level = int(bool(getattr(frame, "is_object_level", False)))
-    f.row_rank, f.row_world = int(row_rank), int(row_world)
+    f.row_rank, f.row_world, f.row_group = int(row_rank), int(row_world), int(row_group)
     return f
 
 
@@ -172,12 +178,12 @@ class GSplatRenderer:
         self._ck(self._lib.gsb_generate_render_geometry(self._h), "gsb_generate_render_geometry")
 
     def render(self, frame, host_rgba: np.ndarray | None = None, device_rgba: int | None = None,
-               row_rank: int = 0, row_world: int = 1):
+               row_rank: int = 0, row_world: int = 1, row_group: int = 1, final_rgba: int | None = None):
         """GSplatRenderer::render(r, isObjectLevel) (R.C:534-658).  ``frame`` supplies what the reference
         reads from RE_Render / glH_*; the finished frame goes to the library's device buffer, to
         ``device_rgba`` (a CUDA pointer) and/or to ``host_rgba`` ([H,W,4] f32, D2H inside the call)."""
-        fc = frame if isinstance(frame, FrameC) else frame_to_c(frame, row_rank, row_world)
-        t = TargetC(device_rgba, None if host_rgba is None else host_rgba.ctypes.data, 0, 0)
+        fc = frame if isinstance(frame, FrameC) else frame_to_c(frame, row_rank, row_world, row_group)
+        t = TargetC(device_rgba, None if host_rgba is None else host_rgba.ctypes.data, 0, 0, final_rgba)
         self._ck(self._lib.gsb_render(self._h, C.byref(fc), C.byref(t)), "gsb_render")
 
     def postRender(self):
@@ -208,6 +214,24 @@ class GSplatRenderer:
 
     def registry_size(self) -> int:
         return int(self._lib.gsb_registry_size(self._h))
+
+    # ---- multi-GPU frame sharing (CUDA IPC; the blend writes finished tiles into the display rank's frame) ----
+    def ipc_export_frame(self, width: int, height: int):
+        """Display rank: allocate the shared frame; returns (64-byte handle, local device pointer)."""
+        h = (C.c_ubyte * 64)(); p = C.c_void_p()
+        self._ck(self._lib.gsb_ipc_export_frame(self._h, int(width), int(height), h, C.byref(p)), "gsb_ipc_export_frame")
+        return bytes(h), int(p.value)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle); p = C.c_void_p()
+        self._ck(self._lib.gsb_ipc_open(self._h, buf, C.byref(p)), "gsb_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._ck(self._lib.gsb_ipc_close(self._h, ptr), "gsb_ipc_close")
+
+    def copy_to_host(self, device_ptr: int, host: np.ndarray):
+        self._ck(self._lib.gsb_copy_to_host(self._h, device_ptr, host.ctypes.data, host.nbytes), "gsb_copy_to_host")
 
     def stats(self) -> dict:
         s = StatsC()

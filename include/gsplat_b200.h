@@ -63,9 +63,10 @@ typedef struct gsb_frame {
     float   obj_view[16];    /* glH_ObjViewMatrix   */
     int32_t width, height;   /* glH_ScreenSize      */
     int32_t is_object_level; /* DM_SceneHookData::disp_options->isObjectLevel() (DM_GSplatHook.C:34) */
-    int32_t row_rank;        /* multi-GPU: this context blends tile rows ty with ty % row_world == row_rank */
+    int32_t row_rank;        /* multi-GPU: this context blends tile rows ty with (ty / row_group) % row_world == row_rank */
     int32_t row_world;       /* 1 = whole frame */
-    int32_t reserved[3];
+    int32_t row_group;       /* tile rows per interleaved band; 0 or 1 = single rows.  Wider bands duplicate fewer splats */
+    int32_t reserved[2];
 } gsb_frame;
 
 /* Where the finished frame goes.  All optional; with everything NULL the frame stays in the
@@ -75,6 +76,10 @@ typedef struct gsb_target {
     void*    host_rgba;      /* if non-NULL the frame is copied here (D2H inside the call, call returns when done) */
     uint32_t gl_texture;     /* CUDA<->GL interop target (RGBA32F GL_TEXTURE_2D); must be 0 in builds without GL */
     uint32_t flags;          /* reserved, 0 */
+    void*    final_rgba;     /* optional: finished tiles are stored HERE instead of device_rgba (which then only holds the
+                                per-chunk blend state).  May be PEER memory of another GPU (gsb_ipc_open): the blend kernel
+                                writes this rank's tile rows straight into the display GPU's frame over NVLink, so a
+                                row-partitioned frame needs no gather pass.  Not readable until every rank has synchronised. */
 } gsb_target;
 
 typedef struct gsb_stats {
@@ -102,13 +107,14 @@ enum gsb_option {
     GSB_OPT_EPS_T = 2,           /* transmittance early-out threshold; default 1e-5; 0 = never stop (reference) */
     GSB_OPT_STAGE_TIMING = 3,    /* record per-stage CUDA events (default 0) */
     GSB_OPT_KEEP_INTERMEDIATES = 4, /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
+    GSB_OPT_COMPACT = 6,         /* compact surviving splats before the depth sort: 0 = auto (row-partitioned frames), 1, 2 = never */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };
 
 enum gsb_debug_buffer {
     GSB_DBG_KEYS_UNSORTED = 0,   /* uint32[N]  depth keys in submission order (needs KEEP_INTERMEDIATES) */
-    GSB_DBG_ORDER = 1,           /* uint32[N]  splat index by depth rank (culled splats last) */
+    GSB_DBG_ORDER = 1,           /* uint32[N]  splat index by depth rank, culled splats last (uint32[V] when compacted) */
     GSB_DBG_RECORDS = 2,         /* 48 B x N   2-D records by splat index (valid where visible) */
     GSB_DBG_RECTS = 3,           /* uint16[4] x N  inclusive pixel rectangle x0,x1,y0,y1 (x0>x1 = culled) */
     GSB_DBG_TILE_RANGES = 4,     /* uint32[2] x tiles  [start,end) into the instance list (last depth chunk) */
@@ -158,6 +164,15 @@ GSB_API int   gsb_set_stream(gsb_context* ctx, void* cuda_stream);   /* run on a
 GSB_API int   gsb_synchronize(gsb_context* ctx);
 GSB_API void* gsb_device_framebuffer(gsb_context* ctx);              /* device pointer of the last library-owned frame */
 GSB_API int   gsb_registry_size(gsb_context* ctx);                   /* live registry entries */
+
+/* Multi-GPU frame sharing (one process per GPU).  The display rank allocates a frame and exports a CUDA IPC handle; the
+ * other ranks open it and pass the mapped pointer as gsb_target.final_rgba. */
+#define GSB_IPC_HANDLE_BYTES 64
+GSB_API int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height, unsigned char handle_out[GSB_IPC_HANDLE_BYTES],
+                                 void** local_ptr_out);
+GSB_API int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYTES], void** peer_ptr_out);
+GSB_API int gsb_ipc_close(gsb_context* ctx, void* peer_ptr);
+GSB_API int gsb_copy_to_host(gsb_context* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes);  /* stream-ordered, synchronous */
 
 /* Test hooks: copy an intermediate device buffer to the host.  *bytes_needed is always set;
  * the copy happens only if dst != NULL and dst_bytes >= needed. */

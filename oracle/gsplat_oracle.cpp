@@ -50,7 +50,8 @@ typedef struct {
     float origin[3];       /* GSplatOrigin        (R.C:403-418)    */
     int32_t width, height; /* glH_ScreenSize                       */
     int32_t sh_order;      /* GSplatShOrder, already 0 if no SH data (R.C:623,628) */
-    int32_t row_rank, row_world; /* tile-row ownership: row ty owned iff ty % world == rank */
+    int32_t row_rank, row_world; /* tile-row ownership: row ty owned iff (ty / row_group) % world == rank */
+    int32_t row_group;           /* tile rows per band, >= 1 */
     float eps_t;           /* transmittance early-out threshold; 0 = never stop (reference) */
 } orc_frame;
 
@@ -70,6 +71,12 @@ typedef struct {
 
 #define ORC_TILE 16
 #define ORC_KEY_CULLED 0xFFFFFFFFu
+
+static inline int orc_owns_row(const orc_frame* F, int ty)
+{
+    int g = F->row_group > 1 ? F->row_group : 1;
+    return F->row_world <= 1 || ((ty / g) % F->row_world) == F->row_rank;
+}
 
 /* ---------------------------------------------------------------- half <-> float */
 static inline float h2f(uint16_t h)
@@ -335,7 +342,7 @@ static int project_one(const orc_frame* F,
     /* tile-row ownership (multi-GPU): survive iff some owned tile row is touched */
     if (F->row_world > 1) {
         int ty0 = y0 / ORC_TILE, ty1 = y1 / ORC_TILE, any = 0;
-        for (int ty = ty0; ty <= ty1 && !any; ++ty) any = (ty % F->row_world) == F->row_rank;
+        for (int ty = ty0; ty <= ty1 && !any; ++ty) any = orc_owns_row(F, ty);
         if (!any) return 0;
     }
     rect->x0 = (uint16_t)x0; rect->x1 = (uint16_t)x1; rect->y0 = (uint16_t)y0; rect->y1 = (uint16_t)y1;
@@ -425,7 +432,7 @@ int64_t orc_bin(const orc_frame* F, int64_t n, const int32_t* order, const uint8
         int32_t i = order[r]; if (!vis[i]) continue;
         const orc_rect& q = rects[i];
         for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
-            if (F->row_world > 1 && (ty % F->row_world) != F->row_rank) continue;
+            if (!orc_owns_row(F, ty)) continue;
             for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) cnt[(size_t)ty * TX + tx] += 1;
         }
     }
@@ -438,7 +445,7 @@ int64_t orc_bin(const orc_frame* F, int64_t n, const int32_t* order, const uint8
         int32_t i = order[r]; if (!vis[i]) continue;
         const orc_rect& q = rects[i];
         for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
-            if (F->row_world > 1 && (ty % F->row_world) != F->row_rank) continue;
+            if (!orc_owns_row(F, ty)) continue;
             for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) inst[cur[(size_t)ty * TX + tx]++] = i;
         }
     }
@@ -474,7 +481,7 @@ int64_t orc_blend(const orc_frame* F, const orc_record* recs, const int64_t* til
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
     for (int t = 0; t < TX * TY; ++t) {
         int ty = t / TX, tx = t % TX;
-        if (F->row_world > 1 && (ty % F->row_world) != F->row_rank) { if (consumed) consumed[t] = 0; continue; }
+        if (!orc_owns_row(F, ty)) { if (consumed) consumed[t] = 0; continue; }
         float C[ORC_TILE * ORC_TILE][3]; float T[ORC_TILE * ORC_TILE]; uint8_t done[ORC_TILE * ORC_TILE];
         int live = 0;
         for (int j = 0; j < ORC_TILE; ++j) for (int i = 0; i < ORC_TILE; ++i) {

@@ -28,7 +28,7 @@ class OrcFrame(C.Structure):
                 ("inv_object", C.c_float * 16), ("obj_view", C.c_float * 16),
                 ("cam", C.c_float * 3), ("origin", C.c_float * 3),
                 ("width", C.c_int32), ("height", C.c_int32), ("sh_order", C.c_int32),
-                ("row_rank", C.c_int32), ("row_world", C.c_int32), ("eps_t", C.c_float)]
+                ("row_rank", C.c_int32), ("row_world", C.c_int32), ("row_group", C.c_int32), ("eps_t", C.c_float)]
 
 
 class OrcStats(C.Structure):
@@ -83,7 +83,7 @@ def camera_from_view(view16: np.ndarray) -> np.ndarray:
 
 
 def make_frame(frame, cam, origin, sh_order: int, eps_t: float = 1e-5,
-               row_rank: int = 0, row_world: int = 1) -> OrcFrame:
+               row_rank: int = 0, row_world: int = 1, row_group: int = 1) -> OrcFrame:
     """frame: scene.Frame-like (width,height,view,proj,object,inv_object,obj_view as 16 f32)."""
     f = OrcFrame()
     for name in ("view", "proj", "object", "inv_object", "obj_view"):
@@ -92,7 +92,7 @@ def make_frame(frame, cam, origin, sh_order: int, eps_t: float = 1e-5,
     f.cam[:] = np.asarray(cam, np.float32).tolist()
     f.origin[:] = np.asarray(origin, np.float32).tolist()
     f.width, f.height, f.sh_order = int(frame.width), int(frame.height), int(sh_order)
-    f.row_rank, f.row_world, f.eps_t = int(row_rank), int(row_world), float(eps_t)
+    f.row_rank, f.row_world, f.row_group, f.eps_t = int(row_rank), int(row_world), int(row_group), float(eps_t)
     return f
 
 

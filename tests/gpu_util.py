@@ -5,11 +5,12 @@ from houdini_gsplat_renderer_b200 import renderer as R
 
 
 def gpu_pipeline(cloud, frame, sh_order, eps_t=1e-5, row_rank=0, row_world=1, cap=0, renderer=None,
-                 explicit_cam=None, origin=None, depth_chunks=1):
+                 explicit_cam=None, origin=None, depth_chunks=1, compact=0, row_group=1):
     r = renderer or R.GSplatRenderer(0)
     r.set_option(R.OPT_KEEP_INTERMEDIATES, 1)
     r.set_option(R.OPT_SPLAT_CAP, cap)
     r.set_option(R.OPT_EPS_T, eps_t)
+    r.set_option(R.OPT_COMPACT, compact)
     r.set_option(R.OPT_DEPTH_CHUNKS, depth_chunks)     # 1 = single pass: the fetched tile lists are the full lists
     rid = r.registerUpdate(0x7f00dead0000, (1, 2, 3, 4), 0, cloud, origin=origin)
     r.includeInRenderPass(rid)
@@ -18,7 +19,7 @@ def gpu_pipeline(cloud, frame, sh_order, eps_t=1e-5, row_rank=0, row_world=1, ca
         r.setExplicitCameraPos(explicit_cam)
     r.generateRenderGeometry()
     host = np.zeros((frame.height, frame.width, 4), np.float32)
-    r.render(frame, host_rgba=host, row_rank=row_rank, row_world=row_world)
+    r.render(frame, host_rgba=host, row_rank=row_rank, row_world=row_world, row_group=row_group)
     st = r.stats()
     r.postRender()
     out = dict(stats=st, rgba=host,
@@ -37,8 +38,10 @@ def assert_stage_parity(O, g, o, cloud_n, rgba_tol=2e-5):
     vis = o["vis"] > 0
     assert g["stats"]["n_visible"] == int(vis.sum())
     assert np.array_equal(g["keys"], o["keys"]), "depth keys differ"
-    assert np.array_equal(g["order"].astype(np.int64), o["order"].astype(np.int64)), "depth order differs"
-    assert np.array_equal(g["keys_sorted"], o["keys"][o["order"]])
+    ns = g["order"].shape[0]                       # N, or V when the survivors were compacted (row-partitioned frames)
+    assert ns in (cloud_n, int(vis.sum()))
+    assert np.array_equal(g["order"].astype(np.int64), o["order"][:ns].astype(np.int64)), "depth order differs"
+    assert np.array_equal(g["keys_sorted"], o["keys"][o["order"]][:ns])
     gr, orc = g["rects"], o["rects"]
     assert np.array_equal(gr["x0"] > gr["x1"], ~vis), "cull decisions differ"
     for f in ("x0", "x1", "y0", "y1"):

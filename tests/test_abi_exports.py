@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     from houdini_gsplat_renderer_b200 import renderer as R
     assert C.sizeof(R.PrimKey) == 48
     assert C.sizeof(R.FrameC) == 5 * 64 + 8 * 4
-    assert C.sizeof(R.TargetC) == 24
+    assert C.sizeof(R.TargetC) == 32
     assert R.RECORD_DTYPE.itemsize == 48 and R.RECT_DTYPE.itemsize == 8
     assert C.sizeof(R.StatsC) == 4 * 8 + 10 * 4 + 6 * 4 + 6 * 4
 

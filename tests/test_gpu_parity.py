@@ -36,6 +36,20 @@ def test_stage_parity(oracle, scene, n, w, h, theta, sh, order, mult):
     assert_stage_parity(O, g, o, n)
 
 
+def test_compaction_forced_on_single_rank_is_bit_identical(oracle, scene):
+    """GSB_OPT_COMPACT=1: culled splats are squeezed out before the sort; everything downstream is unchanged."""
+    O, S = oracle, scene
+    cl = S.make_cloud(60_000, 808, sh=True, scale_mult=1.5)
+    cl.pos[::3, 2] += np.float32(4.5)              # a third of the cloud behind the camera -> culled
+    fr, F = _frame(O, S, cl, 400, 226, 5.0, 3)
+    o = O.pipeline(F, cl)
+    g = gpu_pipeline(cl, fr, 3, compact=1)
+    assert g["order"].shape[0] == o["n_visible"] < cl.n
+    assert_stage_parity(O, g, o, cl.n)
+    g2 = gpu_pipeline(cl, fr, 3, compact=2, depth_chunks=4)
+    assert np.array_equal(g["rgba"], g2["rgba"])
+
+
 def test_no_early_out_matches_reference_semantics(oracle, scene):
     """eps_t = 0: full traversal like the reference's ROP blend (no termination)."""
     O, S = oracle, scene
@@ -127,6 +141,34 @@ def test_depth_chunks_leave_the_frame_bit_identical(oracle, scene, chunks):
     c = gpu_pipeline(cl, fr, 3, depth_chunks=chunks, eps_t=0.0)
     d = gpu_pipeline(cl, fr, 3, depth_chunks=1, eps_t=0.0)
     assert np.array_equal(c["rgba"], d["rgba"]) and c["stats"]["n_instances"] == d["stats"]["n_instances"]
+
+
+def test_final_frame_target_receives_finished_tiles(scene):
+    """gsb_target.final_rgba (the multi-GPU hand-off: peer memory in production, a second local buffer here):
+    every finished tile lands there, bit-identical to the ordinary frame, for 1 and 4 depth chunks and for shards."""
+    from houdini_gsplat_renderer_b200 import renderer as R
+    S = scene
+    cl = S.make_cloud(120_000, 515, sh=True, scale_mult=2.0)
+    fr = S.orbit_frame(360, 200, 75.0)
+    r = R.GSplatRenderer(0)
+    rid = r.registerUpdate(7, (1, 0, 0, 0), 0, cl); r.setSphericalHarmonicsOrder(3)
+    ref = np.zeros((200, 360, 4), np.float32)
+    r.draw([rid], fr, host_rgba=ref)
+    handle, shared = r.ipc_export_frame(360, 200)
+    assert len(handle) == 64 and shared != 0
+    for chunks in (1, 4):
+        r.set_option(R.OPT_DEPTH_CHUNKS, chunks)
+        got = np.full_like(ref, -1.0)
+        r.draw([rid], fr, final_rgba=shared)
+        r.copy_to_host(shared, got)
+        assert np.array_equal(got, ref)
+    # two shards writing into the same final frame reassemble it without any combine pass
+    r.copy_to_host(shared, got)  # (dirty from the previous frame on purpose: every pixel is overwritten)
+    for rk in range(2):
+        r.draw([rid], fr, final_rgba=shared, row_rank=rk, row_world=2, row_group=2)
+    r.copy_to_host(shared, got)
+    assert np.array_equal(got, ref)
+    r.close()
 
 
 def test_full_size_properties_1M_1080p(scene):

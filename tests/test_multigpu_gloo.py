@@ -24,8 +24,9 @@ def _worker(rank, world, port, q):
     cl = S.make_cloud(4000, 77, sh=True, scale_mult=2.0)
     fr = S.orbit_frame(168, 100, 40.0)               # ragged: 7 tile rows, last one 4 px tall
     cam = O.camera_from_view(fr.view)
-    mine = O.pipeline(O.make_frame(fr, cam, cl.barycentre(), 3, row_rank=rank, row_world=world), cl)
-    rows = M.owned_scanlines(fr.height, rank, world)
+    group = 2 if world == 2 else 1
+    mine = O.pipeline(O.make_frame(fr, cam, cl.barycentre(), 3, row_rank=rank, row_world=world, row_group=group), cl)
+    rows = M.owned_scanlines(fr.height, rank, world, group)
     assert not mine["rgba"][~rows].any()             # un-owned scanlines stay zero
     fb = torch.from_numpy(mine["rgba"].copy())
     M.combine_on_root(fb, rank, world)
@@ -52,10 +53,11 @@ def test_tile_row_shards_combine_exactly(world):
 
 def test_row_ownership_partitions_the_frame():
     from houdini_gsplat_renderer_b200 import multigpu as M
-    for h, world in [(1080, 8), (100, 3), (16, 4), (4320, 8)]:
+    for h, world, group in [(1080, 8, 1), (100, 3, 2), (16, 4, 1), (4320, 8, 4), (2160, 2, 8)]:
         cover = np.zeros(h, int)
         rows = []
         for r in range(world):
-            cover += M.owned_scanlines(h, r, world)
-            rows += M.owned_tile_rows(h, r, world)
+            cover += M.owned_scanlines(h, r, world, group)
+            rows += M.owned_tile_rows(h, r, world, group)
         assert np.all(cover == 1) and sorted(rows) == list(range((h + 15) // 16))
+    assert M.default_row_group(4320, 8) == 4 and M.default_row_group(1080, 8) == 1 and M.default_row_group(1080, 2) == 4
