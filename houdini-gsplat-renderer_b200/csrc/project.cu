@@ -134,6 +134,28 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
 
     const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
     const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
+
+    // Conservative pre-cull for row-partitioned frames (multi-GPU): every rank projects every splat, but most splats
+    // touch none of its tile rows.  Upper bound of the vertical half-extent without the covariance chain:
+    //   hy <= 2.3541 * sqrt(2 * (C11 + 0.4)),  C11 <= |J_y|^2 |V3|^2 |O3|^2 |R|^2 smax^2,  |J_y|^2 <= (f/tz)^2 (1 + limY^2),
+    //   |R(q)|_2 <= |1 - |q|^2| + |q|^2  (R(q) = (1 - s) I + s R(q/|q|), s = |q|^2), alpha <= 1 so sqrt(pmax) <= 2.3541.
+    // precull_k = f^2 (1 + limY^2) |V3|_2^2 |O3|_2^2 with a safety factor (host).  Only ever rejects splats whose exact
+    // rectangle would be rejected by the ownership test below, so cull decisions stay bit-identical (asserted by the
+    // shard parity tests); any non-finite intermediate falls through to the exact path.
+    if (F.precull_k > 0.0f && alpha <= 1.0f) {
+        const float tzp = ((MAT(F.view, 2, 0) * psx[0] + MAT(F.view, 2, 1) * psx[1]) + MAT(F.view, 2, 2) * psx[2]) + MAT(F.view, 2, 3);
+        const float s = (qx * qx + qy * qy) + (qz * qz + qr * qr);
+        const float rn = fabsf(1.0f - s) + s;
+        const float sm = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fabsf(sz)) * rn;
+        const float c11b = (F.precull_k / (tzp * tzp)) * (sm * sm);
+        const float eb = 2.3541f * sqrtf(2.0f * (c11b + 0.4f)) * 1.002f + 0.05f;
+        const float lo = floorf(((cy - eb) - 0.5f) * (1.0f / (float)TILE)), hi = floorf(((cy + eb) - 0.5f) * (1.0f / (float)TILE));
+        if (eb < 1.0e6f && lo >= -4.0f && hi <= 70000.0f && hi - lo < 4096.0f) {     // finite, sane (NaN fails the compares)
+            bool any = false;
+            for (int tyy = max((int)lo, 0); tyy <= (int)hi && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
+            if (!any) return false;
+        }
+    }
     float Rt[3][3];
     Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
     Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);

@@ -171,6 +171,39 @@ def test_final_frame_target_receives_finished_tiles(scene):
     r.close()
 
 
+@pytest.mark.parametrize("case", ["aniso", "objmat", "bigsplats", "closeup"])
+def test_precull_never_changes_a_cull_decision(oracle, scene, case):
+    """The cheap pre-cull of row-partitioned frames must be conservative: per shard, the visible set, rectangles,
+    records, order, tile lists and frame equal the oracle's (which has no pre-cull), across nasty geometry."""
+    from houdini_gsplat_renderer_b200 import renderer as R
+    O, S = oracle, scene
+    rng = np.random.default_rng(5)
+    cl = S.make_cloud(30_000, 909, sh=False, scale_mult=2.0)
+    obj = np.eye(4); theta = 25.0; w, h, world, group = 300, 420, 4, 1
+    if case == "aniso":
+        cl.scale_h[:, 1] = (cl.scale_h[:, 1].astype(np.float32) * 12).astype(np.float16)       # needles
+        cl.orient_h[:] = (cl.orient_h.astype(np.float32) * rng.uniform(0.8, 1.25, (cl.n, 1))).astype(np.float16)  # |q| != 1
+    elif case == "objmat":
+        a = 0.7
+        obj[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) @ np.diag([1.3, 0.7, 1.1])
+        obj[:3, 3] = [0.1, 0.05, -0.1]
+    elif case == "bigsplats":
+        cl.scale_h[::7] = np.float16(0.6); world, group = 3, 2
+    elif case == "closeup":
+        theta = 0.0; cl.pos[:, 2] = cl.pos[:, 2] * np.float32(0.2) + np.float32(2.6); world = 5  # just in front of the camera
+    base = S.orbit_frame(w, h, theta)
+    fr = S.Frame(w, h, base.view, base.proj, S.colmajor(obj), S.colmajor(np.linalg.inv(obj)))
+    cam = O.camera_from_view(fr.view)
+    nvis_pre = nvis_nopre = 0
+    for rk in range(world):
+        F = O.make_frame(fr, cam, cl.barycentre(), 0, row_rank=rk, row_world=world, row_group=group)
+        o = O.pipeline(F, cl)
+        g = gpu_pipeline(cl, fr, 0, row_rank=rk, row_world=world, row_group=group)
+        assert_stage_parity(O, g, o, cl.n)
+        nvis_pre += g["stats"]["n_visible"]
+    assert nvis_pre > 0
+
+
 def test_full_size_properties_1M_1080p(scene):
     """BASELINE config 2 size (1M splats, SH 0, 1080p) through size-independent properties: sorted keys,
     order is a permutation, tile lists are depth ordered, ranges partition D, alpha in [0,1], idempotence."""
