@@ -24,7 +24,6 @@ struct FrameConsts {
     int   row_rank, row_world;  // tile-row ownership: row ty is owned iff (ty / row_group) % row_world == row_rank
     int   row_group;
     float eps_t;                // transmittance early-out threshold
-    float precull_k;            // row-partitioned frames: variance bound factor of the conservative pre-cull (0 = off)
 };
 
 // 2-D record written by project and gathered by blend: 48 bytes, three 16-byte chunks.

@@ -135,27 +135,6 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
     const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
 
-    // Conservative pre-cull for row-partitioned frames (multi-GPU): every rank projects every splat, but most splats
-    // touch none of its tile rows.  Upper bound of the vertical half-extent without the covariance chain:
-    //   hy <= 2.3541 * sqrt(2 * (C11 + 0.4)),  C11 <= |J_y|^2 |V3|^2 |O3|^2 |R|^2 smax^2,  |J_y|^2 <= (f/tz)^2 (1 + limY^2),
-    //   |R(q)|_2 <= |1 - |q|^2| + |q|^2  (R(q) = (1 - s) I + s R(q/|q|), s = |q|^2), alpha <= 1 so sqrt(pmax) <= 2.3541.
-    // precull_k = f^2 (1 + limY^2) |V3|_2^2 |O3|_2^2 with a safety factor (host).  Only ever rejects splats whose exact
-    // rectangle would be rejected by the ownership test below, so cull decisions stay bit-identical (asserted by the
-    // shard parity tests); any non-finite intermediate falls through to the exact path.
-    if (F.precull_k > 0.0f && alpha <= 1.0f) {
-        const float tzp = ((MAT(F.view, 2, 0) * psx[0] + MAT(F.view, 2, 1) * psx[1]) + MAT(F.view, 2, 2) * psx[2]) + MAT(F.view, 2, 3);
-        const float s = (qx * qx + qy * qy) + (qz * qz + qr * qr);
-        const float rn = fabsf(1.0f - s) + s;
-        const float sm = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fabsf(sz)) * rn;
-        const float c11b = (F.precull_k / (tzp * tzp)) * (sm * sm);
-        const float eb = 2.3541f * sqrtf(2.0f * (c11b + 0.4f)) * 1.002f + 0.05f;
-        const float lo = floorf(((cy - eb) - 0.5f) * (1.0f / (float)TILE)), hi = floorf(((cy + eb) - 0.5f) * (1.0f / (float)TILE));
-        if (eb < 1.0e6f && lo >= -4.0f && hi <= 70000.0f && hi - lo < 4096.0f) {     // finite, sane (NaN fails the compares)
-            bool any = false;
-            for (int tyy = max((int)lo, 0); tyy <= (int)hi && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
-            if (!any) return false;
-        }
-    }
     float Rt[3][3];
     Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
     Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
@@ -312,8 +291,31 @@ __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedS
     }
 }
 
-// ---- K1: one thread per submitted splat.  Everything is a coalesced stream (random-sector gathers of a lazy
-// per-emitted-splat variant measured slower on B200: r01, 3.75 vs 3.42 ms/frame).
+// per-splat tail of K1: colour, key, rectangle, record (splat i is known to be visible)
+template <int ORDER>
+__device__ __forceinline__ void emit_visible(const FrameConsts& F, const PackedSplats& ps, const int64_t i, const float p[3],
+                                             const float alpha, const Geom& g, uint32_t* __restrict__ keys,
+                                             uint2* __restrict__ rects, Record* __restrict__ recs)
+{
+    float rgb[3];
+    shade_colour<ORDER>(F, ps, i, g.psx, rgb);
+    // depth key on the UNMODIFIED position (R.C:196-202, 454, 584)
+    const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    keys[i] = __float_as_uint(d2);
+    rects[i] = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
+    const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
+                           ((uint32_t)__half_as_ushort(__float2half_ru(g.hy)) << 16);
+    float4* out = reinterpret_cast<float4*>(recs + i);
+    out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
+    out[1] = make_float4(g.m10, g.m11, alpha, g.pmax);
+    out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
+}
+
+// ---- K1: one thread per submitted splat.  Everything is a coalesced stream.  Two sparser variants were measured on
+// B200 in r01 and rejected: (1) lazy records + SH only for emitted splats (random 32-byte-sector gathers: 3.75 vs 3.42
+// ms/frame); (2) for multi-GPU shards, a conservative pre-cull with in-CTA compaction of the ~30 % candidates (fewer
+// instructions, but sparse reads of the 16-byte colour planes still touch ~80 % of the 64-byte DRAM blocks: no gain).
 template <int ORDER>
 __global__ void __launch_bounds__(256)
 project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps, int64_t n,
@@ -329,27 +331,10 @@ project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ Pa
         const float p[3] = { ga.x, ga.y, ga.z };
         Geom g;
         vis = project_geom(F, p, ga.w, gb, g);
-        uint32_t key = KEY_CULLED;
-        uint2 rect = make_uint2(1u, 1u);          // x0=1,x1=0,y0=1,y1=0 : empty
-        if (vis) {
-            float rgb[3];
-            shade_colour<ORDER>(F, ps, i, g.psx, rgb);
-            // depth key on the UNMODIFIED position (R.C:196-202, 454, 584)
-            const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
-            const float d2 = dx * dx + dy * dy + dz * dz;
-            key = __float_as_uint(d2);
-            rect = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
-            const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
-                                   ((uint32_t)__half_as_ushort(__float2half_ru(g.hy)) << 16);
-            float4* out = reinterpret_cast<float4*>(recs + i);
-            out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
-            out[1] = make_float4(g.m10, g.m11, ga.w, g.pmax);
-            out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
-        }
-        keys[i] = key;
         vals[i] = (uint32_t)i;
-        rects[i] = rect;
-        if (vis_flags) vis_flags[i] = vis ? 1u : 0u;         // input of the survivor compaction (multi-GPU shards)
+        if (vis) emit_visible<ORDER>(F, ps, i, p, ga.w, g, keys, rects, recs);
+        else { keys[i] = KEY_CULLED; rects[i] = make_uint2(1u, 1u); }      // x0=1,x1=0,y0=1,y1=0 : empty
+        if (vis_flags) vis_flags[i] = vis ? 1u : 0u;         // input of the survivor compaction
     }
     const unsigned m = __ballot_sync(0xffffffffu, vis);      // one atomic per warp for V
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_visible, (unsigned long long)__popc(m));

@@ -100,7 +100,6 @@ struct gsb_context {
     float   eps_t = 1e-5f;
     bool    stage_timing = false, keep_intermediates = false;
     int     depth_chunks = 0;                                 // 0 = auto
-    bool    precull = true;                                   // conservative pre-cull on row-partitioned frames
     int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
@@ -159,36 +158,6 @@ void camera_from_view(const float view[16], float cam[3])
 }
 
 int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
-
-// upper bound (tight) of the squared spectral norm of the upper-left 3x3 of a column-major 4x4: largest eigenvalue of
-// M^T M by cyclic Jacobi in double, closed with a Gershgorin bound
-double spectral_norm2_3x3(const float m[16])
-{
-    double a[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        a[i][j] = 0.0;
-        for (int k = 0; k < 3; ++k) a[i][j] += (double)m[i * 4 + k] * (double)m[j * 4 + k];   // (M^T M)_ij = col_i . col_j
-    }
-    for (int sweep = 0; sweep < 32; ++sweep) {
-        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        if (off < 1e-30) break;
-        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
-            if (std::fabs(a[p][q]) < 1e-300) continue;
-            double th = 0.5 * std::atan2(2.0 * a[p][q], a[q][q] - a[p][p]);
-            double c = std::cos(th), sn = std::sin(th);
-            for (int k = 0; k < 3; ++k) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq; }
-            for (int k = 0; k < 3; ++k) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk; }
-        }
-    }
-    // Gershgorin on the (nearly diagonal) rotated matrix: a rigorous upper bound whether or not Jacobi converged
-    double best = 0.0;
-    for (int i = 0; i < 3; ++i) {
-        double r = a[i][i];
-        for (int j = 0; j < 3; ++j) if (j != i) r += std::fabs(a[i][j]);
-        best = std::max(best, r);
-    }
-    return best;
-}
 
 }  // namespace
 
@@ -269,7 +238,6 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
         ctx->eps_t = (float)value; return GSB_OK;
     case GSB_OPT_STAGE_TIMING: ctx->stage_timing = value != 0; return GSB_OK;
     case GSB_OPT_KEEP_INTERMEDIATES: ctx->keep_intermediates = value != 0; return GSB_OK;
-    case GSB_OPT_PRECULL: ctx->precull = value != 0; return GSB_OK;
     case GSB_OPT_COMPACT:
         if (value < 0 || value > 2) return fail(GSB_ERR_INVALID, "GSB_OPT_COMPACT must be 0 (auto), 1 (always) or 2 (never)");
         ctx->compact_mode = (int)value; return GSB_OK;
@@ -489,16 +457,6 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     fc.sh_order = do_sh ? std::min(ctx->sh_order, 3) : 0;
     fc.row_rank = fr->row_rank; fc.row_world = fr->row_world; fc.row_group = fr->row_group > 1 ? fr->row_group : 1;
     fc.eps_t = ctx->eps_t;
-    fc.precull_k = 0.0f;
-    if (fr->row_world > 1 && ctx->precull) {
-        // same fp32 expressions as project_geom for limY and focal, then a bound with a relative safety margin
-        const float P00 = fr->proj[0], P11 = fr->proj[5];
-        const float aspect = P00 / P11, tanFovY = 1.0f / (P11 * aspect), limY = 1.3f * tanFovY;
-        const float focal = (fc.W * P00) / 2.0f;
-        const double k = (double)focal * focal * (1.0 + (double)limY * limY) * spectral_norm2_3x3(fr->view) *
-                         spectral_norm2_3x3(fr->object) * 1.01;
-        if (std::isfinite(k) && k > 0.0 && k < 1e30) fc.precull_k = (float)k;
-    }
     const int num_tiles = fc.tiles_x * fc.tiles_y;
     const int64_t n = ctx->splat_count;
     const size_t  N = (size_t)n;

@@ -107,7 +107,6 @@ enum gsb_option {
     GSB_OPT_EPS_T = 2,           /* transmittance early-out threshold; default 1e-5; 0 = never stop (reference) */
     GSB_OPT_STAGE_TIMING = 3,    /* record per-stage CUDA events (default 0) */
     GSB_OPT_KEEP_INTERMEDIATES = 4, /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
-    GSB_OPT_PRECULL = 7,         /* conservative cheap cull before the full projection on row-partitioned frames (default 1) */
     GSB_OPT_COMPACT = 6,         /* compact surviving splats before the depth sort: 0 = auto (row-partitioned frames), 1, 2 = never */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */

@@ -172,9 +172,9 @@ def test_final_frame_target_receives_finished_tiles(scene):
 
 
 @pytest.mark.parametrize("case", ["aniso", "objmat", "bigsplats", "closeup"])
-def test_precull_never_changes_a_cull_decision(oracle, scene, case):
-    """The cheap pre-cull of row-partitioned frames must be conservative: per shard, the visible set, rectangles,
-    records, order, tile lists and frame equal the oracle's (which has no pre-cull), across nasty geometry."""
+def test_shards_match_oracle_on_nasty_geometry(oracle, scene, case):
+    """Row-partitioned shards (cull by owned rows, survivor compaction) on needles with |q| != 1, a non-rigid object
+    matrix, screen-filling splats and a close-up: every stage equals the oracle's shard bit for bit."""
     from houdini_gsplat_renderer_b200 import renderer as R
     O, S = oracle, scene
     rng = np.random.default_rng(5)
