@@ -89,6 +89,16 @@ void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
                         cudaStream_t s);
 
+// ingest.cu: raw fp32 point attributes -> the arrays registerUpdate receives (NULL source = default)
+void launch_ingest_core(const float* P, const float* Cd, const float* alpha, const float* scale, const float* orient,
+                        int64_t n, float* pos_out, uint16_t* cd_out, float* alpha_out, uint16_t* scale_out,
+                        uint16_t* orient_out, cudaStream_t s);
+// src = [n][len][3] (planar = 0, `sh_coefficients`) or [15][n][3] (planar = 1, `sh1`..`sh15`)
+void launch_ingest_sh_vec3(const float* src, int64_t n, int len, int planar, uint16_t* shx, uint16_t* shy, uint16_t* shz,
+                           cudaStream_t s);
+// rest = [45][n] (`f_rest_0`..`f_rest_44`)
+void launch_ingest_sh_rest(const float* rest, int64_t n, uint16_t* shx, uint16_t* shy, uint16_t* shz, cudaStream_t s);
+
 // blend.cu
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
 // chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done;

@@ -313,6 +313,131 @@ int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat
     return GSB_OK;
 }
 
+// ------------------------------------------------------------------ GR_PrimGsplat::update, GR.C:191-458 (SURVEY f-1)
+int gsb_update_from_attributes(gsb_context* ctx, const gsb_prim_key* key, const gsb_raw_attributes* a, gsb_update_result* out)
+{
+    if (!ctx || !key || !a || !out) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: NULL argument");
+    if (a->count < 0 || a->count > 0x3fffffffLL) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: bad count");
+    if (a->count > 0 && !a->P) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: P is required");
+    CU(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof *out);
+    const size_t n = (size_t)a->count;
+    cudaStream_t s = ctx->stream;
+
+    // which SH encoding: sh_coefficients, else sh1..sh15, else f_rest_0..44 (GR.C:145-189); an encoding counts only if complete
+    int sh_kind = 0;
+    if (a->sh_coefficients && a->sh_coefficients_len > 0) sh_kind = 1;
+    if (!sh_kind) { bool all = true; for (int j = 0; j < 15; ++j) all = all && a->sh[j]; if (all) sh_kind = 2; }
+    if (!sh_kind) { bool all = true; for (int j = 0; j < 45; ++j) all = all && a->f_rest[j]; if (all) sh_kind = 3; }
+    const bool sh_found = sh_kind != 0 && n > 0;
+
+    // barycentre + bounding box on the host (sequential fp32 sum, GEO_GSplat.C:338-351: the order of additions matters)
+    float sum[3] = { 0, 0, 0 }, lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+    bool finite = n > 0;
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = a->P[3 * i + k];
+            sum[k] += v;
+            finite = finite && std::isfinite(v);
+            if (i == 0) { lo[k] = hi[k] = v; } else { lo[k] = v < lo[k] ? v : lo[k]; hi[k] = v > hi[k] ? v : hi[k]; }
+        }
+    float bary[3] = { 0, 0, 0 };
+    if (n > 0) { const float fn = (float)a->count; for (int k = 0; k < 3; ++k) bary[k] = sum[k] / fn; }
+
+    const std::string id = make_id(*key);
+    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {          // same eviction as registerUpdate
+        Entry& e = *it->second;
+        if (e.gdp == key->gdp && memcmp(e.version, key->version, sizeof e.version) != 0) it = ctx->registry.erase(it);
+        else ++it;
+    }
+    auto& slot = ctx->registry[id];
+    if (!slot) slot.reset(new Entry);
+    Entry& e = *slot;
+    e.gdp = key->gdp; e.vtx0 = key->vtx0; memcpy(e.version, key->version, sizeof e.version);
+    e.count = a->count; memcpy(e.origin, bary, sizeof bary);
+    e.active = false; e.age = -1; e.age_since_last_active = -1;
+    e.has_sh = sh_found;
+    e.bbox_valid = finite;
+    for (int k = 0; k < 3; ++k) { e.bbox[k] = lo[k]; e.bbox[3 + k] = hi[k]; }
+
+    // raw fp32 -> device staging, then quantise on the GPU
+    DevBuf dP, dCd, dA, dS, dO, dSH;
+    int rc;
+    const float* alpha_src = a->Alpha ? a->Alpha : a->opacity;                     // Alpha wins when both exist (GR.C:246-257)
+    if ((rc = upload(dP, a->P, n * 12, s))) return rc;
+    if (a->Cd && (rc = upload(dCd, a->Cd, n * 12, s))) return rc;
+    if (alpha_src && (rc = upload(dA, alpha_src, n * 4, s))) return rc;
+    if (a->scale && (rc = upload(dS, a->scale, n * 12, s))) return rc;
+    if (a->orient && (rc = upload(dO, a->orient, n * 16, s))) return rc;
+    CU(e.pos.ensure(n * 12 + 16)); CU(e.cd.ensure(n * 6 + 16)); CU(e.alpha.ensure(n * 4 + 16));
+    CU(e.scale.ensure(n * 6 + 16)); CU(e.orient.ensure(n * 8 + 16));
+    launch_ingest_core(dP.as<float>(), a->Cd ? dCd.as<float>() : nullptr, alpha_src ? dA.as<float>() : nullptr,
+                       a->scale ? dS.as<float>() : nullptr, a->orient ? dO.as<float>() : nullptr, a->count,
+                       e.pos.as<float>(), e.cd.as<uint16_t>(), e.alpha.as<float>(), e.scale.as<uint16_t>(), e.orient.as<uint16_t>(), s);
+    if (sh_found) {
+        CU(e.shx.ensure(n * 32)); CU(e.shy.ensure(n * 32)); CU(e.shz.ensure(n * 32));
+        if (sh_kind == 1) {
+            const size_t len = (size_t)a->sh_coefficients_len;
+            if ((rc = upload(dSH, a->sh_coefficients, n * len * 12, s))) return rc;
+            launch_ingest_sh_vec3(dSH.as<float>(), a->count, (int)len, 0, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
+        } else if (sh_kind == 2) {
+            CU(dSH.ensure(n * 15 * 12));
+            for (int j = 0; j < 15; ++j)
+                CU(cudaMemcpyAsync(dSH.as<char>() + (size_t)j * n * 12, a->sh[j], n * 12, cudaMemcpyHostToDevice, s));
+            launch_ingest_sh_vec3(dSH.as<float>(), a->count, 15, 1, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
+        } else {
+            CU(dSH.ensure(n * 45 * 4));
+            for (int j = 0; j < 45; ++j)
+                CU(cudaMemcpyAsync(dSH.as<char>() + (size_t)j * n * 4, a->f_rest[j], n * 4, cudaMemcpyHostToDevice, s));
+            launch_ingest_sh_rest(dSH.as<float>(), a->count, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));          // staging buffers die here; the caller's arrays are not borrowed
+    ctx->active_set.erase(id);
+
+    strncpy(out->id, id.c_str(), GSB_ID_MAX - 1);
+    out->sh_data_found = sh_found ? 1 : 0;
+    out->sh_order = 3;                                                             // GR.C:444
+    if (a->has_sh_order) {
+        out->sh_order = a->sh_order;
+        if (a->sh_order < 0 || a->sh_order > 3) { out->sh_order = 0; out->sh_order_invalid = 1; }   // GR.C:447-452
+    }
+    out->set_explicit_camera = a->has_explicit_camera ? 1 : 0;
+    memcpy(out->explicit_camera, a->explicit_camera, 12);
+    memcpy(out->barycentre, bary, 12);
+    return GSB_OK;
+}
+
+int gsb_debug_fetch_entry(gsb_context* ctx, const char* id, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed)
+{
+    if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
+    auto it = ctx->registry.find(id);
+    if (it == ctx->registry.end()) return fail(GSB_ERR_NOT_FOUND, "gsb_debug_fetch_entry: unknown id");
+    const Entry& e = *it->second;
+    const uint64_t n = (uint64_t)e.count;
+    const void* src = nullptr; uint64_t need = 0;
+    switch (which) {
+    case GSB_ENT_POS: src = e.pos.p; need = n * 12; break;
+    case GSB_ENT_CD: src = e.cd.p; need = n * 6; break;
+    case GSB_ENT_ALPHA: src = e.alpha.p; need = n * 4; break;
+    case GSB_ENT_SCALE: src = e.scale.p; need = n * 6; break;
+    case GSB_ENT_ORIENT: src = e.orient.p; need = n * 8; break;
+    case GSB_ENT_SHX: src = e.shx.p; need = e.has_sh ? n * 32 : 0; break;
+    case GSB_ENT_SHY: src = e.shy.p; need = e.has_sh ? n * 32 : 0; break;
+    case GSB_ENT_SHZ: src = e.shz.p; need = e.has_sh ? n * 32 : 0; break;
+    default: return fail(GSB_ERR_INVALID, "gsb_debug_fetch_entry: unknown array");
+    }
+    if (bytes_needed) *bytes_needed = need;
+    if (dst && need) {
+        if (dst_bytes < need) return fail(GSB_ERR_INVALID, "gsb_debug_fetch_entry: destination too small");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    }
+    return GSB_OK;
+}
+
 int gsb_include_in_render_pass(gsb_context* ctx, const char* id)      // R.C:313-320
 {
     if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");

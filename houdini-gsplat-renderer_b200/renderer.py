@@ -35,7 +35,8 @@ EXPORTS = ["gsb_abi_version", "gsb_create", "gsb_destroy", "gsb_last_error", "gs
            "gsb_set_explicit_camera_pos", "gsb_set_spherical_harmonics_order", "gsb_set_option",
            "gsb_get_stats", "gsb_set_stream", "gsb_synchronize", "gsb_device_framebuffer",
            "gsb_registry_size", "gsb_debug_fetch", "gsb_debug_sort_pairs", "gsb_debug_exclusive_scan",
-           "gsb_ipc_export_frame", "gsb_ipc_open", "gsb_ipc_close", "gsb_copy_to_host"]
+           "gsb_ipc_export_frame", "gsb_ipc_open", "gsb_ipc_close", "gsb_copy_to_host",
+           "gsb_update_from_attributes", "gsb_debug_fetch_entry"]
 
 
 class GsbError(RuntimeError):
@@ -57,6 +58,21 @@ class FrameC(C.Structure):
 class TargetC(C.Structure):
     _fields_ = [("device_rgba", C.c_void_p), ("host_rgba", C.c_void_p),
                 ("gl_texture", C.c_uint32), ("flags", C.c_uint32), ("final_rgba", C.c_void_p)]
+
+
+class RawAttributesC(C.Structure):
+    _fields_ = [("count", C.c_int64), ("P", C.c_void_p), ("Cd", C.c_void_p), ("opacity", C.c_void_p), ("Alpha", C.c_void_p),
+                ("scale", C.c_void_p), ("orient", C.c_void_p), ("sh_coefficients", C.c_void_p),
+                ("sh_coefficients_len", C.c_int32), ("reserved0", C.c_int32),
+                ("sh", C.c_void_p * 15), ("f_rest", C.c_void_p * 45),
+                ("has_sh_order", C.c_int32), ("sh_order", C.c_int32), ("has_explicit_camera", C.c_int32),
+                ("explicit_camera", C.c_float * 3)]
+
+
+class UpdateResultC(C.Structure):
+    _fields_ = [("id", C.c_char * ID_MAX), ("sh_order", C.c_int32), ("sh_order_invalid", C.c_int32),
+                ("sh_data_found", C.c_int32), ("set_explicit_camera", C.c_int32),
+                ("explicit_camera", C.c_float * 3), ("barycentre", C.c_float * 3)]
 
 
 class StatsC(C.Structure):
@@ -105,6 +121,8 @@ def load_library() -> C.CDLL:
         lib.gsb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         lib.gsb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.gsb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.gsb_update_from_attributes.argtypes = [C.c_void_p, C.POINTER(PrimKey), C.POINTER(RawAttributesC), C.POINTER(UpdateResultC)]
+        lib.gsb_debug_fetch_entry.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = lib
     return _lib
 
@@ -166,6 +184,59 @@ class GSplatRenderer:
         self._ck(self._lib.gsb_register_update(self._h, C.byref(key), int(cloud.n), _ptr(origin),
                                                *[_ptr(a) for a in arrs], out), "gsb_register_update")
         return out.value.decode()
+
+    def update(self, gdp: int, gversion, gvtx: int, attrs: dict) -> dict:
+        """GR_PrimGsplat::update (GR_GSplat.C:191-458) on the GPU: ``attrs`` maps Houdini attribute names to fp32 numpy
+        arrays (P, Cd, opacity, Alpha, scale, orient, sh_coefficients | sh1..sh15 | f_rest_0..f_rest_44) plus the detail
+        attributes gsplat__sh_order (int) and gsplat__explicit_camera_pos (3 floats).  Returns what update() leaves
+        for render(): id, sh_order, explicit camera, barycentre."""
+        key = PrimKey(int(gdp), int(gvtx), (C.c_int64 * 4)(*[int(v) for v in gversion]))
+        keep = []
+
+        def arr(name, shape_tail):
+            a = attrs.get(name)
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            assert a.shape[1:] == shape_tail, (name, a.shape)
+            keep.append(a)
+            return a.ctypes.data
+
+        P = np.ascontiguousarray(attrs["P"], np.float32); keep.append(P)
+        ra = RawAttributesC()
+        ra.count = P.shape[0]; ra.P = P.ctypes.data
+        ra.Cd = arr("Cd", (3,)); ra.opacity = arr("opacity", ()); ra.Alpha = arr("Alpha", ())
+        ra.scale = arr("scale", (3,)); ra.orient = arr("orient", (4,))
+        shc = attrs.get("sh_coefficients")
+        if shc is not None:
+            shc = np.ascontiguousarray(shc, np.float32); keep.append(shc)
+            ra.sh_coefficients = shc.ctypes.data; ra.sh_coefficients_len = shc.shape[1]
+        for j in range(15):
+            ra.sh[j] = arr(f"sh{j + 1}", (3,))
+        for j in range(45):
+            ra.f_rest[j] = arr(f"f_rest_{j}", ())
+        if "gsplat__sh_order" in attrs:
+            ra.has_sh_order = 1; ra.sh_order = int(attrs["gsplat__sh_order"])
+        if "gsplat__explicit_camera_pos" in attrs:
+            ra.has_explicit_camera = 1
+            ra.explicit_camera[:] = [float(v) for v in attrs["gsplat__explicit_camera_pos"]]
+        out = UpdateResultC()
+        self._ck(self._lib.gsb_update_from_attributes(self._h, C.byref(key), C.byref(ra), C.byref(out)),
+                 "gsb_update_from_attributes")
+        return dict(id=out.id.decode(), sh_order=out.sh_order, sh_order_invalid=bool(out.sh_order_invalid),
+                    sh_data_found=bool(out.sh_data_found), set_explicit_camera=bool(out.set_explicit_camera),
+                    explicit_camera=np.array(out.explicit_camera[:], np.float32),
+                    barycentre=np.array(out.barycentre[:], np.float32))
+
+    def fetch_entry(self, registry_id: str, which: int) -> np.ndarray:
+        need = C.c_uint64(0)
+        self._ck(self._lib.gsb_debug_fetch_entry(self._h, registry_id.encode(), which, None, 0, C.byref(need)), "gsb_debug_fetch_entry")
+        dt = np.float32 if which in (0, 2) else np.uint16
+        out = np.zeros(need.value // np.dtype(dt).itemsize, dt)
+        if need.value:
+            self._ck(self._lib.gsb_debug_fetch_entry(self._h, registry_id.encode(), which, _ptr(out), need.value, C.byref(need)),
+                     "gsb_debug_fetch_entry")
+        return out
 
     def includeInRenderPass(self, registry_id: str):
         self._ck(self._lib.gsb_include_in_render_pass(self._h, registry_id.encode()), "gsb_include_in_render_pass")

@@ -157,6 +157,43 @@ GSB_API int gsb_set_rendering_enabled(gsb_context* ctx, int enabled);           
 GSB_API int gsb_set_explicit_camera_pos(gsb_context* ctx, const float pos[3]);         /* R.C:685-689 */
 GSB_API int gsb_set_spherical_harmonics_order(gsb_context* ctx, int sh_order);         /* R.C:691-694 */
 
+/* ---- caller side of the boundary: GR_PrimGsplat::update (src/GR_GSplat.C:191-458), SURVEY.md §8 f-1 ------- */
+
+/* Raw fp32 point attributes of one GSplat primitive, as Houdini stores them.  NULL = attribute absent. */
+typedef struct gsb_raw_attributes {
+    int64_t      count;                /* points of the prim (vertex i <-> point i, GEO_GSplat.C:413-431) */
+    const float* P;                    /* [count][3]  required */
+    const float* Cd;                   /* [count][3]  absent -> (0,0,0)            GR.C:309 */
+    const float* opacity;              /* [count]                                   GR.C:240 */
+    const float* Alpha;                /* [count]     preferred over opacity when both exist; neither -> 1   GR.C:241-257,310 */
+    const float* scale;                /* [count][3]  absent -> (1,1,1)            GR.C:311 */
+    const float* orient;               /* [count][4]  (x,y,z,w), absent -> (0,0,0,1)  GR.C:312 */
+    const float* sh_coefficients;      /* [count][sh_coefficients_len][3]  vec3-array attribute, tried first  GR.C:93-113 */
+    int32_t      sh_coefficients_len;  /* vec3 entries per point; entries >= 15 are ignored */
+    int32_t      reserved0;
+    const float* sh[15];               /* sh1..sh15, each [count][3]; used if sh_coefficients is absent and all 15 exist  GR.C:115-128,160-171 */
+    const float* f_rest[45];           /* f_rest_0..44, each [count]; used last, all 45 must exist; coefficient j = (f_rest_j, f_rest_j+15, f_rest_j+30)  GR.C:130-143,173-184,357-366 */
+    int32_t      has_sh_order;         /* detail attribute gsplat__sh_order present  GR.C:284-289 */
+    int32_t      sh_order;
+    int32_t      has_explicit_camera;  /* detail attribute gsplat__explicit_camera_pos present  GR.C:277-282 */
+    float        explicit_camera[3];
+} gsb_raw_attributes;
+
+/* What update() leaves in the GR primitive for its render() to push every pass (GR.C:438-457, 485-492). */
+typedef struct gsb_update_result {
+    char    id[GSB_ID_MAX];            /* registry id (same text as registerUpdate's) */
+    int32_t sh_order;                  /* 3 by default; attribute value if in 0..3; 0 (and an error logged) otherwise */
+    int32_t sh_order_invalid;          /* 1 if gsplat__sh_order was outside 0..3 */
+    int32_t sh_data_found;             /* 1 if one of the three SH encodings was complete */
+    int32_t set_explicit_camera;
+    float   explicit_camera[3];
+    float   barycentre[3];             /* GEO_PrimGsplat::baryCenter: sequential fp32 sum / count (GEO_GSplat.C:338-351) */
+} gsb_update_result;
+
+/* GR_PrimGsplat::update: extracts + quantises on the GPU and registers the prim (as registerUpdate would). */
+GSB_API int gsb_update_from_attributes(gsb_context* ctx, const gsb_prim_key* key, const gsb_raw_attributes* attrs,
+                                       gsb_update_result* out);
+
 /* ---- additions the reference has no equivalent for -------------------------------------- */
 GSB_API int   gsb_set_option(gsb_context* ctx, int option, double value);
 GSB_API int   gsb_get_stats(gsb_context* ctx, gsb_stats* out);
@@ -173,6 +210,11 @@ GSB_API int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height
 GSB_API int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYTES], void** peer_ptr_out);
 GSB_API int gsb_ipc_close(gsb_context* ctx, void* peer_ptr);
 GSB_API int gsb_copy_to_host(gsb_context* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes);  /* stream-ordered, synchronous */
+
+/* Test hook: the arrays a registered prim holds (what registerUpdate received / update quantised). */
+enum gsb_entry_array { GSB_ENT_POS = 0, GSB_ENT_CD = 1, GSB_ENT_ALPHA = 2, GSB_ENT_SCALE = 3, GSB_ENT_ORIENT = 4,
+                       GSB_ENT_SHX = 5, GSB_ENT_SHY = 6, GSB_ENT_SHZ = 7 };
+GSB_API int gsb_debug_fetch_entry(gsb_context* ctx, const char* id, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed);
 
 /* Test hooks: copy an intermediate device buffer to the host.  *bytes_needed is always set;
  * the copy happens only if dst != NULL and dst_bytes >= needed. */
