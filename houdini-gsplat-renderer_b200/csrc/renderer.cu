@@ -22,6 +22,11 @@
 
 using namespace gsb;
 
+// CUDA<->OpenGL interop entry point of the CUDA runtime (cuda_gl_interop.h needs <GL/gl.h>, which this image does not
+// have; the symbol itself lives in libcudart and only needs a current GL context at run time, i.e. inside Houdini).
+extern "C" cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource** resource, unsigned int image,
+                                                   unsigned int target, unsigned int flags);
+
 namespace {
 
 thread_local std::string g_err = "";
@@ -108,6 +113,8 @@ struct gsb_context {
 
     // per-frame device buffers
     DevBuf keys[2], vals[2], keys_unsorted, recs, rects, rects_sorted, counts, ikeys[2], ivals[2], ranges, tile_consumed, tile_done, fb;
+    struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
+    uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
     unsigned long long* counters_h = nullptr;        // pinned mirror
@@ -200,6 +207,7 @@ int gsb_destroy(gsb_context* ctx)
     if (!ctx) return GSB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->gl_res) cudaGraphicsUnregisterResource(ctx->gl_res);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) for (int j = 0; j < 3; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
@@ -565,8 +573,6 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     if (fr->row_world < 1 || fr->row_rank < 0 || fr->row_rank >= fr->row_world)
         return fail(GSB_ERR_INVALID, "gsb_render: bad tile-row partition");
     if (fr->row_group < 0) return fail(GSB_ERR_INVALID, "gsb_render: row_group must be >= 0");
-    if (target && target->gl_texture != 0)
-        return fail(GSB_ERR_INVALID, "gsb_render: this build has no OpenGL; CUDA<->GL interop target unavailable");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
 
@@ -732,6 +738,24 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
         CU(cudaStreamSynchronize(s));
     } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
+    if (target && target->gl_texture != 0) {
+        // hand the frame to the viewport without a host round trip: device->device copy into the mapped
+        // RGBA32F texture; the shim then draws it with the reference's blend state (R.C:613-621).  Needs a current GL context.
+        if (ctx->gl_res && (ctx->gl_tex != target->gl_texture || ctx->gl_w != fr->width || ctx->gl_h != fr->height)) {
+            cudaGraphicsUnregisterResource(ctx->gl_res); ctx->gl_res = nullptr;
+        }
+        if (!ctx->gl_res) {
+            CU(cudaGraphicsGLRegisterImage(&ctx->gl_res, target->gl_texture, 0x0DE1u /* GL_TEXTURE_2D */,
+                                           cudaGraphicsRegisterFlagsWriteDiscard));
+            ctx->gl_tex = target->gl_texture; ctx->gl_w = fr->width; ctx->gl_h = fr->height;
+        }
+        cudaArray_t arr = nullptr;
+        CU(cudaGraphicsMapResources(1, &ctx->gl_res, s));
+        CU(cudaGraphicsSubResourceGetMappedArray(&arr, ctx->gl_res, 0, 0));
+        CU(cudaMemcpy2DToArrayAsync(arr, 0, 0, fb_final, (size_t)fr->width * 16, (size_t)fr->width * 16, (size_t)fr->height,
+                                    cudaMemcpyDeviceToDevice, s));
+        CU(cudaGraphicsUnmapResources(1, &ctx->gl_res, s));
+    }
     ctx->ev_valid = tm;
 
     ctx->last_n = n; ctx->last_sorted = n_sort; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;

@@ -74,7 +74,9 @@ typedef struct gsb_frame {
 typedef struct gsb_target {
     void*    device_rgba;    /* caller-owned device buffer, width*height*16 bytes; NULL = library buffer */
     void*    host_rgba;      /* if non-NULL the frame is copied here (D2H inside the call, call returns when done) */
-    uint32_t gl_texture;     /* CUDA<->GL interop target (RGBA32F GL_TEXTURE_2D); must be 0 in builds without GL */
+    uint32_t gl_texture;     /* CUDA<->GL interop target: an RGBA32F GL_TEXTURE_2D of the frame size; the frame is copied into it
+                                device->device (cudaGraphicsGLRegisterImage).  Needs a current GL context on the calling thread
+                                (Houdini's main thread); without one the call fails with GSB_ERR_CUDA.  0 = none */
     uint32_t flags;          /* reserved, 0 */
     void*    final_rgba;     /* optional: finished tiles are stored HERE instead of device_rgba (which then only holds the
                                 per-chunk blend state).  May be PEER memory of another GPU (gsb_ipc_open): the blend kernel

@@ -91,4 +91,14 @@ def test_bad_arguments_return_errors_not_crashes(scene):
         r.render(bad)
     with pytest.raises(R.GsbError):
         r.set_option(99, 1.0)
+    # CUDA<->GL hand-back without a GL context (this box has no OpenGL): a reported error, not a crash; the context
+    # stays usable afterwards
+    import ctypes as C
+    fc = R.frame_to_c(fr); t = R.TargetC(None, None, 1234, 0, None)
+    r.includeInRenderPass(rid)
+    rc = r._lib.gsb_render(r._h, C.byref(fc), C.byref(t))
+    assert rc != 0 and b"cudaGraphicsGLRegisterImage" in r._lib.gsb_last_error()
+    host = np.zeros((72, 128, 4), np.float32)
+    r.draw([rid], fr, host_rgba=host)
+    assert r.stats()["rendered"] == 1
     r.close()
