@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-A step = one full frame of the hot path (project+SH+key -> depth radix sort -> tile binning -> blend) over
+A step = one full frame of the hot path (cull+key -> depth-chunk partition -> per chunk: live-splat depth sort, records+SH,
+tile binning, blend) over
 the synthetic cloud of SURVEY.md §8d.  Default workload: the north-star target, 20 M splats, SH degree 3,
 1920x1080, one B200 (fits one GPU: 2.6 GB of attributes).  Prints ONE JSON line (rank 0).
 
@@ -256,8 +257,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(K, to_host, collect):
-        acc = {k: 0.0 for k in ("ms_project", "ms_sort", "ms_bin", "ms_blend", "ms_copy")}
-        cnt = {"n_visible": 0, "n_instances": 0, "n_consumed": 0, "launches": 0, "depth_chunks": 0}
+        acc = {k: 0.0 for k in ("ms_project", "ms_sort", "ms_records", "ms_bin", "ms_blend", "ms_copy")}
+        cnt = {"n_visible": 0, "n_instances": 0, "n_consumed": 0, "n_live": 0, "launches": 0, "depth_chunks": 0}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -315,18 +316,31 @@ def run_ours(args):
         return
 
     peak, peak_src = peaks()
-    V, D, Dc = cnt["n_visible"] / K, cnt["n_instances"] / K, cnt["n_consumed"] / K
-    # algorithmic (compulsory) bytes per frame, SURVEY.md §8d formulas; R = 48-byte record; counters from gsb_stats.
-    # N is replicated on every rank (each rank culls all splats), V/D/D_c are summed over ranks.
+    V, D, Dc, L = cnt["n_visible"] / K, cnt["n_instances"] / K, cnt["n_consumed"] / K, cnt["n_live"] / K
+    # algorithmic (compulsory) bytes per frame: what each stage must read and write once, with the per-unit figures of
+    # SURVEY.md §8d (30 B cull read per submitted splat, 6+SH colour bytes and R = 48-byte record per splat that gets one,
+    # 4+R per consumed instance); counters from gsb_stats.  N is replicated on every rank (each rank culls all splats);
+    # V, L (splats that reach a live tile), D, D_c are summed over ranks.
     sh_bytes = {0: 0, 1: 18, 2: 48, 3: 90}[sh_order]
-    tile_passes = max(1, -(-max(1, (((W + 15) // 16) * ((H + 15) // 16) - 1).bit_length()) // 8))
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    tile_passes = max(1, -(-max(1, (tiles - 1).bit_length()) // 8))
+    key_passes = 3                                        # 25 significant key bits at these camera distances: 9+8+8
+    Nw = N * world
     stage_bytes = {
-        "project": N * world * 30 + V * (6 + sh_bytes) + V * (4 + 4 + RECORD_BYTES + 4),
-        "sort": 68 * V,                                   # 32-bit key + 32-bit payload, 4 passes of 8 bits
-        "bin": V * 8 + D * 8 + tile_passes * D * 16 + ((W + 15) // 16) * ((H + 15) // 16) * 8,
+        # K1: cull-phase read + (key, index, packed tile rectangle) written for every submitted splat
+        "project": Nw * 30 + Nw * 12,
+        # chunk partition (12 B read + 12 B written per splat) + live selection (tile-rect read, flag write, flag scan
+        # read/read/write, compaction reads flag+position) + compaction and LSD sort of the L live (key, index, rect) triples
+        "sort": Nw * 24 + Nw * (4 + 4 + 12 + 8) + L * 24 + L * (4 + key_passes * 24),
+        # K2: index + 30 B geometry + colour/SH read, record written, per live splat
+        "records": L * (4 + 30 + 6 + sh_bytes) + L * RECORD_BYTES,
+        # K4: counts (rect read, count write, scan), emit (offset + rect + index read, 8 B per instance written), stable tile
+        # partition (histogram read + passes x 16 B), tile ranges (tile id read, table write)
+        "bin": L * (8 + 12 + 12) + D * 8 + D * 4 + tile_passes * D * 16 + D * 4 + tiles * 8,
         "blend": Dc * (4 + RECORD_BYTES) + (W * H * 16),
     }
-    stage_ms = {"project": acc["ms_project"] / K, "sort": acc["ms_sort"] / K, "bin": acc["ms_bin"] / K, "blend": acc["ms_blend"] / K}
+    stage_ms = {"project": acc["ms_project"] / K, "sort": acc["ms_sort"] / K, "records": acc["ms_records"] / K,
+                "bin": acc["ms_bin"] / K, "blend": acc["ms_blend"] / K}
     stages = {k: {"ms": stage_ms[k], "algorithmic_bytes": stage_bytes[k],
                   "achieved_GBps": stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None,
                   "frac_of_peak": stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 / peak if stage_ms[k] > 0 else None}
@@ -340,7 +354,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "splats": N, "sh_degree": sh_order, "width": W, "height": H,
                    "camera": "orbit 1 deg/frame" if w["orbit"] else "static", "tile": 16, "eps_t": 1e-5,
                    "splat_cap": "lifted (reference caps at 8388607)", "parallelism": f"tile-row bands of {row_group} x16 px interleaved over {world} GPU(s)",
-                   "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (N * 128 / 1e9),
+                   "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (N * 160 / 1e9),
                    "full_pipeline_every_frame": True, "depth_chunks": cnt["depth_chunks"] / K / world},
         "e2e": {"value": e2e_val, "unit": "Msplats/s", "fps": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 352, "d2h_bytes_per_step": frame_bytes,
@@ -353,7 +367,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": stage_bytes["blend"], "ms_per_launch": stage_ms["blend"],
                      "formula": "D_c*(4+48) + W*H*16"},
         "stages": stages,
-        "counters_per_frame": {"N": N, "V": V, "D": D, "D_c": Dc},
+        "counters_per_frame": {"N": N, "V": V, "L": L, "D": D, "D_c": Dc},
         "clocks": clocks,
         "combine": (args.combine if world > 1 else None), "verify": verify,
         "scene_gen_s": gen_s,

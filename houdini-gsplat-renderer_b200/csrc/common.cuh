@@ -35,15 +35,39 @@ struct __align__(16) Record {
 };
 static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
 
-// Packed, render-layout splat attributes (built by pack on active-set change):
-//   geomA[i] = (p.x, p.y, p.z, alpha)                         16 B
-//   geomB[i] = (scale h3 | orient h4 (x,y,z,w) | pad h1)      16 B
-//   col[k][i], k = 0..5: 48 halfs = Cd(3) then SH coefficient j channel c at 3+3j+c   6 x 16 B
-// Degree d needs halfs [0, 3 + 3*{0,3,8,15}) -> planes {1,2,4,6}.
+// Packed, render-layout splat attributes (built by pack on active-set change).  Two copies of the geometry:
+//   streamed by K1 (every splat, every frame), SoA planes:
+//     geomA[i] = (p.x, p.y, p.z, alpha)                         16 B
+//     geomB[i] = (scale h3 | orient h4 (x,y,z,w) | pad h1)      16 B
+//   gathered by K2 (only the splats that reach a live tile), one 128-byte line per splat:
+//     rows[8*i + 0] = geomA bits, rows[8*i + 1] = geomB,
+//     rows[8*i + 2 + k], k = 0..5: 48 halfs = Cd(3) then SH coefficient j channel c at 3+3j+c
+//   Degree d needs halfs [0, 3 + 3*{0,3,8,15}) -> colour chunks {1,2,4,6} of the line.
+constexpr int ROW_U4 = 8;                      // uint4 per splat line
 struct PackedSplats {
     const float4* geomA;
     const uint4*  geomB;
-    const uint4*  col[6];
+    const uint4*  rows;
+};
+
+// Depth buckets: a monotone (non-decreasing) map from the depth key to [0, DEPTH_BUCKETS-2], linear in the distance;
+// culled splats (KEY_CULLED) take the last bucket.  Used to cut the depth order into chunks without sorting it: every
+// step (sqrt, subtract, scale, clamp, truncate) is monotone in fp32, so bucket boundaries are key boundaries.
+constexpr int DEPTH_BUCKETS = 512;
+constexpr int MAX_CHUNKS    = 16;
+struct DepthBuckets { float dmin, scale; };
+__device__ __forceinline__ uint32_t depth_bucket(uint32_t key, DepthBuckets db)
+{
+    if (key == KEY_CULLED) return (uint32_t)(DEPTH_BUCKETS - 1);
+    float t = (sqrtf(__uint_as_float(key)) - db.dmin) * db.scale;
+    t = fminf(fmaxf(t, 0.0f), (float)(DEPTH_BUCKETS - 2));
+    return (uint32_t)t;
+}
+// Chunk plan chosen on the device from the bucket histogram (choose_chunks), mirrored to the host.
+struct ChunkPlan {
+    uint32_t size[MAX_CHUNKS + 1];             // splats per chunk; entry nchunks = culled
+    uint32_t base[32];                         // exclusive scan of size (digit bases of the partition pass, 32 bins)
+    uint8_t  lut[DEPTH_BUCKETS];               // bucket -> chunk
 };
 
 // radix sort / scan primitives (radix_sort.cu, scan.cu)
@@ -55,39 +79,63 @@ size_t   sort_scratch_bytes(size_t n);
 // Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit).  Ping-pongs between
 // (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).  n must be < 2^30.
 // *error_flag (device, may be NULL) is set to 1 if a bounded look-back spin ever times out.
-// If gather_src != NULL the last pass also writes gather_dst[sorted position] = gather_src[value] (8-byte items).
+// aux0/aux1 (optional): a second 32-bit payload that rides along, ping-ponging like the values.
 int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
                           int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
-                          const uint2* gather_src = nullptr, uint2* gather_dst = nullptr,
+                          uint32_t* aux0 = nullptr, uint32_t* aux1 = nullptr,
                           uint32_t key_min = 0u, uint32_t key_span = 0xFFFFFFFFu);
 // The sort orders by min(key - key_min, key_span) (order-preserving for keys in [key_min, key_min + key_span),
 // everything above collapses onto key_span); pass end_bit = sort_key_bits(key_span) to sort only the bits that vary.
 int      sort_key_bits(uint32_t key_span);
 
+// Stable partition of (key, val, aux) triples into depth chunks: digit = plan->lut[depth_bucket(key)] (<= 32 bins), one
+// onesweep pass.  plan->base holds the bins' global offsets.  aux may be NULL.
+void     partition_by_chunk(const uint32_t* k_in, const uint32_t* v_in, const uint32_t* a_in,
+                            uint32_t* k_out, uint32_t* v_out, uint32_t* a_out, size_t n, DepthBuckets db,
+                            const ChunkPlan* plan, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches);
+// exclusive scan of the flags (in[i] != 0); *total_dev = number of non-zero entries
+void     exclusive_scan_flags_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
+                                  unsigned long long* total_dev, cudaStream_t s, int* launches);
+
 // project.cu
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
-                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
-                 int planes, cudaStream_t s);
-// K1: keys (culled -> KEY_CULLED), vals = splat index, rects (x0>x1 = culled), records, *n_visible += V
-// vis_flags (may be NULL): 1/0 per splat, the input of launch_compact's scan
+                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* rows, int has_sh, cudaStream_t s);
+// K1 (every submitted splat): cull, depth key (culled -> KEY_CULLED), vals = splat index, packed tile rectangle
+// (trects, may be NULL), exact pixel rectangle (rects: every splat if rects_all, else only the "wide" ones the packed
+// form cannot hold), *n_visible += V, and (bucket_hist != NULL) the DEPTH_BUCKETS-bin histogram of depth_bucket(key).
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
-                    uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
-                    unsigned long long* n_visible, uint32_t* vis_flags, cudaStream_t s);
-// order-preserving compaction of the surviving (key, index) pairs; positions = exclusive scan of vis_flags
-void launch_compact(const uint32_t* keys, const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
-                    cudaStream_t s);
+                    uint32_t* keys, uint32_t* vals, uint2* rects, int rects_all, uint32_t* trects,
+                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
+// chunk plan from the bucket histogram: chunk c ends at the first bucket whose exclusive count reaches
+// V * (2^(c+1) - 1) / 2^nchunks (geometric: every chunk doubles the covered share of the depth order)
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, ChunkPlan* plan, cudaStream_t s);
+// K2 (only splats that reach a live tile, in depth order): gather the splat's 128-byte line, redo the projection,
+// evaluate SH, write the 48-byte record of live rank j to recs[j]
+void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
+                    Record* recs, cudaStream_t s);
 
 // binning.cu
-// ranks [r0, r0+n) of the depth order; rects_sorted in depth order; tile_done (may be NULL) = saturation flags
-void launch_tile_counts(const uint2* rects_sorted, int64_t r0, int64_t n, FrameConsts fc,
-                        const uint32_t* tile_done, uint32_t* counts, cudaStream_t s);
+// counts[k] = live tiles touched by element r0 + k of (trects, order); trects = packed tile rectangles aligned with
+// order (NULL: read the exact rectangle rects[order[r]], which "wide" entries always do); tile_done (may be NULL) =
+// saturation flags; *d_total += sum of the counts
+void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
+                        FrameConsts fc, const uint32_t* tile_done, uint32_t* counts, unsigned long long* d_total,
+                        cudaStream_t s);
+// order-preserving compaction of the elements with counts[k] != 0 (positions = exclusive scan of those flags)
+void launch_compact_live(const uint32_t* keys, const uint32_t* vals, const uint32_t* trects, const uint32_t* counts,
+                         const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
+                         uint32_t* trects_out, cudaStream_t s);
+// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending;
 // offsets = exclusive scan of the tile counts, *total = its grand total (device)
-void launch_emit(const uint32_t* order, const uint2* rects_sorted, const uint32_t* offsets,
-                 const unsigned long long* total, int64_t r0, int64_t n, FrameConsts fc, const uint32_t* tile_done,
+void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,
+                 const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
                         cudaStream_t s);
+// debug views (GSB_OPT_KEEP_INTERMEDIATES): records by splat index, instances as splat indices
+void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,
+                        const uint32_t* inst_refs, uint64_t d, uint32_t* inst_splats, cudaStream_t s);
 
 // ingest.cu: raw fp32 point attributes -> the arrays registerUpdate receives (NULL source = default)
 void launch_ingest_core(const float* P, const float* Cd, const float* alpha, const float* scale, const float* orient,
@@ -106,6 +154,16 @@ void launch_ingest_sh_rest(const float* rest, int64_t n, uint16_t* shx, uint16_t
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
                   unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s);
+
+// Packed tile rectangle carried through the depth sort: tx0:9 | ty0:9 | (tx1-tx0):7 | (ty1-ty0):7.  Extents of 127 tiles
+// or more saturate to 127 = "wide: read the exact pixel rectangle by splat index".  0xFFFFFFFF = culled.
+// Valid while the screen has at most 512 x 512 tiles (8192 px); larger screens use the exact rectangles only.
+constexpr uint32_t TRECT_CULLED = 0xFFFFFFFFu;
+__host__ __device__ __forceinline__ uint32_t pack_trect(int tx0, int tx1, int ty0, int ty1)
+{
+    const int w = tx1 - tx0, h = ty1 - ty0;
+    return (uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(w > 127 ? 127 : w) << 18) | ((uint32_t)(h > 127 ? 127 : h) << 25);
+}
 
 // tile-row ownership rule shared by every kernel
 __host__ __device__ __forceinline__ bool owns_row(int ty, int rank, int world, int group)

@@ -1,4 +1,5 @@
-// project.cu — K0 pack (active-set change) and K1 project + SH + depth key (every frame), sm_100a.
+// project.cu — K0 pack (active-set change), K1 cull + depth key + tile rectangle (every splat, every frame) and
+// K2 record + SH colour (only splats that reach a live tile), sm_100a.
 //
 // K0 replaces the CPU texture packing of GSplatRenderer::generateRenderGeometry
 //    (/root/reference/gsplat_plugin/src/GSplatRenderer.C:448-505): the per-prim SoA arrays that
@@ -12,7 +13,9 @@
 // The fp32 expression order below IS the spec and matches oracle/gsplat_oracle.cpp
 // operation for operation: this TU is compiled with -fmad=false, IEEE division and sqrt
 // (-prec-div=true -prec-sqrt=true, no fast-math), so keys, records and rectangles are bit-exact.
-// HBM-bound: 32 B read per submitted splat, +16..96 B colour per visible splat, 64 B written.
+// HBM-bound.  K1 streams 32 B per submitted splat and writes 12 B (key, index, packed tile rectangle); K2 gathers one
+// 128-byte line per live splat and writes its 48-byte record, so colour / SH / record traffic is proportional to the
+// splats that can still change a pixel (3 M of 20 M at 20 M / 1080p), not to the cloud.
 #include "common.cuh"
 
 namespace gsb {
@@ -56,19 +59,22 @@ pack_kernel(const float* __restrict__ pos, const uint16_t* __restrict__ cd, cons
             const uint16_t* __restrict__ scale, const uint16_t* __restrict__ orient,
             const uint16_t* __restrict__ shx, const uint16_t* __restrict__ shy, const uint16_t* __restrict__ shz,
             int64_t count, int64_t dst, float4* __restrict__ geomA, uint4* __restrict__ geomB,
-            uint4* __restrict__ c0, uint4* __restrict__ c1, uint4* __restrict__ c2,
-            uint4* __restrict__ c3, uint4* __restrict__ c4, uint4* __restrict__ c5, int planes)
+            uint4* __restrict__ rows, int has_sh)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const int64_t o = dst + i;
-    geomA[o] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], alpha[i]);
+    const float4 ga = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], alpha[i]);
     uint32_t s0 = scale[3 * i], s1 = scale[3 * i + 1], s2 = scale[3 * i + 2];
     uint32_t q0 = orient[4 * i], q1 = orient[4 * i + 1], q2 = orient[4 * i + 2], q3 = orient[4 * i + 3];
-    geomB[o] = make_uint4(s0 | (s1 << 16), s2 | (q0 << 16), q1 | (q2 << 16), q3);
+    const uint4 gb = make_uint4(s0 | (s1 << 16), s2 | (q0 << 16), q1 | (q2 << 16), q3);
+    geomA[o] = ga; geomB[o] = gb;
+    uint4* row = rows + o * ROW_U4;
+    row[0] = make_uint4(__float_as_uint(ga.x), __float_as_uint(ga.y), __float_as_uint(ga.z), __float_as_uint(ga.w));
+    row[1] = gb;
     uint16_t h[48];
     h[0] = cd[3 * i]; h[1] = cd[3 * i + 1]; h[2] = cd[3 * i + 2];
-    if (planes > 1) {
+    if (has_sh) {
 #pragma unroll
         for (int j = 0; j < 15; ++j) {
             h[3 + 3 * j] = shx[16 * i + j]; h[4 + 3 * j] = shy[16 * i + j]; h[5 + 3 * j] = shz[16 * i + j];
@@ -77,17 +83,14 @@ pack_kernel(const float* __restrict__ pos, const uint16_t* __restrict__ cd, cons
 #pragma unroll
         for (int j = 3; j < 48; ++j) h[j] = 0;
     }
-    uint4* cp[6] = { c0, c1, c2, c3, c4, c5 };
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
-        if (p < planes) {
-            uint4 w;
-            w.x = (uint32_t)h[8 * p + 0] | ((uint32_t)h[8 * p + 1] << 16);
-            w.y = (uint32_t)h[8 * p + 2] | ((uint32_t)h[8 * p + 3] << 16);
-            w.z = (uint32_t)h[8 * p + 4] | ((uint32_t)h[8 * p + 5] << 16);
-            w.w = (uint32_t)h[8 * p + 6] | ((uint32_t)h[8 * p + 7] << 16);
-            cp[p][o] = w;
-        }
+        uint4 w;
+        w.x = (uint32_t)h[8 * p + 0] | ((uint32_t)h[8 * p + 1] << 16);
+        w.y = (uint32_t)h[8 * p + 2] | ((uint32_t)h[8 * p + 3] << 16);
+        w.z = (uint32_t)h[8 * p + 4] | ((uint32_t)h[8 * p + 5] << 16);
+        w.w = (uint32_t)h[8 * p + 6] | ((uint32_t)h[8 * p + 7] << 16);
+        row[2 + p] = w;
     }
 }
 
@@ -239,7 +242,8 @@ template <int ORDER>
 __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedSplats& ps, const int64_t i,
                                              const float psx[3], float rgb[3])
 {
-    const uint4 c0 = __ldg(ps.col[0] + i);
+    const uint4* row = ps.rows + i * ROW_U4 + 2;
+    const uint4 c0 = __ldg(row);
     rgb[0] = lo_h(c0.x); rgb[1] = hi_h(c0.x); rgb[2] = lo_h(c0.y);
     if (ORDER > 0) {
         // 48 halfs: Cd(3) then coefficient j channel ch at 3 + 3j + ch
@@ -248,7 +252,7 @@ __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedS
         constexpr int PLANES = ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6);
 #pragma unroll
         for (int pl = 1; pl < PLANES; ++pl) {
-            const uint4 cc = __ldg(ps.col[pl] + i);
+            const uint4 cc = __ldg(row + pl);
             w[4 * pl] = cc.x; w[4 * pl + 1] = cc.y; w[4 * pl + 2] = cc.z; w[4 * pl + 3] = cc.w;
         }
         const float wv[3] = { psx[0] - F.cam[0], psx[1] - F.cam[1], psx[2] - F.cam[2] };
@@ -291,100 +295,174 @@ __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedS
     }
 }
 
-// per-splat tail of K1: colour, key, rectangle, record (splat i is known to be visible)
-template <int ORDER>
-__device__ __forceinline__ void emit_visible(const FrameConsts& F, const PackedSplats& ps, const int64_t i, const float p[3],
-                                             const float alpha, const Geom& g, uint32_t* __restrict__ keys,
-                                             uint2* __restrict__ rects, Record* __restrict__ recs)
+// ---- K1: persistent CTAs, grid-stride over the submitted splats; everything is a coalesced stream.
+// Per splat: cull + projection (project_geom), depth key on the UNMODIFIED position (R.C:196-202, 454, 584), packed tile
+// rectangle.  The colour, the SH evaluation and the 48-byte record are NOT produced here: with per-pixel early-out only
+// a small share of the cloud is ever blended, so they are built later (K2) for the splats that reach a live tile.
+// The CTA also histograms depth_bucket(key) in shared memory (one flush per CTA) for the chunk plan.
+constexpr int K1_THREADS = 256;
+__global__ void __launch_bounds__(K1_THREADS)
+project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA, const uint4* __restrict__ geomB,
+               int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ rects,
+               const int rects_all, uint32_t* __restrict__ trects, unsigned long long* __restrict__ n_visible,
+               const DepthBuckets db, uint32_t* __restrict__ bucket_hist)
 {
+    __shared__ uint32_t sh_hist[DEPTH_BUCKETS];
+    if (bucket_hist) {
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) sh_hist[b] = 0u;
+        __syncthreads();
+    }
+    uint32_t nvis = 0;
+    const int64_t stride = (int64_t)gridDim.x * K1_THREADS;
+    int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
+    float4 ga_next = make_float4(0.f, 0.f, 0.f, 0.f); uint4 gb_next = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n) { ga_next = __ldg(geomA + i); gb_next = __ldg(geomB + i); }
+    for (; i < n; i += stride) {
+        const float4 ga = ga_next;
+        const uint4  gb = gb_next;
+        if (i + stride < n) { ga_next = __ldg(geomA + i + stride); gb_next = __ldg(geomB + i + stride); }   // prefetch
+        const float p[3] = { ga.x, ga.y, ga.z };
+        Geom g;
+        const bool vis = project_geom(F, p, ga.w, gb, g);
+        uint32_t key = KEY_CULLED, tr = TRECT_CULLED;
+        uint2 rect = make_uint2(1u, 1u);                     // x0=1,x1=0,y0=1,y1=0 : empty
+        bool wide = false;
+        if (vis) {
+            const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
+            key = __float_as_uint(dx * dx + dy * dy + dz * dz);
+            const int tx0 = g.x0 / TILE, tx1 = g.x1 / TILE, ty0 = g.y0 / TILE, ty1 = g.y1 / TILE;
+            tr = pack_trect(tx0, tx1, ty0, ty1);
+            wide = (tx1 - tx0 >= 127) || (ty1 - ty0 >= 127);
+            rect = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
+            ++nvis;
+        }
+        keys[i] = key; vals[i] = (uint32_t)i;
+        if (trects) trects[i] = tr;
+        if (rects_all || wide) rects[i] = rect;
+        if (bucket_hist) atomicAdd(&sh_hist[depth_bucket(key, db)], 1u);
+    }
+    nvis = __reduce_add_sync(0xffffffffu, nvis);             // one atomic per warp for V
+    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(n_visible, (unsigned long long)nvis);
+    if (bucket_hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) {
+            const uint32_t c = sh_hist[b];
+            if (c) atomicAdd(bucket_hist + b, c);
+        }
+    }
+}
+
+// ---- chunk plan: one CTA of DEPTH_BUCKETS threads
+__global__ void __launch_bounds__(DEPTH_BUCKETS)
+choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, ChunkPlan* __restrict__ plan)
+{
+    __shared__ uint32_t wtot[DEPTH_BUCKETS / 32];
+    __shared__ uint32_t csize[MAX_CHUNKS + 1];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    if (b <= MAX_CHUNKS) csize[b] = 0u;
+    const uint32_t mine = (b < DEPTH_BUCKETS - 1) ? hist[b] : 0u;       // the last bucket holds the culled splats
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, V = 0;
+#pragma unroll
+    for (int w = 0; w < DEPTH_BUCKETS / 32; ++w) { woff += (w < warp) ? wtot[w] : 0u; V += wtot[w]; }
+    const uint32_t excl = woff + inc - mine;                            // visible splats in nearer buckets
+    int chunk = 0;
+    for (int c = 1; c < nchunks; ++c) {
+        const uint32_t target = (uint32_t)(((unsigned long long)V * ((1ull << c) - 1ull)) >> nchunks);
+        if (excl >= target && target > 0u) ++chunk;                     // thresholds ascend with c: monotone in b
+    }
+    if (b == DEPTH_BUCKETS - 1) chunk = nchunks;
+    plan->lut[b] = (uint8_t)chunk;
+    const uint32_t cnt = (b == DEPTH_BUCKETS - 1) ? hist[b] : mine;
+    if (cnt) atomicAdd(&csize[chunk], cnt);
+    __syncthreads();
+    if (b == 0) {
+        uint32_t run = 0;
+        for (int c = 0; c < 32; ++c) {
+            plan->base[c] = run;
+            if (c <= MAX_CHUNKS) { const uint32_t sz = (c <= nchunks) ? csize[c] : 0u; plan->size[c] = sz; run += sz; }
+        }
+    }
+}
+
+// ---- K2: one thread per live splat, in depth order.  The splat's whole 128-byte line (geometry + colour + SH) is
+// one DRAM burst pair; the projection is redone with the same code as K1 (same bits), the record goes to recs[j].
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+records_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps,
+               const uint32_t* __restrict__ live_splats, const int64_t n_live, Record* __restrict__ recs)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_live) return;
+    const int64_t i = (int64_t)__ldg(live_splats + j);
+    const uint4* row = ps.rows + i * ROW_U4;
+    const uint4 ra = __ldg(row);
+    const uint4 gb = __ldg(row + 1);
+    const float p[3] = { __uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z) };
+    const float alpha = __uint_as_float(ra.w);
+    Geom g;
+    float4* out = reinterpret_cast<float4*>(recs + j);
+    if (!project_geom(F, p, alpha, gb, g)) {                 // cannot happen (K1 kept it); an inert record if it did
+        out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
+        out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     float rgb[3];
     shade_colour<ORDER>(F, ps, i, g.psx, rgb);
-    // depth key on the UNMODIFIED position (R.C:196-202, 454, 584)
-    const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
-    const float d2 = dx * dx + dy * dy + dz * dz;
-    keys[i] = __float_as_uint(d2);
-    rects[i] = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
     const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
                            ((uint32_t)__half_as_ushort(__float2half_ru(g.hy)) << 16);
-    float4* out = reinterpret_cast<float4*>(recs + i);
     out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
     out[1] = make_float4(g.m10, g.m11, alpha, g.pmax);
     out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
-}
-
-// ---- K1: one thread per submitted splat.  Everything is a coalesced stream.  Two sparser variants were measured on
-// B200 in r01 and rejected: (1) lazy records + SH only for emitted splats (random 32-byte-sector gathers: 3.75 vs 3.42
-// ms/frame); (2) for multi-GPU shards, a conservative pre-cull with in-CTA compaction of the ~30 % candidates (fewer
-// instructions, but sparse reads of the 16-byte colour planes still touch ~80 % of the 64-byte DRAM blocks: no gain).
-template <int ORDER>
-__global__ void __launch_bounds__(256)
-project_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps, int64_t n,
-               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, Record* __restrict__ recs,
-               uint2* __restrict__ rects, unsigned long long* __restrict__ n_visible,
-               uint32_t* __restrict__ vis_flags)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool vis = false;
-    if (i < n) {
-        const float4 ga = __ldg(ps.geomA + i);
-        const uint4  gb = __ldg(ps.geomB + i);
-        const float p[3] = { ga.x, ga.y, ga.z };
-        Geom g;
-        vis = project_geom(F, p, ga.w, gb, g);
-        vals[i] = (uint32_t)i;
-        if (vis) emit_visible<ORDER>(F, ps, i, p, ga.w, g, keys, rects, recs);
-        else { keys[i] = KEY_CULLED; rects[i] = make_uint2(1u, 1u); }      // x0=1,x1=0,y0=1,y1=0 : empty
-        if (vis_flags) vis_flags[i] = vis ? 1u : 0u;         // input of the survivor compaction
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, vis);      // one atomic per warp for V
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_visible, (unsigned long long)__popc(m));
 }
 
 }  // namespace
 
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
-                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* const col[6],
-                 int planes, cudaStream_t s)
+                 int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* rows, int has_sh, cudaStream_t s)
 {
     if (count <= 0) return;
     unsigned grid = (unsigned)((count + 255) / 256);
     pack_kernel<<<grid, 256, 0, s>>>(pos, cd_h, alpha, scale_h, orient_h, shx, shy, shz, count, dst_offset,
-                                     geomA, geomB, col[0], col[1], col[2], col[3], col[4], col[5], planes);
+                                     geomA, geomB, rows, has_sh);
 }
 
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
-                    uint32_t* keys, uint32_t* vals, Record* recs, uint2* rects,
-                    unsigned long long* n_visible, uint32_t* vis_flags, cudaStream_t s)
+                    uint32_t* keys, uint32_t* vals, uint2* rects, int rects_all, uint32_t* trects,
+                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s)
 {
     if (n <= 0) return;
-    unsigned grid = (unsigned)((n + 255) / 256);
-    switch (fc.sh_order) {
-    case 0:  project_kernel<0><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
-    case 1:  project_kernel<1><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
-    case 2:  project_kernel<2><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
-    default: project_kernel<3><<<grid, 256, 0, s>>>(fc, ps, n, keys, vals, recs, rects, n_visible, vis_flags); break;
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel, K1_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     }
+    const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    project_kernel<<<grid, K1_THREADS, 0, s>>>(fc, ps.geomA, ps.geomB, n, keys, vals, rects, rects_all, trects, n_visible,
+                                               db, bucket_hist);
 }
 
-namespace {
-// survivors keep their relative (index) order: positions = exclusive scan of the visibility flags
-__global__ void __launch_bounds__(256)
-compact_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ positions, int64_t n,
-               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, ChunkPlan* plan, cudaStream_t s)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = __ldg(keys + i);
-    if (k != KEY_CULLED) { const uint32_t p = __ldg(positions + i); keys_out[p] = k; vals_out[p] = (uint32_t)i; }
+    choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, plan);
 }
-}  // namespace
 
-void launch_compact(const uint32_t* keys, const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
-                    cudaStream_t s)
+void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
+                    Record* recs, cudaStream_t s)
 {
-    if (n <= 0) return;
-    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, positions, n, keys_out, vals_out);
+    if (n_live <= 0) return;
+    const unsigned grid = (unsigned)((n_live + 255) / 256);
+    switch (fc.sh_order) {
+    case 0:  records_kernel<0><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
+    case 1:  records_kernel<1><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
+    case 2:  records_kernel<2><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
+    default: records_kernel<3><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
+    }
 }
 
 }  // namespace gsb

@@ -50,6 +50,7 @@ struct PassSmem {
     uint32_t tile;
     uint32_t sk[RS_TILE];
     uint32_t sv[RS_TILE];
+    uint32_t sa[RS_TILE];               // auxiliary payload (optional)
 };
 
 __device__ __forceinline__ unsigned lanemask_lt()
@@ -72,6 +73,18 @@ __device__ __forceinline__ uint32_t squeeze(uint32_t key, uint32_t key_min, uint
 {
     return min(key - key_min, key_span);
 }
+
+// digit of a key in one pass: a bit field of the squeezed key (LSD passes) ...
+struct BitsDigit {
+    int shift; uint32_t mask, key_min, key_span;
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const { return (squeeze(key, key_min, key_span) >> shift) & mask; }
+};
+// ... or the depth chunk of the key's depth bucket (the chunk partition: monotone in the key, so a stable pass on it
+// cuts the depth order into contiguous ranges without sorting inside them)
+struct ChunkDigit {
+    DepthBuckets db; const uint8_t* lut;
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const { return (uint32_t)__ldg(lut + depth_bucket(key, db)); }
+};
 
 // lanes of the warp whose digit equals this lane's digit (0 for invalid lanes); nbits = digit width of the pass
 template <int NBITS>
@@ -135,21 +148,20 @@ __global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __rest
 
 // ---- one pass ------------------------------------------------------------------------------------------------
 // lookback layout: [tile][nbins]: a tile publishes one coalesced row; a look-back step reads LB_WIN rows.
-template <int NBITS>
+template <int NBITS, class DigitFn>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-               int shift, uint32_t key_min, uint32_t key_span, const uint32_t* __restrict__ digit_base,
+               const DigitFn dig, const uint32_t* __restrict__ digit_base,
                uint32_t* __restrict__ lookback, unsigned num_tiles, uint32_t* __restrict__ ticket,
                uint32_t* __restrict__ error_flag,
-               const uint2* __restrict__ gather_src, uint2* __restrict__ gather_dst)
+               const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ aux_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nbins = 1 << NBITS;
-    constexpr uint32_t mask = (uint32_t)nbins - 1u;
     const unsigned lt = lanemask_lt();
     if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
@@ -167,13 +179,14 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
         k[j] = valid ? __ldg(keys_in + idx) : 0u;
         v[j] = valid ? __ldg(vals_in + idx) : 0u;
     }
+    const bool has_aux = aux_in != nullptr;
 
     // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         size_t idx = item_index(base, warp, lane, j);
         bool valid = idx < n;
-        uint32_t d = (squeeze(k[j], key_min, key_span) >> shift) & mask;
+        uint32_t d = dig(k[j]);
         unsigned peers = match_digit<NBITS>(d, valid);
         uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
         __syncwarp();
@@ -210,9 +223,10 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     for (int j = 0; j < RS_ITEMS; ++j) {
         size_t idx = item_index(base, warp, lane, j);
         if (idx < n) {
-            uint32_t d = (squeeze(k[j], key_min, key_span) >> shift) & mask;
+            uint32_t d = dig(k[j]);
             uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
             sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
+            if (has_aux) sm.sa[lp] = __ldg(aux_in + idx);       // the payload rides along (loaded late: short live range)
         }
     }
 
@@ -258,11 +272,10 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
         uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
         if (i < tile_count) {
             uint32_t key = sm.sk[i];
-            uint32_t d = (squeeze(key, key_min, key_span) >> shift) & mask;
+            uint32_t d = dig(key);
             size_t o = (size_t)(sm.global_delta[d] + i);
-            const uint32_t val = sm.sv[i];
-            keys_out[o] = key; vals_out[o] = val;
-            if (gather_src) gather_dst[o] = __ldg(gather_src + val);     // last pass: payload into sorted order
+            keys_out[o] = key; vals_out[o] = sm.sv[i];
+            if (has_aux) aux_out[o] = sm.sa[i];
         }
     }
 }
@@ -285,12 +298,12 @@ int sort_key_bits(uint32_t key_span)
 
 int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
                      int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
-                     const uint2* gather_src, uint2* gather_dst, uint32_t key_min, uint32_t key_span)
+                     uint32_t* aux0, uint32_t* aux1, uint32_t key_min, uint32_t key_span)
 {
     if (n == 0 || end_bit <= begin_bit) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
+#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
         GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
         GSB_SET_ATTR(8); GSB_SET_ATTR(9);
 #undef GSB_SET_ATTR
@@ -318,11 +331,12 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n, plan, hist);
     os_scan_hist_kernel<<<plan.passes, RS_RADIX, 0, s>>>(hist);
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
+    uint32_t* ain = aux0; uint32_t* aout = aux1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
-        const uint2* gsrc = (p == plan.passes - 1) ? gather_src : nullptr;
-#define GSB_PASS(B) case B: os_pass_kernel<B><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, plan.shift[p], \
-                        key_min, key_span, hist + p * RS_RADIX, lookback + lb_off[p], nb, tickets + p, error_flag, gsrc, gather_dst); break
+#define GSB_PASS(B) case B: os_pass_kernel<B, BitsDigit><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, \
+                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], nb, \
+                        tickets + p, error_flag, ain, aout); break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
         }
@@ -330,10 +344,34 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
+        t = ain; ain = aout; aout = t;
         cur ^= 1;
     }
     if (launches) *launches += 2 + plan.passes;
     return cur;
+}
+
+void partition_by_chunk(const uint32_t* k_in, const uint32_t* v_in, const uint32_t* a_in,
+                        uint32_t* k_out, uint32_t* v_out, uint32_t* a_out, size_t n, DepthBuckets db,
+                        const ChunkPlan* plan, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches)
+{
+    if (n == 0) return;
+    constexpr int PBITS = 5;                                   // MAX_CHUNKS + 1 culled bin <= 32 bins
+    static_assert(MAX_CHUNKS + 1 <= (1 << PBITS), "chunk digit does not fit");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(os_pass_kernel<PBITS, ChunkDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
+        attr_set = true;
+    }
+    const unsigned nb = (unsigned)rs_blocks(n);
+    uint32_t* hist = static_cast<uint32_t*>(scratch);
+    uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
+    if (!error_flag) error_flag = tickets + RS_MAX_PASSES;
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + os_header_bytes());
+    cudaMemsetAsync(scratch, 0, os_header_bytes() + ((size_t)nb << PBITS) * sizeof(uint32_t), s);
+    os_pass_kernel<PBITS, ChunkDigit><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(
+        k_in, v_in, k_out, v_out, n, ChunkDigit{ db, plan->lut }, plan->base, lookback, nb, tickets, error_flag, a_in, a_out);
+    if (launches) *launches += 1;
 }
 
 }  // namespace gsb

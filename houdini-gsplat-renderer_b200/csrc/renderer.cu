@@ -108,22 +108,27 @@ struct gsb_context {
     int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
-    DevBuf geomA, geomB, col[6];
-    int    planes = 1;
+    DevBuf geomA, geomB, rows;
 
-    // per-frame device buffers
-    DevBuf keys[2], vals[2], keys_unsorted, recs, rects, rects_sorted, counts, ikeys[2], ivals[2], ranges, tile_consumed, tile_done, fb;
+    // per-frame device buffers.  keys/vals/trects: [0] = K1 output in submission order, [1] = partitioned into depth
+    // chunks.  lkeys/lvals/ltrects: the live splats of the current chunk (ping-pong of their depth sort).
+    DevBuf keys[2], vals[2], trects[2], lkeys[2], lvals[2], ltrects[2], recs, rects, counts, positions, ikeys[2], ivals[2],
+           ranges, tile_consumed, tile_done, fb, plan, bucket_hist;
+    DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
+    ChunkPlan* plan_h = nullptr;                     // pinned mirror of the chunk plan
+    cudaEvent_t plan_ev = nullptr;
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
     unsigned long long* counters_h = nullptr;        // pinned mirror
     int order_buf = 0, inst_buf = 0;
+    int64_t last_live = 0;                           // live splats of the last depth chunk
     int64_t last_n = 0, last_sorted = 0; uint64_t last_d = 0; int last_tiles = 0; int last_w = 0, last_h = 0;
     float4* last_fb = nullptr;
 
     cudaEvent_t ev[EV_COUNT] = {};
-    cudaEvent_t evc[16][3] = {};                     // per depth chunk: start, after binning, after blend
+    cudaEvent_t evc[16][5] = {};                     // per depth chunk: start, after the live sort, records, binning, blend
     int evc_chunks = 0;
     bool ev_valid = false;
     gsb_stats stats{};
@@ -194,10 +199,13 @@ int gsb_create(int cuda_device, gsb_context** out)
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
-    for (int i = 0; i < 16; ++i) for (int j = 0; j < 3; ++j) CU(cudaEventCreate(&c->evc[i][j]));
+    for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) CU(cudaEventCreate(&c->evc[i][j]));
     CU(c->counters.ensure(64));
     CU(cudaMallocHost(&c->counters_h, 64));
     memset(c->counters_h, 0, 64);
+    CU(cudaMallocHost(&c->plan_h, sizeof(ChunkPlan)));
+    CU(cudaEventCreateWithFlags(&c->plan_ev, cudaEventDisableTiming));
+    CU(c->plan.ensure(sizeof(ChunkPlan))); CU(c->bucket_hist.ensure(DEPTH_BUCKETS * 4));
     *out = c.release();
     return GSB_OK;
 }
@@ -209,8 +217,10 @@ int gsb_destroy(gsb_context* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->gl_res) cudaGraphicsUnregisterResource(ctx->gl_res);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 16; ++i) for (int j = 0; j < 3; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
+    for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+    if (ctx->plan_h) cudaFreeHost(ctx->plan_h);
+    if (ctx->plan_ev) cudaEventDestroy(ctx->plan_ev);
     cudaStream_t s = ctx->own_stream;
     delete ctx;
     if (s) cudaStreamDestroy(s);
@@ -514,7 +524,6 @@ int gsb_generate_render_geometry(gsb_context* ctx)
     ctx->splat_count = std::min(total, cap);
     if (ctx->splat_count > 0x3fffffffLL) return fail(GSB_ERR_LIMIT, "more than 2^30-1 splats in the active set");
     ctx->sh_present = sh_all;
-    ctx->planes = sh_all ? 6 : 1;
 
     // origin = mean of the active prims' barycentres, fp32, iteration order = ascending id (R.C:403-418)
     float o[3] = { 0, 0, 0 }; int clusters = 0;
@@ -537,10 +546,7 @@ int gsb_generate_render_geometry(gsb_context* ctx)
     }
 
     const size_t n = (size_t)ctx->splat_count;
-    CU(ctx->geomA.ensure(n * 16)); CU(ctx->geomB.ensure(n * 16));
-    for (int p = 0; p < ctx->planes; ++p) CU(ctx->col[p].ensure(n * 16));
-    uint4* cols[6];
-    for (int p = 0; p < 6; ++p) cols[p] = ctx->col[p].as<uint4>();
+    CU(ctx->geomA.ensure(n * 16)); CU(ctx->geomB.ensure(n * 16)); CU(ctx->rows.ensure(n * ROW_U4 * 16));
     int64_t offset = 0;
     for (auto& id : ctx->active_set) {                     // R.C:420-511
         const Entry& e = *ctx->registry[id];
@@ -549,7 +555,7 @@ int gsb_generate_render_geometry(gsb_context* ctx)
         const int64_t cnt = std::min(e.count, left);
         launch_pack(e.pos.as<float>(), e.cd.as<uint16_t>(), e.alpha.as<float>(), e.scale.as<uint16_t>(),
                     e.orient.as<uint16_t>(), e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(),
-                    cnt, offset, ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), cols, ctx->planes, ctx->stream);
+                    cnt, offset, ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), sh_all ? 1 : 0, ctx->stream);
         offset += cnt;
     }
     CU(cudaGetLastError());
@@ -574,6 +580,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         return fail(GSB_ERR_INVALID, "gsb_render: bad tile-row partition");
     if (fr->row_group < 0) return fail(GSB_ERR_INVALID, "gsb_render: row_group must be >= 0");
     CU(cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();            // a non-sticky error left by an earlier failed call (e.g. GL interop without a GL context) is not this frame's
     cudaStream_t s = ctx->stream;
 
     FrameConsts fc{};
@@ -592,55 +599,18 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const int64_t n = ctx->splat_count;
     const size_t  N = (size_t)n;
 
-    // buffers
-    for (int b = 0; b < 2; ++b) { CU(ctx->keys[b].ensure(N * 4)); CU(ctx->vals[b].ensure(N * 4)); }
-    CU(ctx->recs.ensure(N * sizeof(Record))); CU(ctx->rects.ensure(N * 8)); CU(ctx->rects_sorted.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16));
-    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N))); CU(ctx->scan_scratch.ensure(scan_scratch_bytes(N)));
-    CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
-    CU(ctx->tile_done.ensure((size_t)num_tiles * 4));
-    if (ctx->keep_intermediates) CU(ctx->keys_unsorted.ensure(N * 4));
-    float4* fb = nullptr;
-    const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
-    if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
-    else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
-    float4* fb_final = (target && target->final_rgba) ? static_cast<float4*>(target->final_rgba) : fb;
+    // depth chunks: the frame is binned and blended front to back in nchunks ranges of the depth order
+    int nchunks = ctx->depth_chunks;
+    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 3 : 1;                // auto (r01 sweep: 3-4 best at 20 M, 1 at 1 M)
+    nchunks = std::min(nchunks, (int)MAX_CHUNKS);
 
-    unsigned long long* cnt = ctx->counters.as<unsigned long long>();
-    const bool tm = ctx->stage_timing;
-    if (tm) CU(cudaEventRecord(ctx->ev[EV_START], s));
-    CU(cudaMemsetAsync(cnt, 0, 64, s));
-
-    // K1 project + SH + key
-    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(),
-                     { ctx->col[0].as<uint4>(), ctx->col[1].as<uint4>(), ctx->col[2].as<uint4>(),
-                       ctx->col[3].as<uint4>(), ctx->col[4].as<uint4>(), ctx->col[5].as<uint4>() } };
-    // A row-partitioned frame (multi-GPU) culls most splats on every rank: compact the survivors (order preserving,
-    // so the tie rule "ascending index" still holds) and sort / bin only V instead of N.
-    const bool compact = ctx->compact_mode == 1 || (ctx->compact_mode == 0 && fr->row_world > 1);
-    launch_project(fc, ps, n, ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), ctx->recs.as<Record>(),
-                   ctx->rects.as<uint2>(), cnt + 0, compact ? ctx->counts.as<uint32_t>() : nullptr, s);
-    st.launches += 1;
-    if (ctx->keep_intermediates)
-        CU(cudaMemcpyAsync(ctx->keys_unsorted.p, ctx->keys[0].p, N * 4, cudaMemcpyDeviceToDevice, s));
-    int64_t n_sort = n;                 // elements that go through the depth sort and the binning
-    int src = 0;                        // which (keys, vals) pair holds the sort input
-    if (compact) {
-        exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), N, ctx->scan_scratch.p, nullptr, s, &st.launches);
-        launch_compact(ctx->keys[0].as<uint32_t>(), ctx->counts.as<uint32_t>(), n, ctx->keys[1].as<uint32_t>(),
-                       ctx->vals[1].as<uint32_t>(), s);
-        st.launches += 1;
-        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        n_sort = (int64_t)ctx->counters_h[0];
-        src = 1;
-    }
-    const size_t NS = (size_t)n_sort;
-    if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
-
-    // K3 global depth sort (stable).  Every key is the fp32 bit pattern of a squared distance from the camera to a point
-    // inside the packed set's bounding box, so keys lie in [bits(dmin^2), bits(dmax^2)]: sorting key - key_min needs only
-    // the bits that vary (25 instead of 32 for the benchmark cloud => 3 passes instead of 4) and gives the identical order.
+    // Every depth key is the fp32 bit pattern of a squared distance from the camera to a point inside the packed set's
+    // bounding box, so keys lie in [bits(dmin^2), bits(dmax^2)]: sorting key - key_min needs only the bits that vary
+    // (25 instead of 32 for the benchmark cloud => 3 passes instead of 4) and gives the identical order.  The same
+    // bound makes the depth buckets (chunk partition) linear in the distance over [dmin, dmax].
     uint32_t key_min = 0u, key_span = 0xFFFFFFFFu;
+    DepthBuckets db{ 0.0f, 0.0f };
+    bool range_ok = false;
     if (ctx->bbox_valid) {
         double dmin2 = 0.0, dmax2 = 0.0;
         for (int k = 0; k < 3; ++k) {
@@ -654,76 +624,149 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         if (std::isfinite(fmin) && std::isfinite(fmax) && fmin >= 0.0f && fmax >= fmin) {
             uint32_t bmin, bmax; memcpy(&bmin, &fmin, 4); memcpy(&bmax, &fmax, 4);
             key_min = bmin; key_span = bmax - bmin + 1u;      // valid keys squeeze to [0, span-1], culled to span
+            const float d0 = std::sqrt(fmin), d1 = std::sqrt(fmax);
+            if (d1 > d0) { db.dmin = d0; db.scale = (float)(DEPTH_BUCKETS - 1) / (d1 - d0); range_ok = std::isfinite(db.scale); }
         }
     }
+    if (!range_ok) nchunks = 1;                               // no finite depth range: a single chunk needs no buckets
     const int key_bits = sort_key_bits(key_span);
-    ctx->order_buf = src ^ radix_sort_pairs(ctx->keys[src].as<uint32_t>(), ctx->vals[src].as<uint32_t>(),
-                                      ctx->keys[src ^ 1].as<uint32_t>(), ctx->vals[src ^ 1].as<uint32_t>(), NS, 0, key_bits,
-                                      ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches,
-                                      ctx->rects.as<uint2>(), ctx->rects_sorted.as<uint2>(), key_min, key_span);
-    const uint32_t* order = ctx->vals[ctx->order_buf].as<uint32_t>();
+
+    // buffers
+    // packed tile rectangles ride along as a payload (screens up to 512 x 512 tiles); otherwise exact rectangles by index
+    const bool use_trects = fc.tiles_x <= 512 && fc.tiles_y <= 512;
+    const int  nbuf = nchunks > 1 ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+        CU(ctx->keys[b].ensure(N * 4)); CU(ctx->vals[b].ensure(N * 4));
+        if (use_trects) CU(ctx->trects[b].ensure(N * 4));
+    }
+    CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16)); CU(ctx->positions.ensure(N * 4 + 16));
+    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N))); CU(ctx->scan_scratch.ensure(scan_scratch_bytes(N)));
+    CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
+    CU(ctx->tile_done.ensure((size_t)num_tiles * 4));
+    float4* fb = nullptr;
+    const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
+    if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
+    else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
+    float4* fb_final = (target && target->final_rgba) ? static_cast<float4*>(target->final_rgba) : fb;
+
+    unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D [2] D_c [3] sort error [4] done tiles [5] L
+    const bool tm = ctx->stage_timing;
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_START], s));
+    CU(cudaMemsetAsync(cnt, 0, 64, s));
+
+    // K1: cull + depth key + tile rectangle for every submitted splat (+ the depth-bucket histogram)
+    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>() };
+    uint32_t* bucket_hist = nchunks > 1 ? ctx->bucket_hist.as<uint32_t>() : nullptr;
+    if (bucket_hist) CU(cudaMemsetAsync(bucket_hist, 0, DEPTH_BUCKETS * 4, s));
+    launch_project(fc, ps, n, ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), ctx->rects.as<uint2>(),
+                   (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects[0].as<uint32_t>() : nullptr,
+                   cnt + 0, db, bucket_hist, s);
+    st.launches += 1;
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
+
+    // K3a: cut the depth order into chunks WITHOUT sorting it: one stable partition pass on the chunk of each key's depth
+    // bucket.  Inside a chunk the splats stay in submission order; only the ones that reach a live tile are sorted later.
+    int src = 0;
+    int64_t chunk_size[MAX_CHUNKS + 1]; chunk_size[0] = n;
+    if (nchunks > 1) {
+        ChunkPlan* plan = ctx->plan.as<ChunkPlan>();
+        launch_choose_chunks(bucket_hist, nchunks, plan, s);
+        CU(cudaMemcpyAsync(ctx->plan_h, plan, sizeof(uint32_t) * (MAX_CHUNKS + 1), cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(ctx->plan_ev, s));
+        partition_by_chunk(ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), use_trects ? ctx->trects[0].as<uint32_t>() : nullptr,
+                           ctx->keys[1].as<uint32_t>(), ctx->vals[1].as<uint32_t>(), use_trects ? ctx->trects[1].as<uint32_t>() : nullptr,
+                           N, db, plan, ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
+        st.launches += 1;
+        CU(cudaEventSynchronize(ctx->plan_ev));               // the plan arrives while the partition pass runs
+        for (int c = 0; c <= nchunks; ++c) chunk_size[c] = (int64_t)ctx->plan_h->size[c];
+        src = 1;
+    }
+    const uint32_t* pkeys = ctx->keys[src].as<uint32_t>();
+    const uint32_t* pvals = ctx->vals[src].as<uint32_t>();
+    const uint32_t* ptrects = use_trects ? ctx->trects[src].as<uint32_t>() : nullptr;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
 
-    // K4 + K5, in depth chunks.  Ranks [r0, r1) of the global depth order are binned and blended, tiles whose pixels
-    // all saturated are flagged, and later (deeper) chunks no longer emit instances into flagged tiles.  The per-pixel
-    // sequence of blended instances is unchanged, so the frame is bit-identical to the single-chunk result.
+    // K3b + K4 + K2 + K5 per depth chunk.  The splats of the chunk that still touch a live tile (owned by this rank, not
+    // saturated by nearer chunks) are compacted, depth-sorted, binned, given their records and blended; tiles whose
+    // pixels all saturated are flagged.  The per-pixel sequence of blended instances is the one a single global sort
+    // would give, so the frame is bit-identical to the single-chunk result.
     uint32_t* tile_done = ctx->tile_done.as<uint32_t>();
     CU(cudaMemsetAsync(tile_done, 0, (size_t)num_tiles * 4, s));
     CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));     // accumulates over chunks
     if (fr->row_world > 1 && fb_final == fb) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));   // rows this rank does not own stay zero
-    int nchunks = ctx->depth_chunks;
-    if (nchunks <= 0) nchunks = (n_sort >= (int64_t)2000000) ? 3 : 1;           // auto (r01 sweep: 3-4 best at 20 M, 1 at 1 M)
-    nchunks = std::min(nchunks, 16);
-    // geometric boundaries: the first chunk is N / 2^(nchunks), every further chunk doubles the covered depth range
-    int64_t bounds[17]; bounds[0] = 0;
-    for (int c = 1; c <= nchunks; ++c) {
-        bounds[c] = (c == nchunks) ? n_sort : std::max<int64_t>(1, (int64_t)(((double)n_sort * (double)((1ll << c) - 1)) / (double)(1ll << nchunks)));
-        bounds[c] = std::min(bounds[c], n_sort);
-    }
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
     // tiles this rank owns: when all of them are saturated no deeper splat can change a pixel and the frame is done
     int owned_rows = 0;
     for (int ty = 0; ty < fc.tiles_y; ++ty) owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
     const uint64_t owned_tiles = (uint64_t)owned_rows * (uint64_t)fc.tiles_x;
-    uint64_t D_total = 0, V = 0, D = 0;
+    uint64_t D_total = 0, L_total = 0, V = 0, D = 0, L = 0;
     int chunks_run = 0;
+    int64_t r0 = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int64_t r0 = bounds[c], cn = bounds[c + 1] - bounds[c];
+        const int64_t cn = chunk_size[c];
         const bool first = (c == 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][0], s));
-        launch_tile_counts(ctx->rects_sorted.as<uint2>(), r0, cn, fc, first ? nullptr : tile_done, ctx->counts.as<uint32_t>(), s);
-        exclusive_scan_u32(ctx->counts.as<uint32_t>(), ctx->counts.as<uint32_t>(), (size_t)cn, ctx->scan_scratch.p, cnt + 1, s, &st.launches);
+        uint32_t* counts = ctx->counts.as<uint32_t>();
+        uint32_t* positions = ctx->positions.as<uint32_t>();
+        CU(cudaMemsetAsync(cnt + 1, 0, 8, s));
+        launch_tile_counts(ptrects, pvals, ctx->rects.as<uint2>(), r0, cn, fc, first ? nullptr : tile_done, counts, cnt + 1, s);
+        exclusive_scan_flags_u32(counts, positions, (size_t)cn, ctx->scan_scratch.p, cnt + 5, s, &st.launches);
         st.launches += 1;
-        // one host sync per chunk: V, this chunk's D, and the number of tiles saturated by the previous chunks
-        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 16, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(ctx->counters_h + 4, cnt + 4, 8, cudaMemcpyDeviceToHost, s));
+        // one host sync per chunk: V, this chunk's D and L, and the number of tiles saturated by the previous chunks
+        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 48, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        V = ctx->counters_h[0]; D = ctx->counters_h[1];
+        V = ctx->counters_h[0]; D = ctx->counters_h[1]; L = ctx->counters_h[5];
         const bool all_done = ctx->counters_h[4] >= owned_tiles;        // implies D == 0
         // the last chunk that has work, or the last chunk at all, finalises the un-saturated tiles
         const bool last = (c == nchunks - 1) || all_done;
         if (D > 0x3fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^30-1 tile instances in one depth chunk");
-        D_total += D;
+        D_total += D; L_total += L;
         chunks_run = c + 1;
         if (all_done && !first) {                                        // every tile was finalised when it saturated
-            if (tm) { CU(cudaEventRecord(ctx->evc[c][1], s)); CU(cudaEventRecord(ctx->evc[c][2], s)); }
+            if (tm) for (int e = 1; e < 5; ++e) CU(cudaEventRecord(ctx->evc[c][e], s));
             break;
         }
-        for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
-        CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)D)));
-        launch_emit(order, ctx->rects_sorted.as<uint2>(), ctx->counts.as<uint32_t>(), cnt + 1, r0, cn, fc,
+        // compact the live splats (order preserving) and sort them by depth: stable LSD, ties keep ascending index
+        for (int b = 0; b < 2; ++b) {
+            CU(ctx->lkeys[b].ensure((size_t)L * 4 + 16)); CU(ctx->lvals[b].ensure((size_t)L * 4 + 16));
+            if (use_trects) CU(ctx->ltrects[b].ensure((size_t)L * 4 + 16));
+            CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16));
+        }
+        CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16));
+        CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)std::max<uint64_t>(D, L))));
+        launch_compact_live(pkeys + r0, pvals + r0, ptrects ? ptrects + r0 : nullptr, counts, positions, cn,
+                            ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                            use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr, s);
+        st.launches += (cn > 0 ? 1 : 0);
+        ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                                          ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), (size_t)L, 0, key_bits,
+                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches,
+                                          use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
+                                          use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, key_min, key_span);
+        const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
+        const uint32_t* trects_sorted = use_trects ? ctx->ltrects[ctx->order_buf].as<uint32_t>() : nullptr;
+        if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
+        // K2: records of the live splats, in depth order
+        launch_records(fc, ps, order, (int64_t)L, ctx->recs.as<Record>(), s);
+        st.launches += (L ? 1 : 0);
+        if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+        // K4: tile counts in depth order -> offsets -> instances -> stable partition by tile -> tile ranges
+        launch_tile_counts(trects_sorted, order, ctx->rects.as<uint2>(), 0, (int64_t)L, fc, first ? nullptr : tile_done, counts, nullptr, s);
+        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cnt + 6, s, &st.launches);
+        launch_emit(order, trects_sorted, ctx->rects.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
-        st.launches += 1;
+        st.launches += (L ? 2 : 0);
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
-        if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
+        if (tm) CU(cudaEventRecord(ctx->evc[c][3], s));
         launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fb_final, fc,
                      first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 2, cnt + 4, s);
         st.launches += 1;
-        if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+        if (tm) CU(cudaEventRecord(ctx->evc[c][4], s));
+        r0 += cn;
     }
     nchunks = chunks_run;
     CU(cudaGetLastError());
@@ -758,10 +801,18 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     }
     ctx->ev_valid = tm;
 
-    ctx->last_n = n; ctx->last_sorted = n_sort; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
+    if (ctx->keep_intermediates) {        // debug views of the last chunk: records by splat index, instances as splat indices
+        CU(ctx->dbg_recs.ensure(N * sizeof(Record) + 16)); CU(ctx->dbg_inst.ensure((size_t)D_last * 4 + 16));
+        CU(cudaMemsetAsync(ctx->dbg_recs.p, 0, N * sizeof(Record), s));
+        launch_debug_views(ctx->recs.as<Record>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), (int64_t)L, ctx->dbg_recs.as<Record>(),
+                           ctx->ivals[ctx->inst_buf].as<uint32_t>(), D_last, ctx->dbg_inst.as<uint32_t>(), s);
+        CU(cudaGetLastError());
+    }
+    ctx->last_live = (int64_t)L;
+    ctx->last_n = n; ctx->last_sorted = (int64_t)L; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
     ctx->last_fb = fb_final;
     st.depth_chunks = nchunks;
-    st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D;
+    st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D; st.n_live = (int64_t)L_total;
     st.sh_order_used = fc.sh_order; st.width = fr->width; st.height = fr->height;
     st.tiles_x = fc.tiles_x; st.tiles_y = fc.tiles_y;
     memcpy(st.camera, fc.cam, 12); memcpy(st.origin, fc.origin, 12);
@@ -792,14 +843,14 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
     if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[2];
     if (st.rendered && ctx->counters_h[3] != 0ull)
         return fail(GSB_ERR_CUDA, "radix sort look-back timed out (internal error); the last frame is invalid");
-    st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = 0.0f;
+    st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = st.ms_records = 0.0f;
     if (st.rendered && ctx->ev_valid) {
         cudaEventElapsedTime(&st.ms_project, ctx->ev[EV_START], ctx->ev[EV_PROJECT]);
         cudaEventElapsedTime(&st.ms_sort, ctx->ev[EV_PROJECT], ctx->ev[EV_SORT]);
         for (int c = 0; c < ctx->evc_chunks; ++c) {                        // summed over depth chunks
-            float a = 0.f, b = 0.f;
-            cudaEventElapsedTime(&a, ctx->evc[c][0], ctx->evc[c][1]); cudaEventElapsedTime(&b, ctx->evc[c][1], ctx->evc[c][2]);
-            st.ms_bin += a; st.ms_blend += b;
+            float t[4] = { 0.f, 0.f, 0.f, 0.f };
+            for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&t[e], ctx->evc[c][e], ctx->evc[c][e + 1]);
+            st.ms_sort += t[0]; st.ms_records += t[1]; st.ms_bin += t[2]; st.ms_blend += t[3];
         }
         cudaEventElapsedTime(&st.ms_copy, ctx->ev[EV_BLEND], ctx->ev[EV_COPY]);
         cudaEventElapsedTime(&st.ms_total, ctx->ev[EV_START], ctx->ev[EV_COPY]);
@@ -861,13 +912,13 @@ int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, 
     const void* src = nullptr; uint64_t need = 0;
     const uint64_t n = (uint64_t)ctx->last_n, d = ctx->last_d, t = (uint64_t)ctx->last_tiles;
     switch (which) {
-    case GSB_DBG_KEYS_UNSORTED: src = ctx->keys_unsorted.p; need = ctx->keep_intermediates ? n * 4 : 0; break;
-    case GSB_DBG_ORDER:         src = ctx->vals[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
-    case GSB_DBG_KEYS_SORTED:   src = ctx->keys[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
-    case GSB_DBG_RECORDS:       src = ctx->recs.p; need = n * sizeof(Record); break;
-    case GSB_DBG_RECTS:         src = ctx->rects.p; need = n * 8; break;
+    case GSB_DBG_KEYS_UNSORTED: src = ctx->keys[0].p; need = n * 4; break;
+    case GSB_DBG_ORDER:         src = ctx->lvals[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
+    case GSB_DBG_KEYS_SORTED:   src = ctx->lkeys[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
+    case GSB_DBG_RECORDS:       src = ctx->dbg_recs.p; need = ctx->keep_intermediates ? n * sizeof(Record) : 0; break;
+    case GSB_DBG_RECTS:         src = ctx->rects.p; need = ctx->keep_intermediates ? n * 8 : 0; break;
     case GSB_DBG_TILE_RANGES:   src = ctx->ranges.p; need = t * 8; break;
-    case GSB_DBG_INSTANCES:     src = ctx->ivals[ctx->inst_buf].p; need = d * 4; break;
+    case GSB_DBG_INSTANCES:     src = ctx->dbg_inst.p; need = ctx->keep_intermediates ? d * 4 : 0; break;
     case GSB_DBG_FRAMEBUFFER:   src = ctx->last_fb; need = (uint64_t)ctx->last_w * ctx->last_h * 16; break;
     case GSB_DBG_TILE_CONSUMED: src = ctx->tile_consumed.p; need = t * 4; break;
     default: return fail(GSB_ERR_INVALID, "gsb_debug_fetch: unknown buffer");

@@ -83,7 +83,8 @@ class StatsC(C.Structure):
                 ("depth_chunks", C.c_int32), ("reserved0", C.c_int32),
                 ("camera", C.c_float * 3), ("origin", C.c_float * 3),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float),
-                ("ms_blend", C.c_float), ("ms_copy", C.c_float), ("ms_total", C.c_float)]
+                ("ms_blend", C.c_float), ("ms_copy", C.c_float), ("ms_total", C.c_float),
+                ("ms_records", C.c_float), ("reserved1", C.c_float), ("n_live", C.c_int64)]
 
 
 _lib = None

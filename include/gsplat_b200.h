@@ -102,6 +102,10 @@ typedef struct gsb_stats {
     /* device time per stage of the last gsb_render, CUDA events on the library stream;
      * valid when GSB_OPT_STAGE_TIMING is on (gsb_get_stats synchronises) */
     float   ms_project, ms_sort, ms_bin, ms_blend, ms_copy, ms_total;
+    float   ms_records;      /* K2 (records + SH of the live splats); ms_sort = chunk partition + live selection + live depth sort */
+    float   reserved1;
+    int64_t n_live;          /* L: splats that reached a live (owned, un-saturated) tile, summed over depth chunks: only these
+                                are depth-sorted, given a 2-D record (SH evaluated) and binned */
 } gsb_stats;
 
 enum gsb_option {
@@ -109,20 +113,24 @@ enum gsb_option {
     GSB_OPT_EPS_T = 2,           /* transmittance early-out threshold; default 1e-5; 0 = never stop (reference) */
     GSB_OPT_STAGE_TIMING = 3,    /* record per-stage CUDA events (default 0) */
     GSB_OPT_KEEP_INTERMEDIATES = 4, /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
-    GSB_OPT_COMPACT = 6,         /* compact surviving splats before the depth sort: 0 = auto (row-partitioned frames), 1, 2 = never */
+    GSB_OPT_COMPACT = 6,         /* accepted for ABI compatibility, no effect: the live splats of every depth chunk are always
+                                    compacted before their depth sort */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };
 
 enum gsb_debug_buffer {
-    GSB_DBG_KEYS_UNSORTED = 0,   /* uint32[N]  depth keys in submission order (needs KEEP_INTERMEDIATES) */
-    GSB_DBG_ORDER = 1,           /* uint32[N]  splat index by depth rank, culled splats last (uint32[V] when compacted) */
-    GSB_DBG_RECORDS = 2,         /* 48 B x N   2-D records by splat index (valid where visible) */
-    GSB_DBG_RECTS = 3,           /* uint16[4] x N  inclusive pixel rectangle x0,x1,y0,y1 (x0>x1 = culled) */
+    GSB_DBG_KEYS_UNSORTED = 0,   /* uint32[N]  depth keys in submission order */
+    GSB_DBG_ORDER = 1,           /* uint32[L]  splat index by depth rank: the live splats of the last depth chunk (with
+                                    GSB_OPT_DEPTH_CHUNKS = 1: every visible splat, i.e. the global depth order) */
+    GSB_DBG_RECORDS = 2,         /* 48 B x N   2-D records by splat index (valid for the live splats of the last chunk;
+                                    needs KEEP_INTERMEDIATES) */
+    GSB_DBG_RECTS = 3,           /* uint16[4] x N  inclusive pixel rectangle x0,x1,y0,y1 (x0>x1 = culled; needs KEEP_INTERMEDIATES) */
     GSB_DBG_TILE_RANGES = 4,     /* uint32[2] x tiles  [start,end) into the instance list (last depth chunk) */
-    GSB_DBG_INSTANCES = 5,       /* uint32[D]  splat index per tile instance, tile-major, depth order inside (last chunk) */
+    GSB_DBG_INSTANCES = 5,       /* uint32[D]  splat index per tile instance, tile-major, depth order inside (last chunk;
+                                    needs KEEP_INTERMEDIATES) */
     GSB_DBG_FRAMEBUFFER = 6,     /* float[4] x W x H */
-    GSB_DBG_KEYS_SORTED = 7,     /* uint32[N] */
+    GSB_DBG_KEYS_SORTED = 7,     /* uint32[L]  keys in the order of GSB_DBG_ORDER */
     GSB_DBG_TILE_CONSUMED = 8    /* uint32 x tiles  instances traversed per tile */
 };
 

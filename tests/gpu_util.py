@@ -38,8 +38,8 @@ def assert_stage_parity(O, g, o, cloud_n, rgba_tol=2e-5):
     vis = o["vis"] > 0
     assert g["stats"]["n_visible"] == int(vis.sum())
     assert np.array_equal(g["keys"], o["keys"]), "depth keys differ"
-    ns = g["order"].shape[0]                       # N, or V when the survivors were compacted (row-partitioned frames)
-    assert ns in (cloud_n, int(vis.sum()))
+    ns = g["order"].shape[0]                       # V: only splats that reach a live tile are depth-sorted
+    assert ns == int(vis.sum()) == g["stats"]["n_live"]
     assert np.array_equal(g["order"].astype(np.int64), o["order"][:ns].astype(np.int64)), "depth order differs"
     assert np.array_equal(g["keys_sorted"], o["keys"][o["order"]][:ns])
     gr, orc = g["rects"], o["rects"]

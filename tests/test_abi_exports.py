@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(R.FrameC) == 5 * 64 + 8 * 4
     assert C.sizeof(R.TargetC) == 32
     assert R.RECORD_DTYPE.itemsize == 48 and R.RECT_DTYPE.itemsize == 8
-    assert C.sizeof(R.StatsC) == 4 * 8 + 10 * 4 + 6 * 4 + 6 * 4
+    assert C.sizeof(R.StatsC) == 4 * 8 + 10 * 4 + 6 * 4 + 8 * 4 + 8
 
 
 def test_no_cpu_fallback_without_device():

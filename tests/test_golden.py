@@ -36,7 +36,7 @@ def test_cuda_reproduces_golden(name):
     out = gpu_pipeline(cl, S.orbit_frame(w, h, theta), order)
     vis = g["vis"] > 0
     assert np.array_equal(out["keys"], g["keys"])
-    assert np.array_equal(out["order"].astype(np.int32), g["order"])
+    assert np.array_equal(out["order"].astype(np.int32), g["order"][:int(vis.sum())])    # culled splats are never sorted
     assert np.array_equal(out["rects"].view(np.uint16).reshape(-1, 4)[vis], g["rects"][vis])
     assert np.array_equal(out["recs"].view(np.uint32).reshape(-1, 12)[vis], g["recs"][vis])
     assert np.array_equal(out["inst"].astype(np.int32), g["inst"])

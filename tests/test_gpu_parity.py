@@ -36,8 +36,9 @@ def test_stage_parity(oracle, scene, n, w, h, theta, sh, order, mult):
     assert_stage_parity(O, g, o, n)
 
 
-def test_compaction_forced_on_single_rank_is_bit_identical(oracle, scene):
-    """GSB_OPT_COMPACT=1: culled splats are squeezed out before the sort; everything downstream is unchanged."""
+def test_culled_splats_never_reach_the_depth_sort(oracle, scene):
+    """Only splats that reach a live tile are compacted and depth-sorted: with a third of the cloud behind the camera
+    the sorted set is exactly the visible set (GSB_OPT_COMPACT is accepted and has no effect)."""
     O, S = oracle, scene
     cl = S.make_cloud(60_000, 808, sh=True, scale_mult=1.5)
     cl.pos[::3, 2] += np.float32(4.5)              # a third of the cloud behind the camera -> culled
@@ -215,10 +216,12 @@ def test_full_size_properties_1M_1080p(scene):
     g = gpu_pipeline(cl, fr, 0, renderer=r)
     n = cl.n
     assert np.all(np.diff(g["keys_sorted"].astype(np.int64)) >= 0)
-    assert np.array_equal(np.sort(g["order"]), np.arange(n, dtype=np.uint32))
     V, D = g["stats"]["n_visible"], g["stats"]["n_instances"]
-    assert 0.9 * n < V <= n and D > V
-    rank = np.empty(n, np.int64); rank[g["order"]] = np.arange(n)
+    assert 0.9 * n < V <= n and D > V and g["stats"]["n_live"] == V
+    vis_idx = np.nonzero(g["rects"]["x0"] <= g["rects"]["x1"])[0].astype(np.uint32)
+    assert np.array_equal(np.sort(g["order"]), vis_idx)          # the sorted set is exactly the visible set
+    assert np.array_equal(g["keys_sorted"], g["keys"][g["order"]])
+    rank = np.full(n, -1, np.int64); rank[g["order"]] = np.arange(V)
     rg = g["ranges"].astype(np.int64)
     ne = rg[:, 1] > rg[:, 0]
     assert (rg[ne, 1] - rg[ne, 0]).sum() == D
@@ -234,4 +237,50 @@ def test_full_size_properties_1M_1080p(scene):
     host2 = np.zeros_like(g["rgba"])
     r.draw([r.registerUpdate(0x7f00dead0000, (1, 2, 3, 4), 0, cl)], fr, host_rgba=host2)
     assert np.array_equal(host2, g["rgba"])
+    r.close()
+
+
+def test_only_live_splats_get_sorted_and_shaded(oracle, scene):
+    """Depth chunks + saturation feedback: deeper chunks sort / shade / bin only the splats that still touch an
+    un-saturated tile.  L (n_live) < V, yet the frame equals the single-chunk frame bit for bit and the oracle."""
+    O, S = oracle, scene
+    cl = S.make_cloud(300_000, 2024, sh=True, scale_mult=2.5)
+    fr, F = _frame(O, S, cl, 480, 270, 140.0, 3)
+    one = gpu_pipeline(cl, fr, 3, depth_chunks=1)
+    assert one["stats"]["n_live"] == one["stats"]["n_visible"]
+    for chunks in (3, 6):
+        many = gpu_pipeline(cl, fr, 3, depth_chunks=chunks)
+        assert np.array_equal(one["rgba"], many["rgba"])
+        assert np.array_equal(one["consumed"], many["consumed"])
+        assert many["stats"]["n_live"] < many["stats"]["n_visible"]
+        assert many["stats"]["n_consumed"] == one["stats"]["n_consumed"]
+        # the live list of the last chunk is depth ordered (keys ascending, ties by ascending index)
+        k, o_ = many["keys_sorted"].astype(np.int64), many["order"].astype(np.int64)
+        assert np.all((np.diff(k) > 0) | ((np.diff(k) == 0) & (np.diff(o_) > 0)))
+        assert np.array_equal(many["keys"][many["order"]], many["keys_sorted"])
+    o = O.pipeline(F, cl)
+    assert np.abs(one["rgba"] - o["rgba"]).max() <= 2e-5
+
+
+def test_wide_splats_use_the_exact_rectangle(oracle, scene):
+    """Splats spanning >= 127 tiles do not fit the packed tile rectangle and fall back to the exact pixel rectangle by
+    splat index; that table is written sparsely unless intermediates are kept, so compare both modes and the oracle."""
+    from houdini_gsplat_renderer_b200 import renderer as R
+    O, S = oracle, scene
+    cl = S.make_cloud(400, 9, sh=False, scale_mult=1.0)
+    cl.scale_h[:6] = np.float16(30.0)                      # axis cap 4096 px: 256+ tiles wide at this resolution
+    cl.alpha[:6] = np.float32(0.05)
+    w, h = 4400, 2300
+    fr, F = _frame(O, S, cl, w, h, 0.0, 0)
+    o = O.pipeline(F, cl)
+    g = gpu_pipeline(cl, fr, 0)
+    assert_stage_parity(O, g, o, cl.n)
+    tx = (g["rects"]["x1"].astype(int) // 16) - (g["rects"]["x0"].astype(int) // 16)
+    assert (tx[g["rects"]["x0"] <= g["rects"]["x1"]] >= 127).sum() >= 3
+    r = R.GSplatRenderer(0)                                # production mode: no intermediates, 2 depth chunks
+    r.set_option(R.OPT_DEPTH_CHUNKS, 2)
+    rid = r.registerUpdate(3, (1, 0, 0, 0), 0, cl)
+    host = np.zeros((h, w, 4), np.float32)
+    r.draw([rid], fr, host_rgba=host)
+    assert np.array_equal(host, g["rgba"])
     r.close()
