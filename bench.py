@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-A step = one full frame of the hot path (cull+key -> depth-chunk partition -> per chunk: live-splat depth sort, records+SH,
-tile binning, blend) over
+A step = one full frame of the hot path (cull + key + tile rectangle for every splat -> per depth chunk: live-splat
+selection, depth sort, records + SH, tile binning, blend) over
 the synthetic cloud of SURVEY.md §8d.  Default workload: the north-star target, 20 M splats, SH degree 3,
 1920x1080, one B200 (fits one GPU: 2.6 GB of attributes).  Prints ONE JSON line (rank 0).
 
@@ -326,12 +326,14 @@ def run_ours(args):
     tile_passes = max(1, -(-max(1, (tiles - 1).bit_length()) // 8))
     key_passes = 3                                        # 25 significant key bits at these camera distances: 9+8+8
     Nw = N * world
+    chunks = max(1.0, cnt["depth_chunks"] / K / world)
     stage_bytes = {
-        # K1: cull-phase read + (key, index, packed tile rectangle) written for every submitted splat
-        "project": Nw * 30 + Nw * 12,
-        # chunk partition (12 B read + 12 B written per splat) + live selection (tile-rect read, flag write, flag scan
-        # read/read/write, compaction reads flag+position) + compaction and LSD sort of the L live (key, index, rect) triples
-        "sort": Nw * 24 + Nw * (4 + 4 + 12 + 8) + L * 24 + L * (4 + key_passes * 24),
+        # K1: cull-phase read (SURVEY: 30 B per submitted splat) + (key, packed tile rectangle) written for every splat
+        "project": Nw * 30 + Nw * 8,
+        # per depth chunk: live selection streams key + tile rectangle of every splat (8 B) and writes/reads one ballot bit
+        # per splat; the L selected (key, index, rect) triples are gathered (8 B) and written (12 B), then LSD-sorted
+        # (histogram read + passes x 24 B)
+        "sort": chunks * Nw * (8 + 0.25) + L * (8 + 12) + L * (4 + key_passes * 24),
         # K2: index + 30 B geometry + colour/SH read, record written, per live splat
         "records": L * (4 + 30 + 6 + sh_bytes) + L * RECORD_BYTES,
         # K4: counts (rect read, count write, scan), emit (offset + rect + index read, 8 B per instance written), stable tile

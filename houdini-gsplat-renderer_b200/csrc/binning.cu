@@ -21,20 +21,30 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
     return t;
 }
 
-// tile rectangle of element r: from the packed payload, or (wide splats / huge screens) from the exact rectangle
+// tile rectangle of element r: from the packed payload, or (wide splats / huge screens) from the exact rectangle of
+// splat order[r] (order == NULL: element r is splat r)
 __device__ __forceinline__ TileRect tile_rect_of(const uint32_t* __restrict__ trects, const uint32_t* __restrict__ order,
                                                  const uint2* __restrict__ rects, int64_t r)
 {
-    if (!trects) {
-        const uint32_t i = __ldg(order + r);
-        TileRect t; t.empty = true; t.tx0 = t.ty0 = 1; t.tx1 = t.ty1 = 0;
-        return i == 0xFFFFFFFFu ? t : tile_rect(__ldg(rects + i));
-    }
+    if (!trects) return tile_rect(__ldg(rects + (order ? (int64_t)__ldg(order + r) : r)));
     const uint32_t p = __ldg(trects + r);
     TileRect t;
     t.empty = p == TRECT_CULLED;
     const int w = (int)((p >> 18) & 127u), h = (int)((p >> 25) & 127u);
-    if (!t.empty && (w == 127 || h == 127)) return tile_rect(__ldg(rects + __ldg(order + r)));
+    if (!t.empty && (w == 127 || h == 127)) return tile_rect(__ldg(rects + (order ? (int64_t)__ldg(order + r) : r)));
+    t.tx0 = (int)(p & 511u); t.ty0 = (int)((p >> 9) & 511u); t.tx1 = t.tx0 + w; t.ty1 = t.ty0 + h;
+    return t;
+}
+
+// same, with the packed word already in a register (has_packed false: exact rectangle of splat i)
+__device__ __forceinline__ TileRect tile_rect_packed(const bool has_packed, const uint32_t p, const uint2* __restrict__ rects,
+                                                     const int64_t i)
+{
+    if (!has_packed) return tile_rect(__ldg(rects + i));
+    TileRect t;
+    t.empty = p == TRECT_CULLED;
+    const int w = (int)((p >> 18) & 127u), h = (int)((p >> 25) & 127u);
+    if (!t.empty && (w == 127 || h == 127)) return tile_rect(__ldg(rects + i));
     t.tx0 = (int)(p & 511u); t.ty0 = (int)((p >> 9) & 511u); t.tx1 = t.tx0 + w; t.ty1 = t.ty0 + h;
     return t;
 }
@@ -67,18 +77,147 @@ tile_count_kernel(const uint32_t* __restrict__ trects, const uint32_t* __restric
     }
 }
 
-// survivors (counts != 0) keep their relative order: positions = exclusive scan of the flags
-__global__ void __launch_bounds__(256)
-compact_live_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ trects,
-                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ positions, int64_t n,
+// ---- live selection, per depth chunk, over the submitted splats (which are never moved).  Element k is selected if its
+// depth bucket belongs to the chunk (lut[depth_bucket(key)] == chunk; lut == NULL: every element) and it touches at
+// least one live tile.  Three kernels, no spin-waits:
+//   A  select_count: one CTA per 2048 elements streams the keys and packed tile rectangles (8 B / splat, all loads
+//      issued before any is used); writes one ballot word per 32 elements (N/8 bytes) and the tile's totals.
+//   S  select_scan:  one CTA turns the per-tile totals into exclusive bases and the grand totals L and D.
+//   B  select_write: scatters the selected (key, splat index, tile rectangle) triples to base + rank, in submission
+//      order, so the stable depth sort that follows breaks ties by ascending index.  CTAs of tiles without a selected
+//      element exit at once (deep chunks: most of them).
+// (r01 measured two other forms first.  A single-pass chained scan: with ~5000 tiles in flight the decoupled look-back
+// chains grew to the number of resident CTAs, 260-320 us per pass.  Loading the rectangle only for the chunk's own
+// elements: the dependent, divergent loads serialised, 130-210 us.  Streaming both arrays unconditionally is faster.)
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_WARPS   = SEL_THREADS / 32;
+constexpr int SEL_ITEMS   = 8;
+constexpr int SEL_TILE    = SEL_THREADS * SEL_ITEMS;     // 2048 elements per CTA
+constexpr int SEL_WORDS   = SEL_TILE / 32;               // ballot words per tile (64)
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects,
+                    const uint2* __restrict__ rects, int64_t n, const uint8_t* __restrict__ lut, const DepthBuckets db,
+                    const uint32_t chunk,
+                    int tiles_x, int row_rank, int row_world, int row_group, const uint32_t* __restrict__ tile_done,
+                    uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
+{
+    __shared__ uint32_t s_wl[SEL_WARPS], s_wd[SEL_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    const int64_t base = (int64_t)tile * SEL_TILE + (int64_t)warp * (32 * SEL_ITEMS);
+
+    // warp-striped items: item j of lane l is element base + j*32 + l, so (j, lane) order is element order
+    uint32_t key[SEL_ITEMS], tr[SEL_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SEL_ITEMS; ++j) {
+        const int64_t k = base + j * 32 + lane;
+        key[j] = (k < n) ? __ldg(keys + k) : KEY_CULLED;
+        tr[j]  = (k < n && trects) ? __ldg(trects + k) : 0u;
+    }
+    uint32_t dsum = 0, wcount = 0, mymask = 0;          // lane j keeps the ballot word of item j
+#pragma unroll
+    for (int j = 0; j < SEL_ITEMS; ++j) {
+        uint32_t c = 0;
+        if (key[j] != KEY_CULLED && (!lut || (uint32_t)__ldg(lut + depth_bucket(key[j], db)) == chunk)) {
+            const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane);
+            if (!t.empty) {
+                for (int ty = t.ty0; ty <= t.ty1; ++ty) {
+                    if (!owns_row(ty, row_rank, row_world, row_group)) continue;
+                    if (!tile_done) c += (uint32_t)(t.tx1 - t.tx0 + 1);
+                    else for (int tx = t.tx0; tx <= t.tx1; ++tx) c += (__ldg(tile_done + ty * tiles_x + tx) == 0u) ? 1u : 0u;
+                }
+            }
+        }
+        dsum += c;
+        const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
+        if (lane == j) mymask = m;
+        wcount += __popc(m);
+    }
+    if (lane < SEL_ITEMS) masks[(size_t)tile * SEL_WORDS + warp * SEL_ITEMS + lane] = mymask;
+    dsum = __reduce_add_sync(0xffffffffu, dsum);
+    if (lane == 0) { s_wl[warp] = wcount; s_wd[warp] = dsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t l = 0, d = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_WARPS; ++w) { l += s_wl[w]; d += s_wd[w]; }
+        tile_l[tile] = l; tile_d[tile] = d;
+    }
+}
+
+// one CTA: tile_base = exclusive scan of tile_l; *l_total, *d_total = grand totals
+__global__ void __launch_bounds__(1024)
+select_scan_kernel(const uint32_t* __restrict__ tile_l, const uint32_t* __restrict__ tile_d, uint32_t nt,
+                   uint32_t* __restrict__ tile_base, unsigned long long* __restrict__ l_total,
+                   unsigned long long* __restrict__ d_total)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ unsigned long long s_d[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0u;
+    unsigned long long dacc = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nt; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = (i < nt) ? tile_l[i] : 0u;
+        dacc += (i < nt) ? (unsigned long long)tile_d[i] : 0ull;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0, btot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) { woff += (w < warp) ? s_w[w] : 0u; btot += s_w[w]; }
+        if (i < nt) tile_base[i] = s_carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += btot;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if (lane == 0) s_d[warp] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long d = 0;
+        for (int w = 0; w < 32; ++w) d += s_d[w];
+        *l_total = (unsigned long long)s_carry; *d_total = d;
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_write_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects, int64_t n,
+                    const uint32_t* __restrict__ masks, const uint32_t* __restrict__ tile_l, const uint32_t* __restrict__ tile_base,
                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t* __restrict__ trects_out)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    if (__ldg(counts + k) != 0u) {
-        const uint32_t p = __ldg(positions + k);
-        keys_out[p] = __ldg(keys + k); vals_out[p] = __ldg(vals + k);
-        if (trects) trects_out[p] = __ldg(trects + k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (tile_l[tile] == 0u) return;                      // CTA-uniform
+    // offset of this warp inside the tile: selected elements of the warps before it
+    const uint32_t* tm = masks + (size_t)tile * SEL_WORDS;
+    uint32_t pre = 0;
+#pragma unroll
+    for (int q = 0; q < SEL_WORDS / 32; ++q) {
+        const int wi = q * 32 + lane;
+        pre += (wi < warp * SEL_ITEMS) ? __popc(__ldg(tm + wi)) : 0u;
+    }
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    const uint32_t mymask = (lane < SEL_ITEMS) ? __ldg(tm + warp * SEL_ITEMS + lane) : 0u;
+    uint32_t p = tile_base[tile] + pre;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t base = (int64_t)tile * SEL_TILE + (int64_t)warp * (32 * SEL_ITEMS);
+#pragma unroll
+    for (int j = 0; j < SEL_ITEMS; ++j) {
+        const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
+        if ((m >> lane) & 1u) {
+            const int64_t k = base + j * 32 + lane;
+            const uint32_t o = p + __popc(m & lt);
+            keys_out[o] = __ldg(keys + k); vals_out[o] = (uint32_t)k;
+            if (trects) trects_out[o] = __ldg(trects + k);
+        }
+        p += __popc(m);
     }
 }
 
@@ -145,13 +284,26 @@ void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uin
                                                                  fc.row_world, fc.row_group, tile_done, counts, d_total);
 }
 
-void launch_compact_live(const uint32_t* keys, const uint32_t* vals, const uint32_t* trects, const uint32_t* counts,
-                         const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
-                         uint32_t* trects_out, cudaStream_t s)
+static inline size_t sel_tiles(int64_t n) { return (size_t)((n + SEL_TILE - 1) / SEL_TILE); }
+
+size_t select_scratch_bytes(int64_t n) { return sel_tiles(n) * (SEL_WORDS + 3) * sizeof(uint32_t) + 64; }
+
+void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
+                        const uint8_t* lut, DepthBuckets db, int chunk,
+                        FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
+                        uint32_t* trects_out, void* scratch, unsigned long long* l_total, unsigned long long* d_total,
+                        cudaStream_t s)
 {
     if (n <= 0) return;
-    compact_live_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, vals, trects, counts, positions, n, keys_out, vals_out,
-                                                                   trects_out);
+    const unsigned nt = (unsigned)sel_tiles(n);
+    uint32_t* tile_l = static_cast<uint32_t*>(scratch);
+    uint32_t* tile_d = tile_l + nt;
+    uint32_t* tile_base = tile_d + nt;
+    uint32_t* masks  = tile_base + nt;
+    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, lut, db, (uint32_t)chunk, fc.tiles_x, fc.row_rank,
+                                                   fc.row_world, fc.row_group, tile_done, masks, tile_l, tile_d);
+    select_scan_kernel<<<1, 1024, 0, s>>>(tile_l, tile_d, nt, tile_base, l_total, d_total);
+    select_write_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, n, masks, tile_l, tile_base, keys_out, vals_out, trects_out);
 }
 
 void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,

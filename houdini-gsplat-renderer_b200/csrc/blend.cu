@@ -11,8 +11,8 @@
 // record as three 16-byte async copies.  Each warp then culls the batch against its own 8x4 block
 // 32 instances at a time (one instance per lane, conservative AABB test, ballot) and walks only the
 // surviving bits in order, so a small splat costs one warp pass instead of eight.  Transmittance
-// is kept per pixel in registers; a warp stops when all its pixels are saturated (T < eps) and the
-// CTA stops when all warps have (early-out: the reference has none).
+// is kept per pixel in registers; a warp stops (checked once per 32 instances) when all its pixels are
+// saturated (T < eps) and the CTA stops when all warps have (early-out: the reference has none).
 //
 // Per-pixel arithmetic is the spec of DESIGN.md §3 and oracle/gsplat_oracle.cpp shade(): explicit
 // fmaf where the spec says fmaf, nothing else contracted (TU built with -fmad=false), so coverage
@@ -21,6 +21,7 @@
 // Algorithmic bytes: D_c * (4 + 48) + W*H*16 — HBM/L2-gather bound by design,
 // FP32-issue bound in practice.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gsb {
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+template <bool OBB_CULL>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
              const uint2* __restrict__ ranges, float4* __restrict__ fb, float4* __restrict__ fb_final,
@@ -62,6 +64,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     // pixel-centre box of this warp's 8x4 block
     const float wx_lo = (float)bx + 0.5f, wx_hi = (float)bx + 7.5f;
     const float wy_lo = (float)by + 0.5f, wy_hi = (float)by + 3.5f;
+    const float wx_mid = (float)bx + 4.0f, wy_mid = (float)by + 2.0f;
     const float eps = F.eps_t;
 
     const uint2 range = ranges[tile];
@@ -77,7 +80,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     }
     bool done = !inside || (T < eps);
     bool warp_done = __all_sync(0xffffffffu, done);
-    uint32_t warp_pos = 0;                       // instances this warp traversed when it saturated
+    uint32_t done_pos = 0;                       // instances traversed when this pixel saturated (0: it started saturated)
     const uint32_t nb = (len + BL_BATCH - 1) / BL_BATCH;
 
     auto stage = [&](uint32_t b) {
@@ -108,6 +111,25 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                     const float hx = __half2float(__ushort_as_half((unsigned short)(hp & 0xffffu)));
                     const float hy = __half2float(__ushort_as_half((unsigned short)(hp >> 16)));
                     ov = (cc.x - hx <= wx_hi) && (cc.x + hx >= wx_lo) && (cc.y - hy <= wy_hi) && (cc.y + hy >= wy_lo);
+                    if (OBB_CULL && ov) {
+                        // second separating-axis test, in the splat's eigen space: the block's pixel centres map into the box
+                        // qc +- (rx, ry); if that box misses |qx| <= 2, |qy| <= 2 or |q|^2 <= pmax no pixel of the block is
+                        // covered.  Margins (1e-5 of the operand magnitudes, 1e-4 on the thresholds) are orders of magnitude
+                        // above fp32 rounding of the per-pixel test below, so the cull is conservative: the frame is unchanged.
+                        const float2 m0 = *reinterpret_cast<const float2*>(&buf[my].m00);
+                        const float2 m1 = *reinterpret_cast<const float2*>(&buf[my].m10);
+                        const float4 ma = make_float4(m0.x, m0.y, m1.x, m1.y);                     // m00 m01 m10 m11
+                        const float pm = buf[my].pmax;
+                        const float ddx = wx_mid - cc.x, ddy = wy_mid - cc.y;
+                        const float qcx = fmaf(ddy, ma.y, ddx * ma.x), qcy = fmaf(ddy, ma.w, ddx * ma.z);
+                        const float a00 = fabsf(ma.x), a01 = fabsf(ma.y), a10 = fabsf(ma.z), a11 = fabsf(ma.w);
+                        const float adx = fabsf(ddx), ady = fabsf(ddy);
+                        const float rx = fmaf(1.5f, a01, 3.5f * a00), ry = fmaf(1.5f, a11, 3.5f * a10);
+                        const float ex = 1e-5f * fmaf(a01, ady + 1.5f, a00 * (adx + 3.5f));
+                        const float ey = 1e-5f * fmaf(a11, ady + 1.5f, a10 * (adx + 3.5f));
+                        const float gx = fmaxf(fabsf(qcx) - rx - ex, 0.0f), gy = fmaxf(fabsf(qcy) - ry - ey, 0.0f);
+                        ov = (gx <= 2.0001f) && (gy <= 2.0001f) && (fmaf(gy, gy, gx * gx) <= fmaf(pm, 1.0001f, 1e-4f));
+                    }
                 }
                 unsigned mask = __ballot_sync(0xffffffffu, ov);
                 while (mask) {
@@ -125,15 +147,13 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                             const float w = T * A;
                             Cr = fmaf(w, r2.x, Cr); Cg = fmaf(w, r2.y, Cg); Cb = fmaf(w, r2.z, Cb);
                             T = T - w;
-                            done = T < eps;
+                            if (T < eps) { done = true; done_pos = b * BL_BATCH + c + (uint32_t)j + 1u; }
                         }
                     }
-                    if (__all_sync(0xffffffffu, done)) {
-                        warp_done = true;
-                        warp_pos = b * BL_BATCH + c + (uint32_t)j + 1u;
-                        break;
-                    }
                 }
+                // early-out vote once per 32 instances, not per visit: a saturated warp may walk the rest of its group
+                // with every lane predicated off (no effect on the frame); done_pos keeps the exact position
+                warp_done = __all_sync(0xffffffffu, done);
             }
         }
         // barrier: everyone is finished with buf before it is refilled; also the CTA-wide early-out vote
@@ -141,6 +161,8 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     }
     cp_async_wait<0>();
 
+    // the warp saturated where its last pixel did
+    const uint32_t warp_pos = __reduce_max_sync(0xffffffffu, done_pos);
     if (lane == 0) atomicMax(&s_consumed, warp_done ? warp_pos : len);
     const bool tile_saturated = __syncthreads_and(warp_done ? 1 : 0) != 0;   // also orders the atomicMax
     if (inside) {
@@ -163,8 +185,12 @@ void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ra
 {
     const int tiles = fc.tiles_x * fc.tiles_y;
     if (tiles <= 0) return;
-    blend_kernel<<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last, tile_done,
-                                              tile_consumed, consumed_total, done_tiles);
+    const char* e = getenv("GSB_BLEND_OBB");   // GSB_BLEND_OBB=0 turns the eigen-space cull off (experiments)
+    const int obb = (e && atoi(e) == 0) ? 0 : 1;
+    if (obb) blend_kernel<true><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last,
+                                                            tile_done, tile_consumed, consumed_total, done_tiles);
+    else blend_kernel<false><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last,
+                                                          tile_done, tile_consumed, consumed_total, done_tiles);
 }
 
 }  // namespace gsb

@@ -37,22 +37,26 @@ static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
 
 // Packed, render-layout splat attributes (built by pack on active-set change).  Two copies of the geometry:
 //   streamed by K1 (every splat, every frame), SoA planes:
-//     geomA[i] = (p.x, p.y, p.z, alpha)                         16 B
+//     geomA[i] = (p.x, p.y, p.z, rr)                            16 B   rr = sqrt(ln(255 alpha)) or -1 (never passes the discard)
 //     geomB[i] = (scale h3 | orient h4 (x,y,z,w) | pad h1)      16 B
 //   gathered by K2 (only the splats that reach a live tile), one 128-byte line per splat:
 //     rows[8*i + 0] = geomA bits, rows[8*i + 1] = geomB,
 //     rows[8*i + 2 + k], k = 0..5: 48 halfs = Cd(3) then SH coefficient j channel c at 3+3j+c
 //   Degree d needs halfs [0, 3 + 3*{0,3,8,15}) -> colour chunks {1,2,4,6} of the line.
 constexpr int ROW_U4 = 8;                      // uint4 per splat line
+//   cached per object matrix (launch_sigma): world-space covariance, upper triangle
+//     sigA[i] = (S00, S01, S02, S11), sigB[i] = (S12, S22)      24 B
 struct PackedSplats {
     const float4* geomA;
     const uint4*  geomB;
     const uint4*  rows;
+    const float4* sigA;
+    const float2* sigB;
 };
 
 // Depth buckets: a monotone (non-decreasing) map from the depth key to [0, DEPTH_BUCKETS-2], linear in the distance;
-// culled splats (KEY_CULLED) take the last bucket.  Used to cut the depth order into chunks without sorting it: every
-// step (sqrt, subtract, scale, clamp, truncate) is monotone in fp32, so bucket boundaries are key boundaries.
+// culled splats (KEY_CULLED) take the last bucket.  Used to cut the depth order into chunks without sorting or moving
+// the cloud: every step (sqrt, subtract, scale, clamp, truncate) is monotone in fp32, so bucket boundaries are key boundaries.
 constexpr int DEPTH_BUCKETS = 512;
 constexpr int MAX_CHUNKS    = 16;
 struct DepthBuckets { float dmin, scale; };
@@ -63,10 +67,9 @@ __device__ __forceinline__ uint32_t depth_bucket(uint32_t key, DepthBuckets db)
     t = fminf(fmaxf(t, 0.0f), (float)(DEPTH_BUCKETS - 2));
     return (uint32_t)t;
 }
-// Chunk plan chosen on the device from the bucket histogram (choose_chunks), mirrored to the host.
+// Chunk plan chosen on the device from the bucket histogram (choose_chunks).
 struct ChunkPlan {
-    uint32_t size[MAX_CHUNKS + 1];             // splats per chunk; entry nchunks = culled
-    uint32_t base[32];                         // exclusive scan of size (digit bases of the partition pass, 32 bins)
+    uint32_t size[MAX_CHUNKS + 1];             // visible splats per chunk; entry nchunks = culled
     uint8_t  lut[DEPTH_BUCKETS];               // bucket -> chunk
 };
 
@@ -88,28 +91,21 @@ int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1
 // everything above collapses onto key_span); pass end_bit = sort_key_bits(key_span) to sort only the bits that vary.
 int      sort_key_bits(uint32_t key_span);
 
-// Stable partition of (key, val, aux) triples into depth chunks: digit = plan->lut[depth_bucket(key)] (<= 32 bins), one
-// onesweep pass.  plan->base holds the bins' global offsets.  aux may be NULL.
-void     partition_by_chunk(const uint32_t* k_in, const uint32_t* v_in, const uint32_t* a_in,
-                            uint32_t* k_out, uint32_t* v_out, uint32_t* a_out, size_t n, DepthBuckets db,
-                            const ChunkPlan* plan, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches);
-// exclusive scan of the flags (in[i] != 0); *total_dev = number of non-zero entries
-void     exclusive_scan_flags_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
-                                  unsigned long long* total_dev, cudaStream_t s, int* launches);
-
 // project.cu
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
                  int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* rows, int has_sh, cudaStream_t s);
-// K1 (every submitted splat): cull, depth key (culled -> KEY_CULLED), vals = splat index, packed tile rectangle
-// (trects, may be NULL), exact pixel rectangle (rects: every splat if rects_all, else only the "wide" ones the packed
-// form cannot hold), *n_visible += V, and (bucket_hist != NULL) the DEPTH_BUCKETS-bin histogram of depth_bucket(key).
+// world-space covariance planes from geomB and the object matrix (run when the object matrix or the packed set changes)
+void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, cudaStream_t s);
+// K1 (every submitted splat): cull, depth key (culled -> KEY_CULLED), packed tile rectangle (trects, may be NULL), exact
+// pixel rectangle (rects: every splat if rects_all, else only the "wide" ones the packed form cannot hold),
+// *n_visible += V, and (bucket_hist != NULL) the DEPTH_BUCKETS-bin histogram of depth_bucket(key).
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
-                    uint32_t* keys, uint32_t* vals, uint2* rects, int rects_all, uint32_t* trects,
+                    uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
                     unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
-// chunk plan from the bucket histogram: chunk c ends at the first bucket whose exclusive count reaches
-// V * (2^(c+1) - 1) / 2^nchunks (geometric: every chunk doubles the covered share of the depth order)
-void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, ChunkPlan* plan, cudaStream_t s);
+// chunk plan from the bucket histogram: chunk c (< nchunks - 1) ends at the first bucket whose exclusive count reaches
+// V * (2^(c+1) - 1) / 2^shift (the first chunk holds V / 2^shift splats, every further one doubles; the last takes the rest)
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, ChunkPlan* plan, cudaStream_t s);
 // K2 (only splats that reach a live tile, in depth order): gather the splat's 128-byte line, redo the projection,
 // evaluate SH, write the 48-byte record of live rank j to recs[j]
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
@@ -122,10 +118,16 @@ void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_
 void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
                         FrameConsts fc, const uint32_t* tile_done, uint32_t* counts, unsigned long long* d_total,
                         cudaStream_t s);
-// order-preserving compaction of the elements with counts[k] != 0 (positions = exclusive scan of those flags)
-void launch_compact_live(const uint32_t* keys, const uint32_t* vals, const uint32_t* trects, const uint32_t* counts,
-                         const uint32_t* positions, int64_t n, uint32_t* keys_out, uint32_t* vals_out,
-                         uint32_t* trects_out, cudaStream_t s);
+// live selection of one depth chunk over the submitted splats: elements whose depth bucket belongs to the chunk
+// (lut[depth_bucket(key)] == chunk; lut NULL = all) and that touch a live tile are compacted, order preserving, into
+// (keys_out, vals_out = splat index, trects_out); *l_total = their number, *d_total = the instances they will emit.
+// scratch: select_scratch_bytes(n).  Three launches, no spin-waits.
+size_t select_scratch_bytes(int64_t n);
+void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
+                        const uint8_t* lut, DepthBuckets db, int chunk,
+                        FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
+                        uint32_t* trects_out, void* scratch, unsigned long long* l_total, unsigned long long* d_total,
+                        cudaStream_t s);
 // instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending;
 // offsets = exclusive scan of the tile counts, *total = its grand total (device)
 void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,

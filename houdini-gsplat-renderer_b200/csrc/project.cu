@@ -13,10 +13,12 @@
 // The fp32 expression order below IS the spec and matches oracle/gsplat_oracle.cpp
 // operation for operation: this TU is compiled with -fmad=false, IEEE division and sqrt
 // (-prec-div=true -prec-sqrt=true, no fast-math), so keys, records and rectangles are bit-exact.
-// HBM-bound.  K1 streams 32 B per submitted splat and writes 12 B (key, index, packed tile rectangle); K2 gathers one
+// K1 streams 40 B per submitted splat (position + discard radius, cached world-space covariance) and writes 8 B (key,
+// packed tile rectangle); it is FP32-issue bound (IEEE divisions and square roots of the spec).  K2 gathers one
 // 128-byte line per live splat and writes its 48-byte record, so colour / SH / record traffic is proportional to the
 // splats that can still change a pixel (3 M of 20 M at 20 M / 1080p), not to the cloud.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gsb {
 
@@ -51,6 +53,23 @@ __device__ __forceinline__ double det_log(double x)
     return (2.0 * s) * p + (double)k * 0.6931471805599453;
 }
 
+// Discard radius of a splat: pmax = ln(255 alpha) as fp32 (SRC.h:308: the fragment survives iff exp(-|q|^2) alpha >= 1/255),
+// or -1 if the splat can never pass the discard (alpha < 1/255, NaN).  View independent, so pack computes it ONCE per
+// geometry change and K1 streams it instead of alpha: the double-precision logarithm leaves the per-frame path.
+__device__ __forceinline__ float pmax_of_alpha(const float alpha)
+{
+    if (!(alpha >= 1.0f / 255.0f)) return -1.0f;
+    const float pmax = (float)det_log((double)alpha * 255.0);
+    return (pmax >= 0.0f) ? pmax : -1.0f;
+}
+
+// rr = sqrt(pmax), the discard radius in eigen space (what K1 needs for the pixel rectangle), or -1
+__device__ __forceinline__ float rr_of_alpha(const float alpha)
+{
+    const float pmax = pmax_of_alpha(alpha);
+    return (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f;
+}
+
 // ------------------------------------------------------------------------------------ K0 pack
 // One thread per splat of one registered prim.  Source layout = what registerUpdate receives
 // (R.h:34-47): pos f32x3, Cd h3, alpha f32, scale h3, orient h4 (x,y,z,w), SH 3 x half[16].
@@ -68,7 +87,7 @@ pack_kernel(const float* __restrict__ pos, const uint16_t* __restrict__ cd, cons
     uint32_t s0 = scale[3 * i], s1 = scale[3 * i + 1], s2 = scale[3 * i + 2];
     uint32_t q0 = orient[4 * i], q1 = orient[4 * i + 1], q2 = orient[4 * i + 2], q3 = orient[4 * i + 3];
     const uint4 gb = make_uint4(s0 | (s1 << 16), s2 | (q0 << 16), q1 | (q2 << 16), q3);
-    geomA[o] = ga; geomB[o] = gb;
+    geomA[o] = make_float4(ga.x, ga.y, ga.z, rr_of_alpha(ga.w)); geomB[o] = gb;
     uint4* row = rows + o * ROW_U4;
     row[0] = make_uint4(__float_as_uint(ga.x), __float_as_uint(ga.y), __float_as_uint(ga.z), __float_as_uint(ga.w));
     row[1] = gb;
@@ -104,17 +123,52 @@ constexpr float SH_C3_0 = -0.5900436f, SH_C3_1 = 2.8906114f, SH_C3_2 = -0.457045
 
 // Geometry of one projected splat: everything the record needs except the colour.
 struct Geom {
-    float cx, cy, m00, m01, m10, m11, pmax, hx, hy;
+    float cx, cy, m00, m01, m10, m11, hx, hy;
     int   x0, x1, y0, y1;
     float psx[3];            // shader-side position (P - origin) + origin
 };
 
 // Centre, cull, covariance chain, eigen axes, discard radius, pixel rectangle.  Returns false if culled.
 // The expression order is the spec; oracle/gsplat_oracle.cpp project_one() is its twin.
-__device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p[3], const float alpha,
-                                             const uint4 gb, Geom& g)
+// World-space covariance Sigma = O3 R S^2 R^T O3^T of one splat (LIB.h:10-35), upper triangle S00 S01 S02 S11 S12 S22.
+// Depends on scale, orient and the object matrix only, so it is cached per splat (sigma planes) and rebuilt only when
+// the object matrix changes; K2 recomputes it from the splat's line.  Same operations either way => same bits.
+struct Sigma { float s[6]; };
+__device__ __forceinline__ Sigma sigma_of(const float* __restrict__ object, const uint4 gb)
 {
-    if (!(alpha >= 1.0f / 255.0f)) return false;
+    const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
+    const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
+
+    float Rt[3][3];
+    Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
+    Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
+    Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float sc[3] = { sx, sy, sz };
+    float Mm[3][3], M2[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            M2[a][b] = (Mm[a][0] * MAT(object, b, 0) + Mm[a][1] * MAT(object, b, 1)) + Mm[a][2] * MAT(object, b, 2);
+    Sigma out;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            out.s[k++] = (M2[0][a] * M2[0][b] + M2[1][a] * M2[1][b]) + M2[2][a] * M2[2][b];
+    return out;
+}
+
+// rr = sqrt(pmax) (or negative: never passes the discard, see rr_of_alpha)
+__device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p[3], const float rr,
+                                             const Sigma& sig, Geom& g)
+{
+    if (!(rr >= 0.0f)) return false;             // alpha < 1/255
 #pragma unroll
     for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; g.psx[k] = t + F.origin[k]; }
     const float* psx = g.psx;
@@ -135,31 +189,8 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     const float cx = ((ndcx + 1.0f) * 0.5f) * F.W;
     const float cy = ((ndcy + 1.0f) * 0.5f) * F.H;
 
-    const float sx = lo_h(gb.x), sy = hi_h(gb.x), sz = lo_h(gb.y);
-    const float qx = hi_h(gb.y), qy = lo_h(gb.z), qz = hi_h(gb.z), qr = lo_h(gb.w);
-
-    float Rt[3][3];
-    Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
-    Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
-    Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
-    const float sc[3] = { sx, sy, sz };
-    float Mm[3][3], M2[3][3], S[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-            M2[a][b] = (Mm[a][0] * MAT(F.object, b, 0) + Mm[a][1] * MAT(F.object, b, 1)) + Mm[a][2] * MAT(F.object, b, 2);
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = a; b < 3; ++b) {
-            S[a][b] = (M2[0][a] * M2[0][b] + M2[1][a] * M2[1][b]) + M2[2][a] * M2[2][b];
-            S[b][a] = S[a][b];
-        }
+    const float (&S)[6] = sig.s;        // S00 S01 S02 S11 S12 S22
+#define SG(a, b) S[(a) <= (b) ? ((a) == 0 ? (b) : (a) + (b) + 1) : ((b) == 0 ? (a) : (a) + (b) + 1)]
 
     float t[3];
 #pragma unroll
@@ -186,8 +217,8 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        B0[k] = (A0[0] * S[0][k] + A0[1] * S[1][k]) + A0[2] * S[2][k];
-        B1[k] = (A1[0] * S[0][k] + A1[1] * S[1][k]) + A1[2] * S[2][k];
+        B0[k] = (A0[0] * SG(0, k) + A0[1] * SG(1, k)) + A0[2] * SG(2, k);
+        B1[k] = (A1[0] * SG(0, k) + A1[1] * SG(1, k)) + A1[2] * SG(2, k);
     }
     const float c00 = (B0[0] * A0[0] + B0[1] * A0[1]) + B0[2] * A0[2];
     const float c01 = (B0[0] * A1[0] + B0[1] * A1[1]) + B0[2] * A1[2];
@@ -209,12 +240,8 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     const float u1x = s1 * ex, u1y = s1 * ey;
     const float u2x = -(s2 * ey), u2y = s2 * ex;
 
-    const float pmax = (float)det_log((double)alpha * 255.0);
-    if (!(pmax >= 0.0f)) return false;
-
     const float bxh = 2.0f * (fabsf(u1x) + fabsf(u2x));
     const float byh = 2.0f * (fabsf(u1y) + fabsf(u2y));
-    const float rr = sqrtf(pmax);
     const float exh = rr * sqrtf(u1x * u1x + u2x * u2x);
     const float eyh = rr * sqrtf(u1y * u1y + u2y * u2y);
     float hx = fminf(bxh, exh); hx = hx + (hx * 0.0001f + 0.01f);
@@ -233,17 +260,18 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     g.cx = cx; g.cy = cy;
     g.m00 = ex / s1; g.m01 = ey / s1;
     g.m10 = (-ey) / s2; g.m11 = ex / s2;
-    g.pmax = pmax; g.hx = hx; g.hy = hy;
+    g.hx = hx; g.hy = hy;
     return true;
+#undef SG
 }
 
 // SH -> RGB for splat i (SRC.h:224,244-275; LIB.h:117-179), term order of LIB.h:148-174
+// crow: the splat's six 16-byte colour chunks (a staged copy in shared memory)
 template <int ORDER>
-__device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedSplats& ps, const int64_t i,
-                                             const float psx[3], float rgb[3])
+__device__ __forceinline__ void shade_colour(const FrameConsts& F, const uint4* crow, const float psx[3], float rgb[3])
 {
-    const uint4* row = ps.rows + i * ROW_U4 + 2;
-    const uint4 c0 = __ldg(row);
+    const uint4* row = crow;
+    const uint4 c0 = row[0];
     rgb[0] = lo_h(c0.x); rgb[1] = hi_h(c0.x); rgb[2] = lo_h(c0.y);
     if (ORDER > 0) {
         // 48 halfs: Cd(3) then coefficient j channel ch at 3 + 3j + ch
@@ -252,7 +280,7 @@ __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedS
         constexpr int PLANES = ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6);
 #pragma unroll
         for (int pl = 1; pl < PLANES; ++pl) {
-            const uint4 cc = __ldg(row + pl);
+            const uint4 cc = row[pl];
             w[4 * pl] = cc.x; w[4 * pl + 1] = cc.y; w[4 * pl + 2] = cc.z; w[4 * pl + 3] = cc.w;
         }
         const float wv[3] = { psx[0] - F.cam[0], psx[1] - F.cam[1], psx[2] - F.cam[2] };
@@ -301,9 +329,10 @@ __device__ __forceinline__ void shade_colour(const FrameConsts& F, const PackedS
 // a small share of the cloud is ever blended, so they are built later (K2) for the splats that reach a live tile.
 // The CTA also histograms depth_bucket(key) in shared memory (one flush per CTA) for the chunk plan.
 constexpr int K1_THREADS = 256;
-__global__ void __launch_bounds__(K1_THREADS)
-project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA, const uint4* __restrict__ geomB,
-               int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ rects,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(K1_THREADS, MIN_CTAS)
+project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA,
+               const float4* __restrict__ sigA, const float2* __restrict__ sigB, int64_t n, uint32_t* __restrict__ keys, uint2* __restrict__ rects,
                const int rects_all, uint32_t* __restrict__ trects, unsigned long long* __restrict__ n_visible,
                const DepthBuckets db, uint32_t* __restrict__ bucket_hist)
 {
@@ -315,15 +344,18 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
     uint32_t nvis = 0;
     const int64_t stride = (int64_t)gridDim.x * K1_THREADS;
     int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
-    float4 ga_next = make_float4(0.f, 0.f, 0.f, 0.f); uint4 gb_next = make_uint4(0u, 0u, 0u, 0u);
-    if (i < n) { ga_next = __ldg(geomA + i); gb_next = __ldg(geomB + i); }
+    float4 ga_next = make_float4(0.f, 0.f, 0.f, 0.f), sa_next = ga_next; float2 sb_next = make_float2(0.f, 0.f);
+    if (i < n) { ga_next = __ldg(geomA + i); sa_next = __ldg(sigA + i); sb_next = __ldg(sigB + i); }
     for (; i < n; i += stride) {
-        const float4 ga = ga_next;
-        const uint4  gb = gb_next;
-        if (i + stride < n) { ga_next = __ldg(geomA + i + stride); gb_next = __ldg(geomB + i + stride); }   // prefetch
+        const float4 ga = ga_next, sa = sa_next;
+        const float2 sb = sb_next;
+        if (i + stride < n) {                                // prefetch
+            ga_next = __ldg(geomA + i + stride); sa_next = __ldg(sigA + i + stride); sb_next = __ldg(sigB + i + stride);
+        }
         const float p[3] = { ga.x, ga.y, ga.z };
+        const Sigma sig{ { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y } };
         Geom g;
-        const bool vis = project_geom(F, p, ga.w, gb, g);
+        const bool vis = project_geom(F, p, ga.w, sig, g);
         uint32_t key = KEY_CULLED, tr = TRECT_CULLED;
         uint2 rect = make_uint2(1u, 1u);                     // x0=1,x1=0,y0=1,y1=0 : empty
         bool wide = false;
@@ -336,7 +368,7 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
             rect = make_uint2((uint32_t)g.x0 | ((uint32_t)g.x1 << 16), (uint32_t)g.y0 | ((uint32_t)g.y1 << 16));
             ++nvis;
         }
-        keys[i] = key; vals[i] = (uint32_t)i;
+        keys[i] = key;
         if (trects) trects[i] = tr;
         if (rects_all || wide) rects[i] = rect;
         if (bucket_hist) atomicAdd(&sh_hist[depth_bucket(key, db)], 1u);
@@ -352,9 +384,22 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
     }
 }
 
+// ---- sigma planes: world-space covariance per splat, rebuilt when the object matrix changes
+struct ObjMat { float m[16]; };
+__global__ void __launch_bounds__(256)
+sigma_kernel(const __grid_constant__ ObjMat O, const uint4* __restrict__ geomB, int64_t n,
+             float4* __restrict__ sigA, float2* __restrict__ sigB)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Sigma sg = sigma_of(O.m, __ldg(geomB + i));
+    sigA[i] = make_float4(sg.s[0], sg.s[1], sg.s[2], sg.s[3]);
+    sigB[i] = make_float2(sg.s[4], sg.s[5]);
+}
+
 // ---- chunk plan: one CTA of DEPTH_BUCKETS threads
 __global__ void __launch_bounds__(DEPTH_BUCKETS)
-choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, ChunkPlan* __restrict__ plan)
+choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const int shift, ChunkPlan* __restrict__ plan)
 {
     __shared__ uint32_t wtot[DEPTH_BUCKETS / 32];
     __shared__ uint32_t csize[MAX_CHUNKS + 1];
@@ -372,7 +417,8 @@ choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, Chunk
     const uint32_t excl = woff + inc - mine;                            // visible splats in nearer buckets
     int chunk = 0;
     for (int c = 1; c < nchunks; ++c) {
-        const uint32_t target = (uint32_t)(((unsigned long long)V * ((1ull << c) - 1ull)) >> nchunks);
+        unsigned long long tq = ((unsigned long long)V * ((1ull << c) - 1ull)) >> shift;
+        const uint32_t target = (uint32_t)(tq < (unsigned long long)V ? tq : (unsigned long long)V);
         if (excl >= target && target > 0u) ++chunk;                     // thresholds ascend with c: monotone in b
     }
     if (b == DEPTH_BUCKETS - 1) chunk = nchunks;
@@ -380,43 +426,55 @@ choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, Chunk
     const uint32_t cnt = (b == DEPTH_BUCKETS - 1) ? hist[b] : mine;
     if (cnt) atomicAdd(&csize[chunk], cnt);
     __syncthreads();
-    if (b == 0) {
-        uint32_t run = 0;
-        for (int c = 0; c < 32; ++c) {
-            plan->base[c] = run;
-            if (c <= MAX_CHUNKS) { const uint32_t sz = (c <= nchunks) ? csize[c] : 0u; plan->size[c] = sz; run += sz; }
-        }
-    }
+    if (b <= MAX_CHUNKS) plan->size[b] = (b <= nchunks) ? csize[b] : 0u;
 }
 
 // ---- K2: one thread per live splat, in depth order.  The splat's whole 128-byte line (geometry + colour + SH) is
-// one DRAM burst pair; the projection is redone with the same code as K1 (same bits), the record goes to recs[j].
+// one DRAM burst pair.  Lines are gathered cooperatively: 8 lanes fetch the 8 16-byte chunks of one line, so every load
+// instruction of a warp covers 4 complete lines and all loads of the warp's 32 lines are in flight together (one
+// latency, not three dependent ones); the lines are staged in shared memory (144-byte pitch: conflict-free both ways)
+// and each thread then reads its own.  The projection is redone with K1's code (same bits); the record goes to recs[j].
+constexpr int K2_THREADS = 256;
+constexpr int K2_PITCH   = ROW_U4 + 1;             // uint4 per staged line
 template <int ORDER>
-__global__ void __launch_bounds__(256)
-records_kernel(const __grid_constant__ FrameConsts F, const __grid_constant__ PackedSplats ps,
+__global__ void __launch_bounds__(K2_THREADS)
+records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
                const uint32_t* __restrict__ live_splats, const int64_t n_live, Record* __restrict__ recs)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
+    constexpr int NCH = 2 + (ORDER == 0 ? 1 : (ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6)));     // chunks of the line this order reads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * K2_THREADS + threadIdx.x;
+    const uint32_t my = (j < n_live) ? __ldg(live_splats + j) : 0u;
+    uint4* sw = srow[warp];
+    const int c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const uint32_t idx = __shfl_sync(0xffffffffu, my, r);
+        if (c < NCH) sw[r * K2_PITCH + c] = __ldg(rows + (size_t)idx * ROW_U4 + c);
+    }
+    __syncwarp();
     if (j >= n_live) return;
-    const int64_t i = (int64_t)__ldg(live_splats + j);
-    const uint4* row = ps.rows + i * ROW_U4;
-    const uint4 ra = __ldg(row);
-    const uint4 gb = __ldg(row + 1);
+    const uint4* row = sw + lane * K2_PITCH;
+    const uint4 ra = row[0];
+    const uint4 gb = row[1];
     const float p[3] = { __uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z) };
     const float alpha = __uint_as_float(ra.w);
     Geom g;
     float4* out = reinterpret_cast<float4*>(recs + j);
-    if (!project_geom(F, p, alpha, gb, g)) {                 // cannot happen (K1 kept it); an inert record if it did
+    const float pmax = pmax_of_alpha(alpha);
+    if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g)) {  // cannot happen (K1 kept it)
         out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
         out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     float rgb[3];
-    shade_colour<ORDER>(F, ps, i, g.psx, rgb);
+    shade_colour<ORDER>(F, row + 2, g.psx, rgb);
     const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
                            ((uint32_t)__half_as_ushort(__float2half_ru(g.hy)) << 16);
     out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
-    out[1] = make_float4(g.m10, g.m11, alpha, g.pmax);
+    out[1] = make_float4(g.m10, g.m11, alpha, pmax);
     out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
 }
 
@@ -432,36 +490,53 @@ void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, con
                                      geomA, geomB, rows, has_sh);
 }
 
+void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, cudaStream_t s)
+{
+    if (n <= 0) return;
+    ObjMat O; for (int k = 0; k < 16; ++k) O.m[k] = object[k];
+    sigma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, geomB, n, sigA, sigB);
+}
+
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
-                    uint32_t* keys, uint32_t* vals, uint2* rects, int rects_all, uint32_t* trects,
+                    uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
                     unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s)
 {
     if (n <= 0) return;
-    static int per_sm = 0;
+    // resident CTAs per SM: 4 (54 registers), 5 (48) or 6 (40, a few spill bytes); GSB_K1_OCC overrides for experiments
+    static int per_sm_of[3] = { 0, 0, 0 };
+    const char* e = getenv("GSB_K1_OCC");
+    int occ = e ? atoi(e) : 5;
+    if (occ < 4 || occ > 6) occ = 5;
+    int& per_sm = per_sm_of[occ - 4];
     if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel, K1_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        cudaError_t rc = occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel<4>, K1_THREADS, 0)
+                       : occ == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel<5>, K1_THREADS, 0)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_kernel<6>, K1_THREADS, 0);
+        if (rc != cudaSuccess || per_sm < 1) per_sm = occ;
     }
     const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    project_kernel<<<grid, K1_THREADS, 0, s>>>(fc, ps.geomA, ps.geomB, n, keys, vals, rects, rects_all, trects, n_visible,
-                                               db, bucket_hist);
+#define GSB_K1(M) project_kernel<M><<<grid, K1_THREADS, 0, s>>>(fc, ps.geomA, ps.sigA, ps.sigB, n, keys, rects, rects_all, trects, \
+                                                                n_visible, db, bucket_hist)
+    if (occ == 4) GSB_K1(4); else if (occ == 5) GSB_K1(5); else GSB_K1(6);
+#undef GSB_K1
 }
 
-void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, ChunkPlan* plan, cudaStream_t s)
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, ChunkPlan* plan, cudaStream_t s)
 {
-    choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, plan);
+    choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, plan);
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
                     Record* recs, cudaStream_t s)
 {
     if (n_live <= 0) return;
-    const unsigned grid = (unsigned)((n_live + 255) / 256);
+    const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
     switch (fc.sh_order) {
-    case 0:  records_kernel<0><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
-    case 1:  records_kernel<1><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
-    case 2:  records_kernel<2><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
-    default: records_kernel<3><<<grid, 256, 0, s>>>(fc, ps, live_splats, n_live, recs); break;
+    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
+    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
+    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
+    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
     }
 }
 

@@ -74,16 +74,10 @@ __device__ __forceinline__ uint32_t squeeze(uint32_t key, uint32_t key_min, uint
     return min(key - key_min, key_span);
 }
 
-// digit of a key in one pass: a bit field of the squeezed key (LSD passes) ...
+// digit of a key in one pass: a bit field of the squeezed key
 struct BitsDigit {
     int shift; uint32_t mask, key_min, key_span;
     __device__ __forceinline__ uint32_t operator()(uint32_t key) const { return (squeeze(key, key_min, key_span) >> shift) & mask; }
-};
-// ... or the depth chunk of the key's depth bucket (the chunk partition: monotone in the key, so a stable pass on it
-// cuts the depth order into contiguous ranges without sorting inside them)
-struct ChunkDigit {
-    DepthBuckets db; const uint8_t* lut;
-    __device__ __forceinline__ uint32_t operator()(uint32_t key) const { return (uint32_t)__ldg(lut + depth_bucket(key, db)); }
 };
 
 // lanes of the warp whose digit equals this lane's digit (0 for invalid lanes); nbits = digit width of the pass
@@ -349,29 +343,6 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     }
     if (launches) *launches += 2 + plan.passes;
     return cur;
-}
-
-void partition_by_chunk(const uint32_t* k_in, const uint32_t* v_in, const uint32_t* a_in,
-                        uint32_t* k_out, uint32_t* v_out, uint32_t* a_out, size_t n, DepthBuckets db,
-                        const ChunkPlan* plan, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches)
-{
-    if (n == 0) return;
-    constexpr int PBITS = 5;                                   // MAX_CHUNKS + 1 culled bin <= 32 bins
-    static_assert(MAX_CHUNKS + 1 <= (1 << PBITS), "chunk digit does not fit");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(os_pass_kernel<PBITS, ChunkDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
-        attr_set = true;
-    }
-    const unsigned nb = (unsigned)rs_blocks(n);
-    uint32_t* hist = static_cast<uint32_t*>(scratch);
-    uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
-    if (!error_flag) error_flag = tickets + RS_MAX_PASSES;
-    uint32_t* lookback = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + os_header_bytes());
-    cudaMemsetAsync(scratch, 0, os_header_bytes() + ((size_t)nb << PBITS) * sizeof(uint32_t), s);
-    os_pass_kernel<PBITS, ChunkDigit><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(
-        k_in, v_in, k_out, v_out, n, ChunkDigit{ db, plan->lut }, plan->base, lookback, nb, tickets, error_flag, a_in, a_out);
-    if (launches) *launches += 1;
 }
 
 }  // namespace gsb

@@ -105,18 +105,19 @@ struct gsb_context {
     float   eps_t = 1e-5f;
     bool    stage_timing = false, keep_intermediates = false;
     int     depth_chunks = 0;                                 // 0 = auto
+    int     chunk_shift = 0;                                  // first chunk = V / 2^shift; 0 = auto (= depth_chunks)
     int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
-    DevBuf geomA, geomB, rows;
+    DevBuf geomA, geomB, rows, sigA, sigB;
+    bool   sigma_valid = false;                      // sigA/sigB match the packed set and sigma_object
+    float  sigma_object[16] = {};
 
-    // per-frame device buffers.  keys/vals/trects: [0] = K1 output in submission order, [1] = partitioned into depth
-    // chunks.  lkeys/lvals/ltrects: the live splats of the current chunk (ping-pong of their depth sort).
-    DevBuf keys[2], vals[2], trects[2], lkeys[2], lvals[2], ltrects[2], recs, rects, counts, positions, ikeys[2], ivals[2],
+    // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
+    // lkeys/lvals/ltrects: the live splats of the current chunk (ping-pong of their depth sort).
+    DevBuf keys, trects, lkeys[2], lvals[2], ltrects[2], recs, rects, counts, ikeys[2], ivals[2],
            ranges, tile_consumed, tile_done, fb, plan, bucket_hist;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
-    ChunkPlan* plan_h = nullptr;                     // pinned mirror of the chunk plan
-    cudaEvent_t plan_ev = nullptr;
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
@@ -203,8 +204,6 @@ int gsb_create(int cuda_device, gsb_context** out)
     CU(c->counters.ensure(64));
     CU(cudaMallocHost(&c->counters_h, 64));
     memset(c->counters_h, 0, 64);
-    CU(cudaMallocHost(&c->plan_h, sizeof(ChunkPlan)));
-    CU(cudaEventCreateWithFlags(&c->plan_ev, cudaEventDisableTiming));
     CU(c->plan.ensure(sizeof(ChunkPlan))); CU(c->bucket_hist.ensure(DEPTH_BUCKETS * 4));
     *out = c.release();
     return GSB_OK;
@@ -219,8 +218,6 @@ int gsb_destroy(gsb_context* ctx)
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
-    if (ctx->plan_h) cudaFreeHost(ctx->plan_h);
-    if (ctx->plan_ev) cudaEventDestroy(ctx->plan_ev);
     cudaStream_t s = ctx->own_stream;
     delete ctx;
     if (s) cudaStreamDestroy(s);
@@ -259,6 +256,9 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
     case GSB_OPT_COMPACT:
         if (value < 0 || value > 2) return fail(GSB_ERR_INVALID, "GSB_OPT_COMPACT must be 0 (auto), 1 (always) or 2 (never)");
         ctx->compact_mode = (int)value; return GSB_OK;
+    case GSB_OPT_CHUNK_SHIFT:
+        if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_CHUNK_SHIFT must be 0 (auto) .. 16");
+        ctx->chunk_shift = (int)value; return GSB_OK;
     case GSB_OPT_DEPTH_CHUNKS:
         if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_DEPTH_CHUNKS must be 0 (auto) .. 16");
         ctx->depth_chunks = (int)value; return GSB_OK;
@@ -559,6 +559,7 @@ int gsb_generate_render_geometry(gsb_context* ctx)
         offset += cnt;
     }
     CU(cudaGetLastError());
+    ctx->sigma_valid = false;
     ctx->can_render = true;
     ctx->stats.repacked = 1;
     return GSB_OK;
@@ -601,7 +602,9 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
 
     // depth chunks: the frame is binned and blended front to back in nchunks ranges of the depth order
     int nchunks = ctx->depth_chunks;
-    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 3 : 1;                // auto (r01 sweep: 3-4 best at 20 M, 1 at 1 M)
+    // auto (r01 sweeps on B200): a small first chunk that saturates most tiles + one chunk for the rest
+    // (20 M: 2 chunks, first = V/16: 2.36 ms vs 2.53 for 3 geometric chunks; 5 M: first = V/8; 1 M: one chunk)
+    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 2 : 1;
     nchunks = std::min(nchunks, (int)MAX_CHUNKS);
 
     // Every depth key is the fp32 bit pattern of a squared distance from the camera to a point inside the packed set's
@@ -634,13 +637,11 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     // buffers
     // packed tile rectangles ride along as a payload (screens up to 512 x 512 tiles); otherwise exact rectangles by index
     const bool use_trects = fc.tiles_x <= 512 && fc.tiles_y <= 512;
-    const int  nbuf = nchunks > 1 ? 2 : 1;
-    for (int b = 0; b < nbuf; ++b) {
-        CU(ctx->keys[b].ensure(N * 4)); CU(ctx->vals[b].ensure(N * 4));
-        if (use_trects) CU(ctx->trects[b].ensure(N * 4));
-    }
-    CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16)); CU(ctx->positions.ensure(N * 4 + 16));
-    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N))); CU(ctx->scan_scratch.ensure(scan_scratch_bytes(N)));
+    CU(ctx->keys.ensure(N * 4));
+    if (use_trects) CU(ctx->trects.ensure(N * 4));
+    CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16));
+    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N)));
+    CU(ctx->scan_scratch.ensure(std::max(scan_scratch_bytes(N), select_scratch_bytes(n))));
     CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
     CU(ctx->tile_done.ensure((size_t)num_tiles * 4));
     float4* fb = nullptr;
@@ -649,41 +650,40 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
     float4* fb_final = (target && target->final_rgba) ? static_cast<float4*>(target->final_rgba) : fb;
 
-    unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D [2] D_c [3] sort error [4] done tiles [5] L
+    unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D_c [2] sort/scan error [3] done tiles [4] D [5] L [6] scan total
     const bool tm = ctx->stage_timing;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_START], s));
     CU(cudaMemsetAsync(cnt, 0, 64, s));
 
     // K1: cull + depth key + tile rectangle for every submitted splat (+ the depth-bucket histogram)
-    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>() };
+    if (!ctx->sigma_valid || memcmp(ctx->sigma_object, fr->object, 64) != 0) {      // the covariance cache follows the object matrix
+        CU(ctx->sigA.ensure(N * 16)); CU(ctx->sigB.ensure(N * 8));
+        launch_sigma(fr->object, ctx->geomB.as<uint4>(), n, ctx->sigA.as<float4>(), ctx->sigB.as<float2>(), s);
+        memcpy(ctx->sigma_object, fr->object, 64);
+        ctx->sigma_valid = true;
+        st.launches += 1;
+    }
+    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), ctx->sigA.as<float4>(), ctx->sigB.as<float2>() };
     uint32_t* bucket_hist = nchunks > 1 ? ctx->bucket_hist.as<uint32_t>() : nullptr;
     if (bucket_hist) CU(cudaMemsetAsync(bucket_hist, 0, DEPTH_BUCKETS * 4, s));
-    launch_project(fc, ps, n, ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), ctx->rects.as<uint2>(),
-                   (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects[0].as<uint32_t>() : nullptr,
+    launch_project(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->rects.as<uint2>(),
+                   (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects.as<uint32_t>() : nullptr,
                    cnt + 0, db, bucket_hist, s);
     st.launches += 1;
-    if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
-
-    // K3a: cut the depth order into chunks WITHOUT sorting it: one stable partition pass on the chunk of each key's depth
-    // bucket.  Inside a chunk the splats stay in submission order; only the ones that reach a live tile are sorted later.
-    int src = 0;
-    int64_t chunk_size[MAX_CHUNKS + 1]; chunk_size[0] = n;
+    // The depth order is cut into chunks WITHOUT sorting or moving the cloud: the chunk plan maps every depth bucket to
+    // a chunk; each chunk then selects its own live splats with one 4-byte-per-splat scan of the keys.
+    const uint8_t* lut = nullptr;
     if (nchunks > 1) {
         ChunkPlan* plan = ctx->plan.as<ChunkPlan>();
-        launch_choose_chunks(bucket_hist, nchunks, plan, s);
-        CU(cudaMemcpyAsync(ctx->plan_h, plan, sizeof(uint32_t) * (MAX_CHUNKS + 1), cudaMemcpyDeviceToHost, s));
-        CU(cudaEventRecord(ctx->plan_ev, s));
-        partition_by_chunk(ctx->keys[0].as<uint32_t>(), ctx->vals[0].as<uint32_t>(), use_trects ? ctx->trects[0].as<uint32_t>() : nullptr,
-                           ctx->keys[1].as<uint32_t>(), ctx->vals[1].as<uint32_t>(), use_trects ? ctx->trects[1].as<uint32_t>() : nullptr,
-                           N, db, plan, ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
+        const int shift = ctx->chunk_shift > 0 ? ctx->chunk_shift
+                        : (ctx->depth_chunks > 0 ? nchunks : (n >= (int64_t)10000000 ? 4 : 3));   // explicit chunk count: geometric
+        launch_choose_chunks(bucket_hist, nchunks, shift, plan, s);
         st.launches += 1;
-        CU(cudaEventSynchronize(ctx->plan_ev));               // the plan arrives while the partition pass runs
-        for (int c = 0; c <= nchunks; ++c) chunk_size[c] = (int64_t)ctx->plan_h->size[c];
-        src = 1;
+        lut = plan->lut;
     }
-    const uint32_t* pkeys = ctx->keys[src].as<uint32_t>();
-    const uint32_t* pvals = ctx->vals[src].as<uint32_t>();
-    const uint32_t* ptrects = use_trects ? ctx->trects[src].as<uint32_t>() : nullptr;
+    const uint32_t* pkeys = ctx->keys.as<uint32_t>();
+    const uint32_t* ptrects = use_trects ? ctx->trects.as<uint32_t>() : nullptr;
+    if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
     if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
 
     // K3b + K4 + K2 + K5 per depth chunk.  The splats of the chunk that still touch a live tile (owned by this rank, not
@@ -701,22 +701,27 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const uint64_t owned_tiles = (uint64_t)owned_rows * (uint64_t)fc.tiles_x;
     uint64_t D_total = 0, L_total = 0, V = 0, D = 0, L = 0;
     int chunks_run = 0;
-    int64_t r0 = 0;
+    // upper bound of a chunk's live splats: the visible splats of the chunk (all of them for the first chunk); the
+    // live buffers are sized once for the cloud so no size has to come back from the device before the selection
+    for (int b = 0; b < 2; ++b) {
+        CU(ctx->lkeys[b].ensure(N * 4 + 16)); CU(ctx->lvals[b].ensure(N * 4 + 16));
+        if (use_trects) CU(ctx->ltrects[b].ensure(N * 4 + 16));
+    }
     for (int c = 0; c < nchunks; ++c) {
-        const int64_t cn = chunk_size[c];
         const bool first = (c == 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][0], s));
         uint32_t* counts = ctx->counts.as<uint32_t>();
-        uint32_t* positions = ctx->positions.as<uint32_t>();
-        CU(cudaMemsetAsync(cnt + 1, 0, 8, s));
-        launch_tile_counts(ptrects, pvals, ctx->rects.as<uint2>(), r0, cn, fc, first ? nullptr : tile_done, counts, cnt + 1, s);
-        exclusive_scan_flags_u32(counts, positions, (size_t)cn, ctx->scan_scratch.p, cnt + 5, s, &st.launches);
-        st.launches += 1;
+        // live selection, one pass over the keys: the splats of the chunk that still touch a live tile, compacted in
+        // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
+        launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, lut, db, c, fc,
+                           first ? nullptr : tile_done, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                           use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr, ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
+        st.launches += 3;
         // one host sync per chunk: V, this chunk's D and L, and the number of tiles saturated by the previous chunks
         CU(cudaMemcpyAsync(ctx->counters_h, cnt, 48, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        V = ctx->counters_h[0]; D = ctx->counters_h[1]; L = ctx->counters_h[5];
-        const bool all_done = ctx->counters_h[4] >= owned_tiles;        // implies D == 0
+        V = ctx->counters_h[0]; D = ctx->counters_h[4]; L = ctx->counters_h[5];
+        const bool all_done = ctx->counters_h[3] >= owned_tiles;        // implies D == 0
         // the last chunk that has work, or the last chunk at all, finalises the un-saturated tiles
         const bool last = (c == nchunks - 1) || all_done;
         if (D > 0x3fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^30-1 tile instances in one depth chunk");
@@ -726,21 +731,13 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
             if (tm) for (int e = 1; e < 5; ++e) CU(cudaEventRecord(ctx->evc[c][e], s));
             break;
         }
-        // compact the live splats (order preserving) and sort them by depth: stable LSD, ties keep ascending index
-        for (int b = 0; b < 2; ++b) {
-            CU(ctx->lkeys[b].ensure((size_t)L * 4 + 16)); CU(ctx->lvals[b].ensure((size_t)L * 4 + 16));
-            if (use_trects) CU(ctx->ltrects[b].ensure((size_t)L * 4 + 16));
-            CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16));
-        }
+        // depth sort of the live splats: stable LSD, ties keep ascending index
+        for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
         CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16));
         CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)std::max<uint64_t>(D, L))));
-        launch_compact_live(pkeys + r0, pvals + r0, ptrects ? ptrects + r0 : nullptr, counts, positions, cn,
-                            ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
-                            use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr, s);
-        st.launches += (cn > 0 ? 1 : 0);
         ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), (size_t)L, 0, key_bits,
-                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches,
+                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches,
                                           use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
                                           use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, key_min, key_span);
         const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
@@ -758,15 +755,14 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         st.launches += (L ? 2 : 0);
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
-                                         ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 3), s, &st.launches);
+                                         ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches);
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][3], s));
         launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fb_final, fc,
-                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 2, cnt + 4, s);
+                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 1, cnt + 3, s);
         st.launches += 1;
         if (tm) CU(cudaEventRecord(ctx->evc[c][4], s));
-        r0 += cn;
     }
     nchunks = chunks_run;
     CU(cudaGetLastError());
@@ -774,7 +770,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const uint64_t D_last = D;      // the instance buffers hold the last chunk only
     D = D_total;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
-    CU(cudaMemcpyAsync(ctx->counters_h + 2, cnt + 2, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
+    CU(cudaMemcpyAsync(ctx->counters_h + 1, cnt + 1, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
 
     if (target && target->host_rgba) {
         CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
@@ -840,8 +836,8 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     gsb_stats& st = ctx->stats;
-    if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[2];
-    if (st.rendered && ctx->counters_h[3] != 0ull)
+    if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[1];
+    if (st.rendered && ctx->counters_h[2] != 0ull)
         return fail(GSB_ERR_CUDA, "radix sort look-back timed out (internal error); the last frame is invalid");
     st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = st.ms_records = 0.0f;
     if (st.rendered && ctx->ev_valid) {
@@ -912,7 +908,7 @@ int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, 
     const void* src = nullptr; uint64_t need = 0;
     const uint64_t n = (uint64_t)ctx->last_n, d = ctx->last_d, t = (uint64_t)ctx->last_tiles;
     switch (which) {
-    case GSB_DBG_KEYS_UNSORTED: src = ctx->keys[0].p; need = n * 4; break;
+    case GSB_DBG_KEYS_UNSORTED: src = ctx->keys.p; need = n * 4; break;
     case GSB_DBG_ORDER:         src = ctx->lvals[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
     case GSB_DBG_KEYS_SORTED:   src = ctx->lkeys[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
     case GSB_DBG_RECORDS:       src = ctx->dbg_recs.p; need = ctx->keep_intermediates ? n * sizeof(Record) : 0; break;

@@ -20,9 +20,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// load 16 consecutive elements of this thread (vectorised when the chunk is full and aligned);
-// FLAG: scan the predicate (x != 0) instead of x
-template <bool FLAG>
+// load 16 consecutive elements of this thread (vectorised when the chunk is full and aligned)
 __device__ __forceinline__ void load_items(const uint32_t* __restrict__ in, size_t base, size_t n,
                                            uint32_t (&x)[SCAN_ITEMS])
 {
@@ -38,19 +36,14 @@ __device__ __forceinline__ void load_items(const uint32_t* __restrict__ in, size
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k) x[k] = (first + k < n) ? in[first + k] : 0u;
     }
-    if (FLAG) {
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) x[k] = x[k] ? 1u : 0u;
-    }
 }
 
-template <bool FLAG>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, size_t n,
                                                                    uint32_t* __restrict__ partial)
 {
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     uint32_t x[SCAN_ITEMS];
-    load_items<FLAG>(in, (size_t)blockIdx.x * SCAN_CHUNK, n, x);
+    load_items(in, (size_t)blockIdx.x * SCAN_CHUNK, n, x);
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) s += x[k];
@@ -107,7 +100,6 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(const uint32_t* __r
     if (threadIdx.x == 0 && total) *total = carry_s;
 }
 
-template <bool FLAG>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ in,
                                                                   uint32_t* __restrict__ out, size_t n,
                                                                   const unsigned long long* __restrict__ prefix)
@@ -116,7 +108,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t base = (size_t)blockIdx.x * SCAN_CHUNK;
     uint32_t x[SCAN_ITEMS];
-    load_items<FLAG>(in, base, n, x);
+    load_items(in, base, n, x);
     uint32_t tsum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) tsum += x[k];
@@ -150,9 +142,8 @@ size_t scan_scratch_bytes(size_t n)
     return ((m * sizeof(uint32_t) + 255) & ~size_t(255)) + m * sizeof(unsigned long long) + 256;
 }
 
-template <bool FLAG>
-static void scan_impl(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
-                      unsigned long long* total_dev, cudaStream_t s, int* launches)
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
+                        unsigned long long* total_dev, cudaStream_t s, int* launches)
 {
     if (n == 0) {
         if (total_dev) cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), s);
@@ -162,22 +153,10 @@ static void scan_impl(const uint32_t* in, uint32_t* out, size_t n, void* scratch
     uint32_t* partial = static_cast<uint32_t*>(scratch);
     unsigned long long* prefix = reinterpret_cast<unsigned long long*>(
         static_cast<char*>(scratch) + (((m + 1) * sizeof(uint32_t) + 255) & ~size_t(255)));
-    scan_reduce_kernel<FLAG><<<(unsigned)m, SCAN_THREADS, 0, s>>>(in, n, partial);
+    scan_reduce_kernel<<<(unsigned)m, SCAN_THREADS, 0, s>>>(in, n, partial);
     scan_partials_kernel<<<1, 1024, 0, s>>>(partial, m, prefix, total_dev);
-    scan_apply_kernel<FLAG><<<(unsigned)m, SCAN_THREADS, 0, s>>>(in, out, n, prefix);
+    scan_apply_kernel<<<(unsigned)m, SCAN_THREADS, 0, s>>>(in, out, n, prefix);
     if (launches) *launches += 3;
-}
-
-void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
-                        unsigned long long* total_dev, cudaStream_t s, int* launches)
-{
-    scan_impl<false>(in, out, n, scratch, total_dev, s, launches);
-}
-
-void exclusive_scan_flags_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
-                              unsigned long long* total_dev, cudaStream_t s, int* launches)
-{
-    scan_impl<true>(in, out, n, scratch, total_dev, s, launches);
 }
 
 }  // namespace gsb

@@ -115,6 +115,8 @@ enum gsb_option {
     GSB_OPT_KEEP_INTERMEDIATES = 4, /* keep unsorted keys etc. for gsb_debug_fetch (default 0) */
     GSB_OPT_COMPACT = 6,         /* accepted for ABI compatibility, no effect: the live splats of every depth chunk are always
                                     compacted before their depth sort */
+    GSB_OPT_CHUNK_SHIFT = 7,     /* the first depth chunk holds V / 2^shift visible splats, each further chunk doubles, the last
+                                    takes the rest; 0 = auto.  Any value gives the same frame */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };

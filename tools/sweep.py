@@ -19,8 +19,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="20M_sh3_1080p")
     ap.add_argument("--chunks", default="1,2,3,4,5,6")
+    ap.add_argument("--shifts", default="0", help="GSB_OPT_CHUNK_SHIFT values (first chunk = V / 2^shift; 0 = auto)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--env", default="", help="semicolon-separated experiment settings, each a comma-separated list of "
+                                              "NAME=VALUE library knobs (GSB_K1_OCC, GSB_BLEND_OBB), e.g. 'GSB_K1_OCC=4;GSB_K1_OCC=6'")
     a = ap.parse_args()
     import torch
     from houdini_gsplat_renderer_b200 import renderer as R, scene as S
@@ -35,7 +38,13 @@ def main():
     rid = r.registerUpdate(0xB200, (1, 0, 0, 0), 0, cloud)
     fb = torch.zeros((w["height"], w["width"], 4), dtype=torch.float32, device="cuda")
     ref = None
-    for c in [int(x) for x in a.chunks.split(",")]:
+    import os
+    settings = [(c, sh, e) for e in (a.env.split(";") if a.env else [""]) for c in [int(x) for x in a.chunks.split(",")]
+                for sh in [int(x) for x in a.shifts.split(",")]]
+    for c, sh, envs in settings:
+        r.set_option(R.OPT_CHUNK_SHIFT, sh)
+        for kv in filter(None, envs.split(",")):
+            k, v = kv.split("="); os.environ[k] = v
         r.set_option(R.OPT_DEPTH_CHUNKS, c)
 
         def step(i):
@@ -59,6 +68,8 @@ def main():
         out = {k: round(v / a.steps, 4) for k, v in acc.items()}
         out["ms_frame"] = round(e0.elapsed_time(e1) / a.steps, 4)
         out["chunks_requested"] = c
+        out["chunk_shift"] = sh
+        out["env"] = envs
         out["workload"] = a.workload
         if not w["orbit"]:
             cur = fb.cpu().numpy()
