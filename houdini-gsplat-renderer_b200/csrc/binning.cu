@@ -49,6 +49,31 @@ __device__ __forceinline__ TileRect tile_rect_packed(const bool has_packed, cons
     return t;
 }
 
+// Saturation flags (tile_done): one BIT per tile, rows padded to whole 32-bit words (done_words_per_row), set by the
+// blend of an earlier depth chunk.  The live tiles of a splat's row segment [tx0, tx1] are then a mask and a popcount
+// per word (one word for almost every splat) instead of a load per tile.
+__device__ __forceinline__ uint32_t live_word(const uint32_t* __restrict__ done, int wpr, int ty, int w, int tx0, int tx1)
+{
+    uint32_t m = 0xffffffffu;
+    if (w == (tx0 >> 5)) m &= 0xffffffffu << (tx0 & 31);
+    if (w == (tx1 >> 5)) m &= 0xffffffffu >> (31 - (tx1 & 31));
+    return m & ~__ldg(done + ty * wpr + w);
+}
+
+// number of live tiles of rectangle t: rows this rank owns, tiles not yet saturated
+__device__ __forceinline__ uint32_t live_tiles(const TileRect& t, int tiles_x, int row_rank, int row_world, int row_group,
+                                               const uint32_t* __restrict__ done)
+{
+    uint32_t c = 0;
+    const int wpr = done_words_per_row(tiles_x);
+    for (int ty = t.ty0; ty <= t.ty1; ++ty) {
+        if (!owns_row(ty, row_rank, row_world, row_group)) continue;
+        if (!done) c += (uint32_t)(t.tx1 - t.tx0 + 1);
+        else for (int w = t.tx0 >> 5; w <= (t.tx1 >> 5); ++w) c += __popc(live_word(done, wpr, ty, w, t.tx0, t.tx1));
+    }
+    return c;
+}
+
 // counts[k] = number of live tiles touched by element r0 + k (0 for culled splats); a coalesced 4-byte stream.
 // A tile is live if this rank owns its row and it is not yet saturated (tile_done, set by the blend
 // of an earlier depth chunk): instances behind a saturated tile can never change a pixel.
@@ -62,13 +87,7 @@ tile_count_kernel(const uint32_t* __restrict__ trects, const uint32_t* __restric
     uint32_t c = 0;
     if (k < n) {
         const TileRect t = tile_rect_of(trects, order, rects, r0 + k);
-        if (!t.empty) {
-            for (int ty = t.ty0; ty <= t.ty1; ++ty) {
-                if (!owns_row(ty, row_rank, row_world, row_group)) continue;
-                if (!tile_done) c += (uint32_t)(t.tx1 - t.tx0 + 1);
-                else for (int tx = t.tx0; tx <= t.tx1; ++tx) c += (__ldg(tile_done + ty * tiles_x + tx) == 0u) ? 1u : 0u;
-            }
-        }
+        if (!t.empty) c = live_tiles(t, tiles_x, row_rank, row_world, row_group, tile_done);
         counts[k] = c;
     }
     if (d_total) {
@@ -78,34 +97,37 @@ tile_count_kernel(const uint32_t* __restrict__ trects, const uint32_t* __restric
 }
 
 // ---- live selection, per depth chunk, over the submitted splats (which are never moved).  Element k is selected if its
-// depth bucket belongs to the chunk (lut[depth_bucket(key)] == chunk; lut == NULL: every element) and it touches at
-// least one live tile.  Three kernels, no spin-waits:
-//   A  select_count: one CTA per 2048 elements streams the keys and packed tile rectangles (8 B / splat, all loads
-//      issued before any is used); writes one ballot word per 32 elements (N/8 bytes) and the tile's totals.
-//   S  select_scan:  one CTA turns the per-tile totals into exclusive bases and the grand totals L and D.
-//   B  select_write: scatters the selected (key, splat index, tile rectangle) triples to base + rank, in submission
-//      order, so the stable depth sort that follows breaks ties by ascending index.  CTAs of tiles without a selected
-//      element exit at once (deep chunks: most of them).
-// (r01 measured two other forms first.  A single-pass chained scan: with ~5000 tiles in flight the decoupled look-back
+// depth key lies in the chunk's key interval [key_lo, key_hi) (the chunk plan turns its bucket boundaries into key
+// boundaries, so membership is two integer compares) and it touches at least one live tile.  Three kernels, no spin-waits:
+//   A  select_count:  one CTA per 2048 elements streams the keys and packed tile rectangles (8 B / splat, all loads
+//      issued before any is used), compacts the selected (key, splat index, tile rectangle) triples order-preservingly
+//      INSIDE the CTA and stores them as one contiguous run at the CTA's own slot of a staging area
+//      (stage[tile * 2048 ..]); writes the tile's totals.
+//   S  select_scan:   one CTA turns the per-tile totals into exclusive bases and the grand totals L and D.
+//   B  select_gather: moves every tile's run to base[tile]: contiguous reads, contiguous writes, 12 B per SELECTED
+//      element.  Submission order is kept, so the stable depth sort that follows breaks ties by ascending index.
+// (r01 measured three other forms first.  A single-pass chained scan: with ~5000 tiles in flight the decoupled look-back
 // chains grew to the number of resident CTAs, 260-320 us per pass.  Loading the rectangle only for the chunk's own
-// elements: the dependent, divergent loads serialised, 130-210 us.  Streaming both arrays unconditionally is faster.)
+// elements: the dependent, divergent loads serialised, 130-210 us.  Ballot words + a second pass that re-reads keys and
+// rectangles of the selected elements: the sparse 32-byte-sector gathers cost 81 us per chunk at 20 M, DRAM-latency bound.)
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_WARPS   = SEL_THREADS / 32;
 constexpr int SEL_ITEMS   = 8;
 constexpr int SEL_TILE    = SEL_THREADS * SEL_ITEMS;     // 2048 elements per CTA
-constexpr int SEL_WORDS   = SEL_TILE / 32;               // ballot words per tile (64)
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects,
-                    const uint2* __restrict__ rects, int64_t n, const uint8_t* __restrict__ lut, const DepthBuckets db,
-                    const uint32_t chunk,
+                    const uint2* __restrict__ rects, int64_t n, const ChunkPlan* __restrict__ plan, const int chunk,
                     int tiles_x, int row_rank, int row_world, int row_group, const uint32_t* __restrict__ tile_done,
-                    uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
+                    uint32_t* __restrict__ stage_k, uint32_t* __restrict__ stage_v, uint32_t* __restrict__ stage_t,
+                    uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
 {
     __shared__ uint32_t s_wl[SEL_WARPS], s_wd[SEL_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
     const int64_t base = (int64_t)tile * SEL_TILE + (int64_t)warp * (32 * SEL_ITEMS);
+    const uint32_t key_lo = plan ? __ldg(&plan->key_lo[chunk]) : 0u;
+    const uint32_t key_hi = plan ? __ldg(&plan->key_lo[chunk + 1]) : KEY_CULLED;
 
     // warp-striped items: item j of lane l is element base + j*32 + l, so (j, lane) order is element order
     uint32_t key[SEL_ITEMS], tr[SEL_ITEMS];
@@ -115,34 +137,37 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
         key[j] = (k < n) ? __ldg(keys + k) : KEY_CULLED;
         tr[j]  = (k < n && trects) ? __ldg(trects + k) : 0u;
     }
-    uint32_t dsum = 0, wcount = 0, mymask = 0;          // lane j keeps the ballot word of item j
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t dsum = 0, wcount = 0, selbits = 0;
+    uint32_t pos[SEL_ITEMS];                            // rank of item j among the warp's selected elements
 #pragma unroll
     for (int j = 0; j < SEL_ITEMS; ++j) {
         uint32_t c = 0;
-        if (key[j] != KEY_CULLED && (!lut || (uint32_t)__ldg(lut + depth_bucket(key[j], db)) == chunk)) {
+        if (key[j] >= key_lo && key[j] < key_hi) {      // key_hi <= KEY_CULLED: culled splats never pass
             const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane);
-            if (!t.empty) {
-                for (int ty = t.ty0; ty <= t.ty1; ++ty) {
-                    if (!owns_row(ty, row_rank, row_world, row_group)) continue;
-                    if (!tile_done) c += (uint32_t)(t.tx1 - t.tx0 + 1);
-                    else for (int tx = t.tx0; tx <= t.tx1; ++tx) c += (__ldg(tile_done + ty * tiles_x + tx) == 0u) ? 1u : 0u;
-                }
-            }
+            if (!t.empty) c = live_tiles(t, tiles_x, row_rank, row_world, row_group, tile_done);
         }
         dsum += c;
         const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
-        if (lane == j) mymask = m;
+        pos[j] = wcount + __popc(m & lt);
+        selbits |= (c != 0u ? 1u : 0u) << j;
         wcount += __popc(m);
     }
-    if (lane < SEL_ITEMS) masks[(size_t)tile * SEL_WORDS + warp * SEL_ITEMS + lane] = mymask;
     dsum = __reduce_add_sync(0xffffffffu, dsum);
     if (lane == 0) { s_wl[warp] = wcount; s_wd[warp] = dsum; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t l = 0, d = 0;
+    uint32_t wbase = 0, l = 0, d = 0;
 #pragma unroll
-        for (int w = 0; w < SEL_WARPS; ++w) { l += s_wl[w]; d += s_wd[w]; }
-        tile_l[tile] = l; tile_d[tile] = d;
+    for (int w = 0; w < SEL_WARPS; ++w) { wbase += (w < warp) ? s_wl[w] : 0u; l += s_wl[w]; d += s_wd[w]; }
+    if (threadIdx.x == 0) { tile_l[tile] = l; tile_d[tile] = d; }
+    const size_t sb = (size_t)tile * SEL_TILE + wbase;
+#pragma unroll
+    for (int j = 0; j < SEL_ITEMS; ++j) {
+        if ((selbits >> j) & 1u) {
+            const size_t o = sb + pos[j];
+            stage_k[o] = key[j]; stage_v[o] = (uint32_t)(base + j * 32 + lane);
+            if (stage_t) stage_t[o] = tr[j];
+        }
     }
 }
 
@@ -187,37 +212,23 @@ select_scan_kernel(const uint32_t* __restrict__ tile_l, const uint32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
-select_write_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects, int64_t n,
-                    const uint32_t* __restrict__ masks, const uint32_t* __restrict__ tile_l, const uint32_t* __restrict__ tile_base,
-                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t* __restrict__ trects_out)
+// one warp per selection tile: copy its run of selected triples from the staging slot to base[tile]
+constexpr int GATHER_THREADS = 256;
+__global__ void __launch_bounds__(GATHER_THREADS)
+select_gather_kernel(const uint32_t* __restrict__ stage_k, const uint32_t* __restrict__ stage_v,
+                     const uint32_t* __restrict__ stage_t, const uint32_t* __restrict__ tile_l,
+                     const uint32_t* __restrict__ tile_base, uint32_t nt,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t* __restrict__ trects_out)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    if (tile_l[tile] == 0u) return;                      // CTA-uniform
-    // offset of this warp inside the tile: selected elements of the warps before it
-    const uint32_t* tm = masks + (size_t)tile * SEL_WORDS;
-    uint32_t pre = 0;
-#pragma unroll
-    for (int q = 0; q < SEL_WORDS / 32; ++q) {
-        const int wi = q * 32 + lane;
-        pre += (wi < warp * SEL_ITEMS) ? __popc(__ldg(tm + wi)) : 0u;
-    }
-    pre = __reduce_add_sync(0xffffffffu, pre);
-    const uint32_t mymask = (lane < SEL_ITEMS) ? __ldg(tm + warp * SEL_ITEMS + lane) : 0u;
-    uint32_t p = tile_base[tile] + pre;
-    const unsigned lt = (1u << lane) - 1u;
-    const int64_t base = (int64_t)tile * SEL_TILE + (int64_t)warp * (32 * SEL_ITEMS);
-#pragma unroll
-    for (int j = 0; j < SEL_ITEMS; ++j) {
-        const unsigned m = __shfl_sync(0xffffffffu, mymask, j);
-        if ((m >> lane) & 1u) {
-            const int64_t k = base + j * 32 + lane;
-            const uint32_t o = p + __popc(m & lt);
-            keys_out[o] = __ldg(keys + k); vals_out[o] = (uint32_t)k;
-            if (trects) trects_out[o] = __ldg(trects + k);
-        }
-        p += __popc(m);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
+    if (tile >= nt) return;
+    const uint32_t l = __ldg(tile_l + tile);
+    if (l == 0u) return;
+    const size_t src = (size_t)tile * SEL_TILE, dst = (size_t)__ldg(tile_base + tile);
+    for (uint32_t i = lane; i < l; i += 32) {
+        keys_out[dst + i] = __ldg(stage_k + src + i); vals_out[dst + i] = __ldg(stage_v + src + i);
+        if (stage_t) trects_out[dst + i] = __ldg(stage_t + src + i);
     }
 }
 
@@ -235,14 +246,20 @@ emit_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tre
     if (o1 == o0) return;                                    // culled, or every tile it touches is saturated
     const TileRect t = tile_rect_of(trects, order, rects, k);
     size_t o = o0;
+    const int wpr = done_words_per_row(tiles_x);
     for (int ty = t.ty0; ty <= t.ty1; ++ty) {
         if (!owns_row(ty, row_rank, row_world, row_group)) continue;
-        for (int tx = t.tx0; tx <= t.tx1; ++tx) {
-            const uint32_t tile = (uint32_t)(ty * tiles_x + tx);
-            if (tile_done && __ldg(tile_done + tile) != 0u) continue;
-            inst_keys[o] = tile;
-            inst_vals[o] = (uint32_t)k;
-            ++o;
+        if (!tile_done) {
+            for (int tx = t.tx0; tx <= t.tx1; ++tx) { inst_keys[o] = (uint32_t)(ty * tiles_x + tx); inst_vals[o] = (uint32_t)k; ++o; }
+        } else {
+            for (int w = t.tx0 >> 5; w <= (t.tx1 >> 5); ++w) {
+                uint32_t live = live_word(tile_done, wpr, ty, w, t.tx0, t.tx1);
+                while (live) {                                   // ascending columns
+                    const int b = __ffs(live) - 1;
+                    live &= live - 1;
+                    inst_keys[o] = (uint32_t)(ty * tiles_x + w * 32 + b); inst_vals[o] = (uint32_t)k; ++o;
+                }
+            }
         }
     }
 }
@@ -286,12 +303,14 @@ void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uin
 
 static inline size_t sel_tiles(int64_t n) { return (size_t)((n + SEL_TILE - 1) / SEL_TILE); }
 
-size_t select_scratch_bytes(int64_t n) { return sel_tiles(n) * (SEL_WORDS + 3) * sizeof(uint32_t) + 64; }
+size_t select_scratch_bytes(int64_t n) { return sel_tiles(n) * 3 * sizeof(uint32_t) + 64; }
+size_t select_stage_elems(int64_t n) { return sel_tiles(n) * SEL_TILE; }
 
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
-                        const uint8_t* lut, DepthBuckets db, int chunk,
+                        const ChunkPlan* plan, int chunk,
                         FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
-                        uint32_t* trects_out, void* scratch, unsigned long long* l_total, unsigned long long* d_total,
+                        uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
+                        void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s)
 {
     if (n <= 0) return;
@@ -299,11 +318,12 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
     uint32_t* tile_l = static_cast<uint32_t*>(scratch);
     uint32_t* tile_d = tile_l + nt;
     uint32_t* tile_base = tile_d + nt;
-    uint32_t* masks  = tile_base + nt;
-    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, lut, db, (uint32_t)chunk, fc.tiles_x, fc.row_rank,
-                                                   fc.row_world, fc.row_group, tile_done, masks, tile_l, tile_d);
+    if (!trects) stage_t = nullptr;
+    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, fc.row_rank,
+                                                   fc.row_world, fc.row_group, tile_done, stage_k, stage_v, stage_t, tile_l, tile_d);
     select_scan_kernel<<<1, 1024, 0, s>>>(tile_l, tile_d, nt, tile_base, l_total, d_total);
-    select_write_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, n, masks, tile_l, tile_base, keys_out, vals_out, trects_out);
+    select_gather_kernel<<<(nt + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32), GATHER_THREADS, 0, s>>>(
+        stage_k, stage_v, stage_t, tile_l, tile_base, nt, keys_out, vals_out, trects_out);
 }
 
 void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,

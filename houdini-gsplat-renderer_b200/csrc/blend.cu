@@ -54,7 +54,8 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     const int tile = blockIdx.x;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
     if (!owns_row(ty, F.row_rank, F.row_world, F.row_group)) return;      // CTA-uniform
-    if (!first && tile_done[tile] != 0u) return;                          // saturated and finalised in an earlier chunk
+    uint32_t* const done_word = tile_done + ty * done_words_per_row(F.tiles_x) + (tx >> 5);
+    if (!first && ((*done_word >> (tx & 31)) & 1u) != 0u) return;         // saturated and finalised in an earlier chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bx = tx * TILE + (warp & 1) * 8, by = ty * TILE + (warp >> 1) * 4;
@@ -171,7 +172,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
         else fb[(size_t)py * F.width + px] = make_float4(Cr, Cg, Cb, T);
     }
     if (tid == 0) {
-        if (tile_saturated) { tile_done[tile] = 1u; atomicAdd(done_tiles, 1ull); }
+        if (tile_saturated) { atomicOr(done_word, 1u << (tx & 31)); atomicAdd(done_tiles, 1ull); }
         if (tile_consumed) tile_consumed[tile] += s_consumed;
         if (consumed_total && s_consumed) atomicAdd(consumed_total, (unsigned long long)s_consumed);
     }

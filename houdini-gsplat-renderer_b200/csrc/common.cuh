@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t depth_bucket(uint32_t key, DepthBuckets db)
 // Chunk plan chosen on the device from the bucket histogram (choose_chunks).
 struct ChunkPlan {
     uint32_t size[MAX_CHUNKS + 1];             // visible splats per chunk; entry nchunks = culled
+    uint32_t key_lo[MAX_CHUNKS + 2];           // chunk c holds the keys in [key_lo[c], key_lo[c + 1]); key_lo[nchunks] = KEY_CULLED
     uint8_t  lut[DEPTH_BUCKETS];               // bucket -> chunk
 };
 
@@ -105,7 +106,9 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
 // chunk plan from the bucket histogram: chunk c (< nchunks - 1) ends at the first bucket whose exclusive count reaches
 // V * (2^(c+1) - 1) / 2^shift (the first chunk holds V / 2^shift splats, every further one doubles; the last takes the rest)
-void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, ChunkPlan* plan, cudaStream_t s);
+// and the bucket boundaries are turned into key boundaries (plan->key_lo: the smallest key whose bucket belongs to the
+// chunk, found by bisection over the monotone map key -> bucket -> chunk), so membership is two integer compares
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s);
 // K2 (only splats that reach a live tile, in depth order): gather the splat's 128-byte line, redo the projection,
 // evaluate SH, write the 48-byte record of live rank j to recs[j]
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
@@ -114,19 +117,23 @@ void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_
 // binning.cu
 // counts[k] = live tiles touched by element r0 + k of (trects, order); trects = packed tile rectangles aligned with
 // order (NULL: read the exact rectangle rects[order[r]], which "wide" entries always do); tile_done (may be NULL) =
-// saturation flags; *d_total += sum of the counts
+// saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) + tx / 32;
+// *d_total += sum of the counts
 void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
                         FrameConsts fc, const uint32_t* tile_done, uint32_t* counts, unsigned long long* d_total,
                         cudaStream_t s);
-// live selection of one depth chunk over the submitted splats: elements whose depth bucket belongs to the chunk
-// (lut[depth_bucket(key)] == chunk; lut NULL = all) and that touch a live tile are compacted, order preserving, into
-// (keys_out, vals_out = splat index, trects_out); *l_total = their number, *d_total = the instances they will emit.
-// scratch: select_scratch_bytes(n).  Three launches, no spin-waits.
+// live selection of one depth chunk over the submitted splats: elements whose depth key belongs to the chunk
+// (plan->key_lo[chunk] <= key < plan->key_lo[chunk + 1]; plan NULL = every visible splat) and that touch a live tile are
+// compacted, order preserving, into (keys_out, vals_out = splat index, trects_out); *l_total = their number, *d_total =
+// the instances they will emit.  stage_k/v/t: select_stage_elems(n) uint32 each (CTA-local runs before the gather; may be
+// the second halves of the sort's ping-pong buffers); scratch: select_scratch_bytes(n).  Three launches, no spin-waits.
 size_t select_scratch_bytes(int64_t n);
+size_t select_stage_elems(int64_t n);
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
-                        const uint8_t* lut, DepthBuckets db, int chunk,
+                        const ChunkPlan* plan, int chunk,
                         FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
-                        uint32_t* trects_out, void* scratch, unsigned long long* l_total, unsigned long long* d_total,
+                        uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
+                        void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s);
 // instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending;
 // offsets = exclusive scan of the tile counts, *total = its grand total (device)
@@ -151,7 +158,7 @@ void launch_ingest_sh_rest(const float* rest, int64_t n, uint16_t* shx, uint16_t
 
 // blend.cu
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
-// chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done;
+// chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done (bit map);
 // last: every remaining tile is finalised.  Finalised tiles are stored to fb_final (NULL = fb; may be peer memory).  *done_tiles counts the tiles flagged so far (early termination).
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
@@ -166,6 +173,9 @@ __host__ __device__ __forceinline__ uint32_t pack_trect(int tx0, int tx1, int ty
     const int w = tx1 - tx0, h = ty1 - ty0;
     return (uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(w > 127 ? 127 : w) << 18) | ((uint32_t)(h > 127 ? 127 : h) << 25);
 }
+
+// words per tile row of the saturation bit map (tile_done)
+__host__ __device__ __forceinline__ int done_words_per_row(int tiles_x) { return (tiles_x + 31) >> 5; }
 
 // tile-row ownership rule shared by every kernel
 __host__ __device__ __forceinline__ bool owns_row(int ty, int rank, int world, int group)

@@ -399,10 +399,12 @@ sigma_kernel(const __grid_constant__ ObjMat O, const uint4* __restrict__ geomB, 
 
 // ---- chunk plan: one CTA of DEPTH_BUCKETS threads
 __global__ void __launch_bounds__(DEPTH_BUCKETS)
-choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const int shift, ChunkPlan* __restrict__ plan)
+choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const int shift, const DepthBuckets db,
+                     ChunkPlan* __restrict__ plan)
 {
     __shared__ uint32_t wtot[DEPTH_BUCKETS / 32];
     __shared__ uint32_t csize[MAX_CHUNKS + 1];
+    __shared__ uint8_t  s_lut[DEPTH_BUCKETS];
     const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
     if (b <= MAX_CHUNKS) csize[b] = 0u;
     const uint32_t mine = (b < DEPTH_BUCKETS - 1) ? hist[b] : 0u;       // the last bucket holds the culled splats
@@ -422,11 +424,31 @@ choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const
         if (excl >= target && target > 0u) ++chunk;                     // thresholds ascend with c: monotone in b
     }
     if (b == DEPTH_BUCKETS - 1) chunk = nchunks;
-    plan->lut[b] = (uint8_t)chunk;
+    plan->lut[b] = (uint8_t)chunk; s_lut[b] = (uint8_t)chunk;
     const uint32_t cnt = (b == DEPTH_BUCKETS - 1) ? hist[b] : mine;
     if (cnt) atomicAdd(&csize[chunk], cnt);
     __syncthreads();
     if (b <= MAX_CHUNKS) plan->size[b] = (b <= nchunks) ? csize[b] : 0u;
+    // key boundaries: key -> bucket -> chunk is monotone, so chunk c starts at the smallest key whose chunk is >= c
+    // (bisection over the non-negative fp32 bit patterns up to +inf); chunks beyond the last non-empty one start at
+    // KEY_CULLED, i.e. are empty
+    if (b <= nchunks) {
+        uint32_t klo = 0u;
+        if (b == nchunks) klo = KEY_CULLED;
+        else if (b > 0) {
+            uint32_t lo = 0u, hi = 0x7F800000u;
+            if ((int)s_lut[depth_bucket(hi, db)] < b) klo = KEY_CULLED;
+            else {
+                while (lo < hi) {
+                    const uint32_t mid = lo + ((hi - lo) >> 1);
+                    if ((int)s_lut[depth_bucket(mid, db)] >= b) hi = mid; else lo = mid + 1u;
+                }
+                klo = lo;
+            }
+        }
+        plan->key_lo[b] = klo;
+    }
+    if (b == nchunks + 1 && b <= MAX_CHUNKS + 1) plan->key_lo[b] = KEY_CULLED;
 }
 
 // ---- K2: one thread per live splat, in depth order.  The splat's whole 128-byte line (geometry + colour + SH) is
@@ -522,9 +544,9 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
 #undef GSB_K1
 }
 
-void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, ChunkPlan* plan, cudaStream_t s)
+void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s)
 {
-    choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, plan);
+    choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, db, plan);
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,

@@ -106,6 +106,7 @@ struct gsb_context {
     bool    stage_timing = false, keep_intermediates = false;
     int     depth_chunks = 0;                                 // 0 = auto
     int     chunk_shift = 0;                                  // first chunk = V / 2^shift; 0 = auto (= depth_chunks)
+    bool    host_direct = true;                               // finished tiles go straight to pinned host targets
     int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
@@ -256,6 +257,7 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
     case GSB_OPT_COMPACT:
         if (value < 0 || value > 2) return fail(GSB_ERR_INVALID, "GSB_OPT_COMPACT must be 0 (auto), 1 (always) or 2 (never)");
         ctx->compact_mode = (int)value; return GSB_OK;
+    case GSB_OPT_HOST_DIRECT: ctx->host_direct = value != 0; return GSB_OK;
     case GSB_OPT_CHUNK_SHIFT:
         if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_CHUNK_SHIFT must be 0 (auto) .. 16");
         ctx->chunk_shift = (int)value; return GSB_OK;
@@ -643,12 +645,23 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N)));
     CU(ctx->scan_scratch.ensure(std::max(scan_scratch_bytes(N), select_scratch_bytes(n))));
     CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
-    CU(ctx->tile_done.ensure((size_t)num_tiles * 4));
+    const size_t done_bytes = (size_t)done_words_per_row(fc.tiles_x) * (size_t)fc.tiles_y * 4;      // one bit per tile
+    CU(ctx->tile_done.ensure(done_bytes));
     float4* fb = nullptr;
     const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
     if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
     else { CU(ctx->fb.ensure(fb_bytes)); fb = ctx->fb.as<float4>(); }
     float4* fb_final = (target && target->final_rgba) ? static_cast<float4*>(target->final_rgba) : fb;
+    // A pinned, device-addressable host target receives the finished tiles directly from the blend kernel (zero-copy
+    // stores over PCIe, overlapped with the binning of the deeper chunks) instead of a D2H pass after the frame.
+    bool host_is_final = false;
+    if (target && target->host_rgba && !target->final_rgba && ctx->host_direct && fr->row_world == 1) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, target->host_rgba) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            fb_final = static_cast<float4*>(pa.devicePointer);
+            host_is_final = true;
+        } else (void)cudaGetLastError();
+    }
 
     unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D_c [2] sort/scan error [3] done tiles [4] D [5] L [6] scan total
     const bool tm = ctx->stage_timing;
@@ -672,14 +685,14 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     st.launches += 1;
     // The depth order is cut into chunks WITHOUT sorting or moving the cloud: the chunk plan maps every depth bucket to
     // a chunk; each chunk then selects its own live splats with one 4-byte-per-splat scan of the keys.
-    const uint8_t* lut = nullptr;
+    const ChunkPlan* chunk_plan = nullptr;
     if (nchunks > 1) {
         ChunkPlan* plan = ctx->plan.as<ChunkPlan>();
         const int shift = ctx->chunk_shift > 0 ? ctx->chunk_shift
                         : (ctx->depth_chunks > 0 ? nchunks : (n >= (int64_t)10000000 ? 4 : 3));   // explicit chunk count: geometric
-        launch_choose_chunks(bucket_hist, nchunks, shift, plan, s);
+        launch_choose_chunks(bucket_hist, nchunks, shift, db, plan, s);
         st.launches += 1;
-        lut = plan->lut;
+        chunk_plan = plan;
     }
     const uint32_t* pkeys = ctx->keys.as<uint32_t>();
     const uint32_t* ptrects = use_trects ? ctx->trects.as<uint32_t>() : nullptr;
@@ -691,7 +704,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     // pixels all saturated are flagged.  The per-pixel sequence of blended instances is the one a single global sort
     // would give, so the frame is bit-identical to the single-chunk result.
     uint32_t* tile_done = ctx->tile_done.as<uint32_t>();
-    CU(cudaMemsetAsync(tile_done, 0, (size_t)num_tiles * 4, s));
+    CU(cudaMemsetAsync(tile_done, 0, done_bytes, s));
     CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));     // accumulates over chunks
     if (fr->row_world > 1 && fb_final == fb) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));   // rows this rank does not own stay zero
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
@@ -703,9 +716,11 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     int chunks_run = 0;
     // upper bound of a chunk's live splats: the visible splats of the chunk (all of them for the first chunk); the
     // live buffers are sized once for the cloud so no size has to come back from the device before the selection
+    // (the second halves double as the selection's staging area: CTA-local runs, dead before the sort ping-pongs)
+    const size_t live_bytes = select_stage_elems(n) * 4 + 16;
     for (int b = 0; b < 2; ++b) {
-        CU(ctx->lkeys[b].ensure(N * 4 + 16)); CU(ctx->lvals[b].ensure(N * 4 + 16));
-        if (use_trects) CU(ctx->ltrects[b].ensure(N * 4 + 16));
+        CU(ctx->lkeys[b].ensure(live_bytes)); CU(ctx->lvals[b].ensure(live_bytes));
+        if (use_trects) CU(ctx->ltrects[b].ensure(live_bytes));
     }
     for (int c = 0; c < nchunks; ++c) {
         const bool first = (c == 0);
@@ -713,9 +728,11 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         uint32_t* counts = ctx->counts.as<uint32_t>();
         // live selection, one pass over the keys: the splats of the chunk that still touch a live tile, compacted in
         // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
-        launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, lut, db, c, fc,
+        launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, chunk_plan, c, fc,
                            first ? nullptr : tile_done, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
-                           use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr, ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
+                           use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
+                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(),
+                           use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
         st.launches += 3;
         // one host sync per chunk: V, this chunk's D and L, and the number of tiles saturated by the previous chunks
         CU(cudaMemcpyAsync(ctx->counters_h, cnt, 48, cudaMemcpyDeviceToHost, s));
@@ -773,9 +790,9 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     CU(cudaMemcpyAsync(ctx->counters_h + 1, cnt + 1, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
 
     if (target && target->host_rgba) {
-        CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
+        if (!host_is_final) CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
         if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
-        CU(cudaStreamSynchronize(s));
+        CU(cudaStreamSynchronize(s));                  // the call returns when the frame is in host memory
     } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
     if (target && target->gl_texture != 0) {
         // hand the frame to the viewport without a host round trip: device->device copy into the mapped

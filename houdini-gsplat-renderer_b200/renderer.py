@@ -19,7 +19,7 @@ LIB_PATH = HERE / "libgsplat_b200.so"
 ID_MAX = 128
 REFERENCE_SPLAT_CAP = 8388607
 
-OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS, OPT_COMPACT, OPT_CHUNK_SHIFT = 1, 2, 3, 4, 5, 6, 7
+OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS, OPT_COMPACT, OPT_CHUNK_SHIFT, OPT_HOST_DIRECT = 1, 2, 3, 4, 5, 6, 7, 8
 (DBG_KEYS_UNSORTED, DBG_ORDER, DBG_RECORDS, DBG_RECTS, DBG_TILE_RANGES, DBG_INSTANCES,
  DBG_FRAMEBUFFER, DBG_KEYS_SORTED, DBG_TILE_CONSUMED) = range(9)
 

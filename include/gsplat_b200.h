@@ -73,7 +73,8 @@ typedef struct gsb_frame {
  * library-owned device buffer (gsb_device_framebuffer). */
 typedef struct gsb_target {
     void*    device_rgba;    /* caller-owned device buffer, width*height*16 bytes; NULL = library buffer */
-    void*    host_rgba;      /* if non-NULL the frame is copied here (D2H inside the call, call returns when done) */
+    void*    host_rgba;      /* if non-NULL the frame is delivered here (D2H inside the call, call returns when done); see
+                                GSB_OPT_HOST_DIRECT for pinned memory */
     uint32_t gl_texture;     /* CUDA<->GL interop target: an RGBA32F GL_TEXTURE_2D of the frame size; the frame is copied into it
                                 device->device (cudaGraphicsGLRegisterImage).  Needs a current GL context on the calling thread
                                 (Houdini's main thread); without one the call fails with GSB_ERR_CUDA.  0 = none */
@@ -117,6 +118,10 @@ enum gsb_option {
                                     compacted before their depth sort */
     GSB_OPT_CHUNK_SHIFT = 7,     /* the first depth chunk holds V / 2^shift visible splats, each further chunk doubles, the last
                                     takes the rest; 0 = auto.  Any value gives the same frame */
+    GSB_OPT_HOST_DIRECT = 8,     /* 1 (default): when gsb_target.host_rgba is pinned host memory the device can address
+                                    (cudaHostAlloc / cudaHostRegister), the blend kernel stores finished tiles straight into it
+                                    over PCIe while later depth chunks are still being binned (no separate D2H pass);
+                                    pageable memory always takes the staged copy.  0: always cudaMemcpyAsync.  Same bytes */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };

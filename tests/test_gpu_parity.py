@@ -172,6 +172,30 @@ def test_final_frame_target_receives_finished_tiles(scene):
     r.close()
 
 
+def test_pinned_host_target_is_written_by_the_blend_kernel(scene):
+    """GSB_OPT_HOST_DIRECT: a pinned (device-addressable) host frame receives the finished tiles straight from the blend
+    kernel; the bytes equal the staged-copy path (pageable target / option off) for 1 and 3 depth chunks."""
+    import torch
+    from houdini_gsplat_renderer_b200 import renderer as R
+    S = scene
+    cl = S.make_cloud(150_000, 616, sh=True, scale_mult=2.0)
+    fr = S.orbit_frame(500, 281, 40.0)               # ragged tiles on both axes
+    r = R.GSplatRenderer(0)
+    rid = r.registerUpdate(9, (1, 0, 0, 0), 0, cl); r.setSphericalHarmonicsOrder(3)
+    ref = np.zeros((281, 500, 4), np.float32)        # pageable: staged cudaMemcpyAsync
+    r.draw([rid], fr, host_rgba=ref)
+    assert ref[..., 3].max() > 0.5
+    pinned = torch.full((281, 500, 4), -1.0, dtype=torch.float32).pin_memory()
+    for chunks in (1, 3):
+        for direct in (1, 0):
+            r.set_option(R.OPT_DEPTH_CHUNKS, chunks); r.set_option(R.OPT_HOST_DIRECT, direct)
+            pinned.fill_(-1.0)
+            r.draw([rid], fr, host_rgba=pinned.numpy())
+            assert np.array_equal(pinned.numpy(), ref), (chunks, direct)
+            assert np.array_equal(r.fetch(R.DBG_FRAMEBUFFER).reshape(281, 500, 4), ref)
+    r.close()
+
+
 @pytest.mark.parametrize("case", ["aniso", "objmat", "bigsplats", "closeup"])
 def test_shards_match_oracle_on_nasty_geometry(oracle, scene, case):
     """Row-partitioned shards (cull by owned rows, survivor compaction) on needles with |q| != 1, a non-rigid object
