@@ -60,18 +60,46 @@ __device__ __forceinline__ uint32_t live_word(const uint32_t* __restrict__ done,
     return m & ~__ldg(done + ty * wpr + w);
 }
 
-// number of live tiles of rectangle t: rows this rank owns, tiles not yet saturated
-__device__ __forceinline__ uint32_t live_tiles(const TileRect& t, int tiles_x, int row_rank, int row_world, int row_group,
-                                               const uint32_t* __restrict__ done)
+// number of live tiles of rectangle t (live = row owned by this rank, tile not yet saturated): four look-ups in the
+// summed-area table of the live map (sat[y * (tiles_x + 1) + x] = live tiles in rows < y, columns < x), no loop and no
+// divergence; sat == NULL means every tile is live (single rank, first depth chunk)
+__device__ __forceinline__ uint32_t live_tiles(const TileRect& t, int tiles_x, const uint32_t* __restrict__ sat)
 {
-    uint32_t c = 0;
-    const int wpr = done_words_per_row(tiles_x);
-    for (int ty = t.ty0; ty <= t.ty1; ++ty) {
-        if (!owns_row(ty, row_rank, row_world, row_group)) continue;
-        if (!done) c += (uint32_t)(t.tx1 - t.tx0 + 1);
-        else for (int w = t.tx0 >> 5; w <= (t.tx1 >> 5); ++w) c += __popc(live_word(done, wpr, ty, w, t.tx0, t.tx1));
+    if (!sat) return (uint32_t)((t.tx1 - t.tx0 + 1) * (t.ty1 - t.ty0 + 1));
+    const int st = tiles_x + 1;
+    const uint32_t* r0 = sat + t.ty0 * st;
+    const uint32_t* r1 = sat + (t.ty1 + 1) * st;
+    return (__ldg(r1 + t.tx1 + 1) - __ldg(r0 + t.tx1 + 1)) - (__ldg(r1 + t.tx0) - __ldg(r0 + t.tx0));
+}
+
+// summed-area table of the live map, one CTA: row prefixes (a warp per row), then column sums (a thread per column;
+// the loads do not depend on the running sum, so they pipeline)
+__global__ void __launch_bounds__(1024)
+live_sat_kernel(const uint32_t* __restrict__ done, int tiles_x, int tiles_y, int row_rank, int row_world, int row_group,
+                uint32_t* __restrict__ sat)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int st = tiles_x + 1, wpr = done_words_per_row(tiles_x);
+    for (int x = threadIdx.x; x < st; x += 1024) sat[x] = 0u;
+    for (int y = warp; y < tiles_y; y += 32) {
+        const bool owned = owns_row(y, row_rank, row_world, row_group);
+        uint32_t carry = 0;
+        if (lane == 0) sat[(y + 1) * st] = 0u;
+        for (int w = 0; w < wpr; ++w) {
+            const int x = w * 32 + lane;
+            const uint32_t dw = done ? done[y * wpr + w] : 0u;
+            const uint32_t livew = owned ? ~dw : 0u;
+            const uint32_t upto = __popc(livew & (0xffffffffu >> (31 - lane)));      // live tiles of this word at columns <= x
+            if (x < tiles_x) sat[(y + 1) * st + x + 1] = carry + upto;
+            carry += __popc(livew);          // columns >= tiles_x are never read
+        }
     }
-    return c;
+    __syncthreads();
+    for (int x = threadIdx.x; x < st; x += 1024) {
+        uint32_t run = 0;
+#pragma unroll 8
+        for (int y = 1; y <= tiles_y; ++y) { run += sat[y * st + x]; sat[y * st + x] = run; }
+    }
 }
 
 // counts[k] = number of live tiles touched by element r0 + k (0 for culled splats); a coalesced 4-byte stream.
@@ -80,14 +108,14 @@ __device__ __forceinline__ uint32_t live_tiles(const TileRect& t, int tiles_x, i
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const uint32_t* __restrict__ trects, const uint32_t* __restrict__ order,
                   const uint2* __restrict__ rects, int64_t r0, int64_t n,
-                  int tiles_x, int row_rank, int row_world, int row_group, const uint32_t* __restrict__ tile_done,
+                  int tiles_x, const uint32_t* __restrict__ sat,
                   uint32_t* __restrict__ counts, unsigned long long* __restrict__ d_total)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t c = 0;
     if (k < n) {
         const TileRect t = tile_rect_of(trects, order, rects, r0 + k);
-        if (!t.empty) c = live_tiles(t, tiles_x, row_rank, row_world, row_group, tile_done);
+        if (!t.empty) c = live_tiles(t, tiles_x, sat);
         counts[k] = c;
     }
     if (d_total) {
@@ -118,7 +146,7 @@ constexpr int SEL_TILE    = SEL_THREADS * SEL_ITEMS;     // 2048 elements per CT
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects,
                     const uint2* __restrict__ rects, int64_t n, const ChunkPlan* __restrict__ plan, const int chunk,
-                    int tiles_x, int row_rank, int row_world, int row_group, const uint32_t* __restrict__ tile_done,
+                    int tiles_x, const uint32_t* __restrict__ sat,
                     uint32_t* __restrict__ stage_k, uint32_t* __restrict__ stage_v, uint32_t* __restrict__ stage_t,
                     uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
 {
@@ -145,7 +173,7 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
         uint32_t c = 0;
         if (key[j] >= key_lo && key[j] < key_hi) {      // key_hi <= KEY_CULLED: culled splats never pass
             const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane);
-            if (!t.empty) c = live_tiles(t, tiles_x, row_rank, row_world, row_group, tile_done);
+            if (!t.empty) c = live_tiles(t, tiles_x, sat);
         }
         dsum += c;
         const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
@@ -292,13 +320,17 @@ debug_instances_kernel(const uint32_t* __restrict__ inst_refs, const uint32_t* _
 
 }  // namespace
 
+void launch_live_sat(FrameConsts fc, const uint32_t* tile_done, uint32_t* sat, cudaStream_t s)
+{
+    live_sat_kernel<<<1, 1024, 0, s>>>(tile_done, fc.tiles_x, fc.tiles_y, fc.row_rank, fc.row_world, fc.row_group, sat);
+}
+
 void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
-                        FrameConsts fc, const uint32_t* tile_done, uint32_t* counts, unsigned long long* d_total,
+                        FrameConsts fc, const uint32_t* sat, uint32_t* counts, unsigned long long* d_total,
                         cudaStream_t s)
 {
     if (n <= 0) return;
-    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(trects, order, rects, r0, n, fc.tiles_x, fc.row_rank,
-                                                                 fc.row_world, fc.row_group, tile_done, counts, d_total);
+    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(trects, order, rects, r0, n, fc.tiles_x, sat, counts, d_total);
 }
 
 static inline size_t sel_tiles(int64_t n) { return (size_t)((n + SEL_TILE - 1) / SEL_TILE); }
@@ -308,7 +340,7 @@ size_t select_stage_elems(int64_t n) { return sel_tiles(n) * SEL_TILE; }
 
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
                         const ChunkPlan* plan, int chunk,
-                        FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
+                        FrameConsts fc, const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
                         uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
                         void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s)
@@ -319,8 +351,8 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
     uint32_t* tile_d = tile_l + nt;
     uint32_t* tile_base = tile_d + nt;
     if (!trects) stage_t = nullptr;
-    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, fc.row_rank,
-                                                   fc.row_world, fc.row_group, tile_done, stage_k, stage_v, stage_t, tile_l, tile_d);
+    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, sat,
+                                                   stage_k, stage_v, stage_t, tile_l, tile_d);
     select_scan_kernel<<<1, 1024, 0, s>>>(tile_l, tile_d, nt, tile_base, l_total, d_total);
     select_gather_kernel<<<(nt + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32), GATHER_THREADS, 0, s>>>(
         stage_k, stage_v, stage_t, tile_l, tile_base, nt, keys_out, vals_out, trects_out);

@@ -116,12 +116,16 @@ void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_
 
 // binning.cu
 // counts[k] = live tiles touched by element r0 + k of (trects, order); trects = packed tile rectangles aligned with
-// order (NULL: read the exact rectangle rects[order[r]], which "wide" entries always do); tile_done (may be NULL) =
-// saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) + tx / 32;
-// *d_total += sum of the counts
+// order (NULL: read the exact rectangle rects[order[r]], which "wide" entries always do); sat = summed-area table of the
+// live map (launch_live_sat; NULL = every tile live); *d_total += sum of the counts
 void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
-                        FrameConsts fc, const uint32_t* tile_done, uint32_t* counts, unsigned long long* d_total,
+                        FrameConsts fc, const uint32_t* sat, uint32_t* counts, unsigned long long* d_total,
                         cudaStream_t s);
+// tile_done: saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) +
+// tx / 32 (NULL = none).  A tile is live if this rank owns its row and it is not saturated.  sat: (tiles_y + 1) x
+// (tiles_x + 1) uint32, sat[y][x] = live tiles in rows < y and columns < x, so the live tiles of any tile rectangle are
+// four look-ups.  One small CTA per depth chunk.
+void launch_live_sat(FrameConsts fc, const uint32_t* tile_done, uint32_t* sat, cudaStream_t s);
 // live selection of one depth chunk over the submitted splats: elements whose depth key belongs to the chunk
 // (plan->key_lo[chunk] <= key < plan->key_lo[chunk + 1]; plan NULL = every visible splat) and that touch a live tile are
 // compacted, order preserving, into (keys_out, vals_out = splat index, trects_out); *l_total = their number, *d_total =
@@ -131,7 +135,7 @@ size_t select_scratch_bytes(int64_t n);
 size_t select_stage_elems(int64_t n);
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
                         const ChunkPlan* plan, int chunk,
-                        FrameConsts fc, const uint32_t* tile_done, uint32_t* keys_out, uint32_t* vals_out,
+                        FrameConsts fc, const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
                         uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
                         void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s);

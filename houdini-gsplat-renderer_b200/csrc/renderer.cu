@@ -117,7 +117,7 @@ struct gsb_context {
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
     // lkeys/lvals/ltrects: the live splats of the current chunk (ping-pong of their depth sort).
     DevBuf keys, trects, lkeys[2], lvals[2], ltrects[2], recs, rects, counts, ikeys[2], ivals[2],
-           ranges, tile_consumed, tile_done, fb, plan, bucket_hist;
+           ranges, tile_consumed, tile_done, live_sat, fb, plan, bucket_hist;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
@@ -647,6 +647,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
     const size_t done_bytes = (size_t)done_words_per_row(fc.tiles_x) * (size_t)fc.tiles_y * 4;      // one bit per tile
     CU(ctx->tile_done.ensure(done_bytes));
+    CU(ctx->live_sat.ensure((size_t)(fc.tiles_x + 1) * (size_t)(fc.tiles_y + 1) * 4));
     float4* fb = nullptr;
     const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
     if (target && target->device_rgba) fb = static_cast<float4*>(target->device_rgba);
@@ -726,10 +727,17 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         const bool first = (c == 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][0], s));
         uint32_t* counts = ctx->counts.as<uint32_t>();
+        // live map of this chunk as a summed-area table (first chunk of a single rank: every tile is live, no table)
+        const uint32_t* sat = nullptr;
+        if (!first || fr->row_world > 1) {
+            launch_live_sat(fc, first ? nullptr : tile_done, ctx->live_sat.as<uint32_t>(), s);
+            st.launches += 1;
+            sat = ctx->live_sat.as<uint32_t>();
+        }
         // live selection, one pass over the keys: the splats of the chunk that still touch a live tile, compacted in
         // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
         launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, chunk_plan, c, fc,
-                           first ? nullptr : tile_done, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                           sat, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                            use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
                            ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(),
                            use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
@@ -765,7 +773,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
         // K4: tile counts in depth order -> offsets -> instances -> stable partition by tile -> tile ranges
-        launch_tile_counts(trects_sorted, order, ctx->rects.as<uint2>(), 0, (int64_t)L, fc, first ? nullptr : tile_done, counts, nullptr, s);
+        launch_tile_counts(trects_sorted, order, ctx->rects.as<uint2>(), 0, (int64_t)L, fc, sat, counts, nullptr, s);
         exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cnt + 6, s, &st.launches);
         launch_emit(order, trects_sorted, ctx->rects.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
