@@ -21,21 +21,6 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
     return t;
 }
 
-// tile rectangle of element r: from the packed payload, or (wide splats / huge screens) from the exact rectangle of
-// splat order[r] (order == NULL: element r is splat r)
-__device__ __forceinline__ TileRect tile_rect_of(const uint32_t* __restrict__ trects, const uint32_t* __restrict__ order,
-                                                 const uint2* __restrict__ rects, int64_t r)
-{
-    if (!trects) return tile_rect(__ldg(rects + (order ? (int64_t)__ldg(order + r) : r)));
-    const uint32_t p = __ldg(trects + r);
-    TileRect t;
-    t.empty = p == TRECT_CULLED;
-    const int w = (int)((p >> 18) & 127u), h = (int)((p >> 25) & 127u);
-    if (!t.empty && (w == 127 || h == 127)) return tile_rect(__ldg(rects + (order ? (int64_t)__ldg(order + r) : r)));
-    t.tx0 = (int)(p & 511u); t.ty0 = (int)((p >> 9) & 511u); t.tx1 = t.tx0 + w; t.ty1 = t.ty0 + h;
-    return t;
-}
-
 // same, with the packed word already in a register (has_packed false: exact rectangle of splat i)
 __device__ __forceinline__ TileRect tile_rect_packed(const bool has_packed, const uint32_t p, const uint2* __restrict__ rects,
                                                      const int64_t i)
@@ -58,18 +43,6 @@ __device__ __forceinline__ uint32_t live_word(const uint32_t* __restrict__ done,
     if (w == (tx0 >> 5)) m &= 0xffffffffu << (tx0 & 31);
     if (w == (tx1 >> 5)) m &= 0xffffffffu >> (31 - (tx1 & 31));
     return m & ~__ldg(done + ty * wpr + w);
-}
-
-// number of live tiles of rectangle t (live = row owned by this rank, tile not yet saturated): four look-ups in the
-// summed-area table of the live map (sat[y * (tiles_x + 1) + x] = live tiles in rows < y, columns < x), no loop and no
-// divergence; sat == NULL means every tile is live (single rank, first depth chunk)
-__device__ __forceinline__ uint32_t live_tiles(const TileRect& t, int tiles_x, const uint32_t* __restrict__ sat)
-{
-    if (!sat) return (uint32_t)((t.tx1 - t.tx0 + 1) * (t.ty1 - t.ty0 + 1));
-    const int st = tiles_x + 1;
-    const uint32_t* r0 = sat + t.ty0 * st;
-    const uint32_t* r1 = sat + (t.ty1 + 1) * st;
-    return (__ldg(r1 + t.tx1 + 1) - __ldg(r0 + t.tx1 + 1)) - (__ldg(r1 + t.tx0) - __ldg(r0 + t.tx0));
 }
 
 // summed-area table of the live map, one CTA: row prefixes (a warp per row), then column sums (a thread per column;
@@ -102,37 +75,15 @@ live_sat_kernel(const uint32_t* __restrict__ done, int tiles_x, int tiles_y, int
     }
 }
 
-// counts[k] = number of live tiles touched by element r0 + k (0 for culled splats); a coalesced 4-byte stream.
-// A tile is live if this rank owns its row and it is not yet saturated (tile_done, set by the blend
-// of an earlier depth chunk): instances behind a saturated tile can never change a pixel.
-__global__ void __launch_bounds__(256)
-tile_count_kernel(const uint32_t* __restrict__ trects, const uint32_t* __restrict__ order,
-                  const uint2* __restrict__ rects, int64_t r0, int64_t n,
-                  int tiles_x, const uint32_t* __restrict__ sat,
-                  uint32_t* __restrict__ counts, unsigned long long* __restrict__ d_total)
-{
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t c = 0;
-    if (k < n) {
-        const TileRect t = tile_rect_of(trects, order, rects, r0 + k);
-        if (!t.empty) c = live_tiles(t, tiles_x, sat);
-        counts[k] = c;
-    }
-    if (d_total) {
-        const uint32_t w = __reduce_add_sync(0xffffffffu, c);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(d_total, (unsigned long long)w);
-    }
-}
-
 // ---- live selection, per depth chunk, over the submitted splats (which are never moved).  Element k is selected if its
 // depth key lies in the chunk's key interval [key_lo, key_hi) (the chunk plan turns its bucket boundaries into key
 // boundaries, so membership is two integer compares) and it touches at least one live tile.  Three kernels, no spin-waits:
 //   A  select_count:  one CTA per 2048 elements streams the keys and packed tile rectangles (8 B / splat, all loads
-//      issued before any is used), compacts the selected (key, splat index, tile rectangle) triples order-preservingly
+//      issued before any is used), compacts the selected (key, splat index) pairs order-preservingly
 //      INSIDE the CTA and stores them as one contiguous run at the CTA's own slot of a staging area
 //      (stage[tile * 2048 ..]); writes the tile's totals.
 //   S  select_scan:   one CTA turns the per-tile totals into exclusive bases and the grand totals L and D.
-//   B  select_gather: moves every tile's run to base[tile]: contiguous reads, contiguous writes, 12 B per SELECTED
+//   B  select_gather: moves every tile's run to base[tile]: contiguous reads, contiguous writes, 8 B per SELECTED
 //      element.  Submission order is kept, so the stable depth sort that follows breaks ties by ascending index.
 // (r01 measured three other forms first.  A single-pass chained scan: with ~5000 tiles in flight the decoupled look-back
 // chains grew to the number of resident CTAs, 260-320 us per pass.  Loading the rectangle only for the chunk's own
@@ -147,7 +98,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects,
                     const uint2* __restrict__ rects, int64_t n, const ChunkPlan* __restrict__ plan, const int chunk,
                     int tiles_x, const uint32_t* __restrict__ sat,
-                    uint32_t* __restrict__ stage_k, uint32_t* __restrict__ stage_v, uint32_t* __restrict__ stage_t,
+                    uint32_t* __restrict__ stage_k, uint32_t* __restrict__ stage_v,
                     uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
 {
     __shared__ uint32_t s_wl[SEL_WARPS], s_wd[SEL_WARPS];
@@ -173,7 +124,7 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
         uint32_t c = 0;
         if (key[j] >= key_lo && key[j] < key_hi) {      // key_hi <= KEY_CULLED: culled splats never pass
             const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane);
-            if (!t.empty) c = live_tiles(t, tiles_x, sat);
+            if (!t.empty) c = live_tiles(t.tx0, t.tx1, t.ty0, t.ty1, tiles_x, sat);
         }
         dsum += c;
         const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
@@ -194,7 +145,6 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
         if ((selbits >> j) & 1u) {
             const size_t o = sb + pos[j];
             stage_k[o] = key[j]; stage_v[o] = (uint32_t)(base + j * 32 + lane);
-            if (stage_t) stage_t[o] = tr[j];
         }
     }
 }
@@ -240,13 +190,12 @@ select_scan_kernel(const uint32_t* __restrict__ tile_l, const uint32_t* __restri
     }
 }
 
-// one warp per selection tile: copy its run of selected triples from the staging slot to base[tile]
+// one warp per selection tile: copy its run of selected pairs from the staging slot to base[tile]
 constexpr int GATHER_THREADS = 256;
 __global__ void __launch_bounds__(GATHER_THREADS)
 select_gather_kernel(const uint32_t* __restrict__ stage_k, const uint32_t* __restrict__ stage_v,
-                     const uint32_t* __restrict__ stage_t, const uint32_t* __restrict__ tile_l,
-                     const uint32_t* __restrict__ tile_base, uint32_t nt,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t* __restrict__ trects_out)
+                     const uint32_t* __restrict__ tile_l, const uint32_t* __restrict__ tile_base, uint32_t nt,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t tile = blockIdx.x * (GATHER_THREADS / 32) + (threadIdx.x >> 5);
@@ -256,14 +205,13 @@ select_gather_kernel(const uint32_t* __restrict__ stage_k, const uint32_t* __res
     const size_t src = (size_t)tile * SEL_TILE, dst = (size_t)__ldg(tile_base + tile);
     for (uint32_t i = lane; i < l; i += 32) {
         keys_out[dst + i] = __ldg(stage_k + src + i); vals_out[dst + i] = __ldg(stage_v + src + i);
-        if (stage_t) trects_out[dst + i] = __ldg(stage_t + src + i);
     }
 }
 
-// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending
+// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only
 __global__ void __launch_bounds__(256)
-emit_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ trects, const uint2* __restrict__ rects,
-            const uint32_t* __restrict__ offsets, const unsigned long long* __restrict__ total,
+emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ offsets,
+            const unsigned long long* __restrict__ total,
             int64_t n, int tiles_x, int row_rank, int row_world, int row_group,
             const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
 {
@@ -271,17 +219,18 @@ emit_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tre
     if (k >= n) return;
     const uint32_t o0 = offsets[k];
     const uint32_t o1 = (k + 1 < n) ? offsets[k + 1] : (uint32_t)(*total);
-    if (o1 == o0) return;                                    // culled, or every tile it touches is saturated
-    const TileRect t = tile_rect_of(trects, order, rects, k);
+    if (o1 == o0) return;                                    // every tile it touches is saturated
+    const uint2 tr = __ldg(tile_rects + k);
+    const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
     size_t o = o0;
     const int wpr = done_words_per_row(tiles_x);
-    for (int ty = t.ty0; ty <= t.ty1; ++ty) {
+    for (int ty = ty0; ty <= ty1; ++ty) {
         if (!owns_row(ty, row_rank, row_world, row_group)) continue;
         if (!tile_done) {
-            for (int tx = t.tx0; tx <= t.tx1; ++tx) { inst_keys[o] = (uint32_t)(ty * tiles_x + tx); inst_vals[o] = (uint32_t)k; ++o; }
+            for (int tx = tx0; tx <= tx1; ++tx) { inst_keys[o] = (uint32_t)(ty * tiles_x + tx); inst_vals[o] = (uint32_t)k; ++o; }
         } else {
-            for (int w = t.tx0 >> 5; w <= (t.tx1 >> 5); ++w) {
-                uint32_t live = live_word(tile_done, wpr, ty, w, t.tx0, t.tx1);
+            for (int w = tx0 >> 5; w <= (tx1 >> 5); ++w) {
+                uint32_t live = live_word(tile_done, wpr, ty, w, tx0, tx1);
                 while (live) {                                   // ascending columns
                     const int b = __ffs(live) - 1;
                     live &= live - 1;
@@ -325,14 +274,6 @@ void launch_live_sat(FrameConsts fc, const uint32_t* tile_done, uint32_t* sat, c
     live_sat_kernel<<<1, 1024, 0, s>>>(tile_done, fc.tiles_x, fc.tiles_y, fc.row_rank, fc.row_world, fc.row_group, sat);
 }
 
-void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
-                        FrameConsts fc, const uint32_t* sat, uint32_t* counts, unsigned long long* d_total,
-                        cudaStream_t s)
-{
-    if (n <= 0) return;
-    tile_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(trects, order, rects, r0, n, fc.tiles_x, sat, counts, d_total);
-}
-
 static inline size_t sel_tiles(int64_t n) { return (size_t)((n + SEL_TILE - 1) / SEL_TILE); }
 
 size_t select_scratch_bytes(int64_t n) { return sel_tiles(n) * 3 * sizeof(uint32_t) + 64; }
@@ -341,7 +282,7 @@ size_t select_stage_elems(int64_t n) { return sel_tiles(n) * SEL_TILE; }
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
                         const ChunkPlan* plan, int chunk,
                         FrameConsts fc, const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
-                        uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
+                        uint32_t* stage_k, uint32_t* stage_v,
                         void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s)
 {
@@ -350,20 +291,19 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
     uint32_t* tile_l = static_cast<uint32_t*>(scratch);
     uint32_t* tile_d = tile_l + nt;
     uint32_t* tile_base = tile_d + nt;
-    if (!trects) stage_t = nullptr;
     select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, sat,
-                                                   stage_k, stage_v, stage_t, tile_l, tile_d);
+                                                   stage_k, stage_v, tile_l, tile_d);
     select_scan_kernel<<<1, 1024, 0, s>>>(tile_l, tile_d, nt, tile_base, l_total, d_total);
     select_gather_kernel<<<(nt + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32), GATHER_THREADS, 0, s>>>(
-        stage_k, stage_v, stage_t, tile_l, tile_base, nt, keys_out, vals_out, trects_out);
+        stage_k, stage_v, tile_l, tile_base, nt, keys_out, vals_out);
 }
 
-void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,
+void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                  const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
 {
     if (n <= 0) return;
-    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(order, trects, rects, offsets, total, n, fc.tiles_x,
+    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tile_rects, offsets, total, n, fc.tiles_x,
                                                            fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals);
 }
 

@@ -110,17 +110,12 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
 // chunk, found by bisection over the monotone map key -> bucket -> chunk), so membership is two integer compares
 void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s);
 // K2 (only splats that reach a live tile, in depth order): gather the splat's 128-byte line, redo the projection,
-// evaluate SH, write the 48-byte record of live rank j to recs[j]
+// evaluate SH, write the 48-byte record of live rank j to recs[j], its tile rectangle (tx0 | tx1 << 16, ty0 | ty1 << 16)
+// to tile_rects[j] and the number of live tiles it touches to counts[j] (sat: launch_live_sat, NULL = every tile live)
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    Record* recs, cudaStream_t s);
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, cudaStream_t s);
 
 // binning.cu
-// counts[k] = live tiles touched by element r0 + k of (trects, order); trects = packed tile rectangles aligned with
-// order (NULL: read the exact rectangle rects[order[r]], which "wide" entries always do); sat = summed-area table of the
-// live map (launch_live_sat; NULL = every tile live); *d_total += sum of the counts
-void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uint2* rects, int64_t r0, int64_t n,
-                        FrameConsts fc, const uint32_t* sat, uint32_t* counts, unsigned long long* d_total,
-                        cudaStream_t s);
 // tile_done: saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) +
 // tx / 32 (NULL = none).  A tile is live if this rank owns its row and it is not saturated.  sat: (tiles_y + 1) x
 // (tiles_x + 1) uint32, sat[y][x] = live tiles in rows < y and columns < x, so the live tiles of any tile rectangle are
@@ -128,20 +123,21 @@ void launch_tile_counts(const uint32_t* trects, const uint32_t* order, const uin
 void launch_live_sat(FrameConsts fc, const uint32_t* tile_done, uint32_t* sat, cudaStream_t s);
 // live selection of one depth chunk over the submitted splats: elements whose depth key belongs to the chunk
 // (plan->key_lo[chunk] <= key < plan->key_lo[chunk + 1]; plan NULL = every visible splat) and that touch a live tile are
-// compacted, order preserving, into (keys_out, vals_out = splat index, trects_out); *l_total = their number, *d_total =
-// the instances they will emit.  stage_k/v/t: select_stage_elems(n) uint32 each (CTA-local runs before the gather; may be
-// the second halves of the sort's ping-pong buffers); scratch: select_scratch_bytes(n).  Three launches, no spin-waits.
+// compacted, order preserving, into (keys_out, vals_out = splat index); *l_total = their number, *d_total = the
+// instances they will emit.  trects = K1's packed tile rectangles (NULL: exact rectangles in rects); stage_k/v:
+// select_stage_elems(n) uint32 each (CTA-local runs before the gather; may be the second halves of the sort's ping-pong
+// buffers); scratch: select_scratch_bytes(n).  Three launches, no spin-waits.
 size_t select_scratch_bytes(int64_t n);
 size_t select_stage_elems(int64_t n);
 void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint2* rects, int64_t n,
                         const ChunkPlan* plan, int chunk,
                         FrameConsts fc, const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
-                        uint32_t* trects_out, uint32_t* stage_k, uint32_t* stage_v, uint32_t* stage_t,
+                        uint32_t* stage_k, uint32_t* stage_v,
                         void* scratch, unsigned long long* l_total, unsigned long long* d_total,
                         cudaStream_t s);
-// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending;
-// offsets = exclusive scan of the tile counts, *total = its grand total (device)
-void launch_emit(const uint32_t* order, const uint32_t* trects, const uint2* rects, const uint32_t* offsets,
+// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only;
+// tile_rects = K2's rectangles by live rank; offsets = exclusive scan of K2's counts, *total = its grand total (device)
+void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                  const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
@@ -176,6 +172,18 @@ __host__ __device__ __forceinline__ uint32_t pack_trect(int tx0, int tx1, int ty
 {
     const int w = tx1 - tx0, h = ty1 - ty0;
     return (uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(w > 127 ? 127 : w) << 18) | ((uint32_t)(h > 127 ? 127 : h) << 25);
+}
+
+// number of live tiles of the tile rectangle [tx0, tx1] x [ty0, ty1] (live = row owned by this rank, tile not yet
+// saturated): four look-ups in the summed-area table of the live map (sat[y * (tiles_x + 1) + x] = live tiles in rows
+// < y, columns < x), no loop and no divergence; sat == NULL means every tile is live (single rank, first depth chunk)
+__device__ __forceinline__ uint32_t live_tiles(int tx0, int tx1, int ty0, int ty1, int tiles_x, const uint32_t* __restrict__ sat)
+{
+    if (!sat) return (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
+    const int st = tiles_x + 1;
+    const uint32_t* r0 = sat + ty0 * st;
+    const uint32_t* r1 = sat + (ty1 + 1) * st;
+    return (__ldg(r1 + tx1 + 1) - __ldg(r0 + tx1 + 1)) - (__ldg(r1 + tx0) - __ldg(r0 + tx0));
 }
 
 // words per tile row of the saturation bit map (tile_done)

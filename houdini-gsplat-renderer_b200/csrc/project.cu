@@ -455,13 +455,15 @@ choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const
 // one DRAM burst pair.  Lines are gathered cooperatively: 8 lanes fetch the 8 16-byte chunks of one line, so every load
 // instruction of a warp covers 4 complete lines and all loads of the warp's 32 lines are in flight together (one
 // latency, not three dependent ones); the lines are staged in shared memory (144-byte pitch: conflict-free both ways)
-// and each thread then reads its own.  The projection is redone with K1's code (same bits); the record goes to recs[j].
+// and each thread then reads its own.  The projection is redone with K1's code (same bits); the record goes to recs[j],
+// and the splat's tile rectangle and live-tile count (the binning inputs) to tile_rects[j] / counts[j].
 constexpr int K2_THREADS = 256;
 constexpr int K2_PITCH   = ROW_U4 + 1;             // uint4 per staged line
 template <int ORDER>
 __global__ void __launch_bounds__(K2_THREADS)
 records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
-               const uint32_t* __restrict__ live_splats, const int64_t n_live, Record* __restrict__ recs)
+               const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
+               Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts)
 {
     __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
     constexpr int NCH = 2 + (ORDER == 0 ? 1 : (ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6)));     // chunks of the line this order reads
@@ -489,7 +491,14 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g)) {  // cannot happen (K1 kept it)
         out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
         out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tile_rects[j] = make_uint2(1u, 1u); counts[j] = 0u;
         return;
+    }
+    // binning inputs of this live splat: its tile rectangle and the number of live tiles in it
+    {
+        const int tx0 = g.x0 / TILE, tx1 = g.x1 / TILE, ty0 = g.y0 / TILE, ty1 = g.y1 / TILE;
+        tile_rects[j] = make_uint2((uint32_t)tx0 | ((uint32_t)tx1 << 16), (uint32_t)ty0 | ((uint32_t)ty1 << 16));
+        counts[j] = live_tiles(tx0, tx1, ty0, ty1, F.tiles_x, sat);
     }
     float rgb[3];
     shade_colour<ORDER>(F, row + 2, g.psx, rgb);
@@ -550,15 +559,15 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    Record* recs, cudaStream_t s)
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, cudaStream_t s)
 {
     if (n_live <= 0) return;
     const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
     switch (fc.sh_order) {
-    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
-    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
-    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
-    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, recs); break;
+    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
+    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
+    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
+    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
     }
 }
 

@@ -23,9 +23,19 @@
 namespace gsb {
 
 namespace {
-constexpr int RS_THREADS = 512;
+// tile shape: compile-time knobs so tools/build_variants.sh can build experiment libraries (r01 sweep in DESIGN.md)
+#ifndef GSB_RS_THREADS
+#define GSB_RS_THREADS 512
+#endif
+#ifndef GSB_RS_ITEMS
+#define GSB_RS_ITEMS 8
+#endif
+#ifndef GSB_RS_MINB
+#define GSB_RS_MINB 2
+#endif
+constexpr int RS_THREADS = GSB_RS_THREADS;
 constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_ITEMS   = 8;
+constexpr int RS_ITEMS   = GSB_RS_ITEMS;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096
 constexpr int RS_MAXBITS = 9;
 constexpr int RS_RADIX   = 1 << RS_MAXBITS;         // up to 512 bins per pass
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __rest
 // ---- one pass ------------------------------------------------------------------------------------------------
 // lookback layout: [tile][nbins]: a tile publishes one coalesced row; a look-back step reads LB_WIN rows.
 template <int NBITS, class DigitFn>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, GSB_RS_MINB)
 os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                const DigitFn dig, const uint32_t* __restrict__ digit_base,

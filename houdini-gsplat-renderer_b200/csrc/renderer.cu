@@ -115,8 +115,8 @@ struct gsb_context {
     float  sigma_object[16] = {};
 
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
-    // lkeys/lvals/ltrects: the live splats of the current chunk (ping-pong of their depth sort).
-    DevBuf keys, trects, lkeys[2], lvals[2], ltrects[2], recs, rects, counts, ikeys[2], ivals[2],
+    // lkeys/lvals: the live splats of the current chunk (ping-pong of their depth sort); ltiles: their tile rectangles (K2).
+    DevBuf keys, trects, lkeys[2], lvals[2], ltiles, recs, rects, counts, ikeys[2], ivals[2],
            ranges, tile_consumed, tile_done, live_sat, fb, plan, bucket_hist;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
@@ -721,7 +721,6 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     const size_t live_bytes = select_stage_elems(n) * 4 + 16;
     for (int b = 0; b < 2; ++b) {
         CU(ctx->lkeys[b].ensure(live_bytes)); CU(ctx->lvals[b].ensure(live_bytes));
-        if (use_trects) CU(ctx->ltrects[b].ensure(live_bytes));
     }
     for (int c = 0; c < nchunks; ++c) {
         const bool first = (c == 0);
@@ -738,9 +737,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
         launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, chunk_plan, c, fc,
                            sat, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
-                           use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
-                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(),
-                           use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
+                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
         st.launches += 3;
         // one host sync per chunk: V, this chunk's D and L, and the number of tiles saturated by the previous chunks
         CU(cudaMemcpyAsync(ctx->counters_h, cnt, 48, cudaMemcpyDeviceToHost, s));
@@ -758,26 +755,23 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         }
         // depth sort of the live splats: stable LSD, ties keep ascending index
         for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
-        CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16));
+        CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16)); CU(ctx->ltiles.ensure((size_t)L * 8 + 16));
         CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)std::max<uint64_t>(D, L))));
         ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), (size_t)L, 0, key_bits,
                                           ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches,
-                                          use_trects ? ctx->ltrects[0].as<uint32_t>() : nullptr,
-                                          use_trects ? ctx->ltrects[1].as<uint32_t>() : nullptr, key_min, key_span);
+                                          nullptr, nullptr, key_min, key_span);
         const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
-        const uint32_t* trects_sorted = use_trects ? ctx->ltrects[ctx->order_buf].as<uint32_t>() : nullptr;
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
-        // K2: records of the live splats, in depth order
-        launch_records(fc, ps, order, (int64_t)L, ctx->recs.as<Record>(), s);
+        // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
+        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        // K4: tile counts in depth order -> offsets -> instances -> stable partition by tile -> tile ranges
-        launch_tile_counts(trects_sorted, order, ctx->rects.as<uint2>(), 0, (int64_t)L, fc, sat, counts, nullptr, s);
+        // K4: live-tile counts (K2) -> offsets -> instances -> stable partition by tile -> tile ranges
         exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cnt + 6, s, &st.launches);
-        launch_emit(order, trects_sorted, ctx->rects.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
+        launch_emit(ctx->ltiles.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
-        st.launches += (L ? 2 : 0);
+        st.launches += (L ? 1 : 0);
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches);

@@ -24,9 +24,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--env", default="", help="semicolon-separated experiment settings, each a comma-separated list of "
                                               "NAME=VALUE library knobs (GSB_K1_OCC, GSB_BLEND_OBB), e.g. 'GSB_K1_OCC=4;GSB_K1_OCC=6'")
+    ap.add_argument("--lib", default="", help="experiment library built by tools/build_variants.sh (name in _exp/); default = the product library")
     a = ap.parse_args()
     import torch
     from houdini_gsplat_renderer_b200 import renderer as R, scene as S
+    if a.lib:
+        R.LIB_PATH = ROOT / "houdini-gsplat-renderer_b200" / "_exp" / f"lib_{a.lib}.so"
     w = S.WORKLOADS[a.workload]
     cloud = S.make_cloud(w["n"], w["seed"], sh=w["sh"])
     r = R.GSplatRenderer(0)
@@ -71,6 +74,7 @@ def main():
         out["chunk_shift"] = sh
         out["env"] = envs
         out["workload"] = a.workload
+        out["lib"] = a.lib or "product"
         if not w["orbit"]:
             cur = fb.cpu().numpy()
             if ref is None:
