@@ -9,7 +9,7 @@ the synthetic cloud of SURVEY.md §8d.  Default workload: the north-star target,
 1920x1080, one B200 (fits one GPU: 2.6 GB of attributes).  Prints ONE JSON line (rank 0).
 
   value        whole-job Msplats/s (= submitted splats x fps / 1e6), attributes resident in HBM, frame left on device
-  e2e          same metric through the C ABI with HOST buffers: gsb_frame (352 B) in, RGBA32F frame copied to pinned
+  e2e          same metric through the C ABI with HOST buffers: gsb_frame (368 B) in, RGBA32F frame copied to pinned
                host memory inside the timed call.  Geometry is NOT re-uploaded per frame — neither does the reference
                (its textures persist until the active set changes, GSplatRenderer.C:324-327); the cold cost
                (gsb_register_update H2D + pack) is reported separately as e2e_cold_ms.
@@ -368,7 +368,7 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (N * 160 / 1e9),
                    "full_pipeline_every_frame": True, "depth_chunks": cnt["depth_chunks"] / K / world},
         "e2e": {"value": e2e_val, "unit": "Msplats/s", "fps": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 352, "d2h_bytes_per_step": frame_bytes,
+                "h2d_bytes_per_step": 368, "d2h_bytes_per_step": frame_bytes,
                 "host_direct": bool(args.host_direct) and world == 1,
                 "note": "gsb_render with host target: gsb_frame in, RGBA32F frame to pinned host memory, the call returns when "
                         "the frame is there; geometry resident (the reference also re-uploads only on active-set change)"},

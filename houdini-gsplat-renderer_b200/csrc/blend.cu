@@ -35,20 +35,30 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <bool OBB_CULL>
+// DEPTH: scene-depth occlusion (R.C:608-610 depth test on / writes off, SRC.h:278-282 one depth per quad):
+// the window depth of every staged instance rides along in shared memory, each pixel keeps the scene depth at its
+// position in a register, and a fragment that fails F.depth_func is dropped (no colour, no transmittance change).
+template <bool OBB_CULL, bool DEPTH>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
              const uint2* __restrict__ ranges, float4* __restrict__ fb, float4* __restrict__ fb_final,
              const __grid_constant__ FrameConsts F, const int first, const int last,
              uint32_t* __restrict__ tile_done,
              uint32_t* __restrict__ tile_consumed, unsigned long long* __restrict__ consumed_total,
-             unsigned long long* __restrict__ done_tiles)
+             unsigned long long* __restrict__ done_tiles,
+             const float* __restrict__ zdepth, const float* __restrict__ scene_depth)
 {
     __shared__ __align__(16) Record srec[2][BL_BATCH];
+    __shared__ float sz[DEPTH ? 2 : 1][DEPTH ? BL_BATCH : 1];
     __shared__ uint32_t s_consumed;
 
     const int tile = blockIdx.x;
@@ -79,6 +89,15 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
         const float4 st = fb[(size_t)py * F.width + px];
         Cr = st.x; Cg = st.y; Cb = st.z; T = st.w;
     }
+    // scene depth at this pixel; the farthest one of the warp's block culls whole instances
+    float sd = 0.0f, sd_max = 0.0f;
+    const bool lequal = F.depth_func == 2;
+    if (DEPTH) {
+        sd = inside ? __ldg(scene_depth + (size_t)py * F.width + px) : -1.0e30f;
+        sd_max = sd;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sd_max = fmaxf(sd_max, __shfl_xor_sync(0xffffffffu, sd_max, o));
+    }
     bool done = !inside || (T < eps);
     bool warp_done = __all_sync(0xffffffffu, done);
     uint32_t done_pos = 0;                       // instances traversed when this pixel saturated (0: it started saturated)
@@ -91,6 +110,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
             const char* src = reinterpret_cast<const char*>(recs + ref);
             char* dst = reinterpret_cast<char*>(&srec[b & 1][tid]);
             cp_async16(dst, src); cp_async16(dst + 16, src + 16); cp_async16(dst + 32, src + 32);
+            if (DEPTH) cp_async4(&sz[b & 1][tid], zdepth + ref);
         }
         cp_async_commit();
     };
@@ -112,6 +132,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                     const float hx = __half2float(__ushort_as_half((unsigned short)(hp & 0xffffu)));
                     const float hy = __half2float(__ushort_as_half((unsigned short)(hp >> 16)));
                     ov = (cc.x - hx <= wx_hi) && (cc.x + hx >= wx_lo) && (cc.y - hy <= wy_hi) && (cc.y + hy >= wy_lo);
+                    if (DEPTH) { const float zw = sz[b & 1][my]; ov = ov && (lequal ? (zw <= sd_max) : (zw < sd_max)); }
                     if (OBB_CULL && ov) {
                         // second separating-axis test, in the splat's eigen space: the block's pixel centres map into the box
                         // qc +- (rx, ry); if that box misses |qx| <= 2, |qy| <= 2 or |q|^2 <= pmax no pixel of the block is
@@ -138,7 +159,9 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                     mask &= mask - 1;
                     const float4* rp = reinterpret_cast<const float4*>(&buf[c + j]);
                     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-                    if (!done) {
+                    bool zpass = true;
+                    if (DEPTH) { const float zw = sz[b & 1][c + j]; zpass = lequal ? (zw <= sd) : (zw < sd); }
+                    if (!done && zpass) {
                         const float dx = fpx - r0.x, dy = fpy - r0.y;
                         const float qx = fmaf(dy, r0.w, dx * r0.z);
                         const float qy = fmaf(dy, r1.y, dx * r1.x);
@@ -182,16 +205,19 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
-                  unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s)
+                  unsigned long long* consumed_total, unsigned long long* done_tiles,
+                  const float* zdepth, const float* scene_depth, cudaStream_t s)
 {
     const int tiles = fc.tiles_x * fc.tiles_y;
     if (tiles <= 0) return;
     const char* e = getenv("GSB_BLEND_OBB");   // GSB_BLEND_OBB=0 turns the eigen-space cull off (experiments)
     const int obb = (e && atoi(e) == 0) ? 0 : 1;
-    if (obb) blend_kernel<true><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last,
-                                                            tile_done, tile_consumed, consumed_total, done_tiles);
-    else blend_kernel<false><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, last,
-                                                          tile_done, tile_consumed, consumed_total, done_tiles);
+    const bool depth = fc.depth_func != 0 && zdepth && scene_depth;
+#define GSB_BLEND(O, D) blend_kernel<O, D><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, \
+                            last, tile_done, tile_consumed, consumed_total, done_tiles, zdepth, scene_depth)
+    if (depth) { if (obb) GSB_BLEND(true, true); else GSB_BLEND(false, true); }
+    else       { if (obb) GSB_BLEND(true, false); else GSB_BLEND(false, false); }
+#undef GSB_BLEND
 }
 
 }  // namespace gsb

@@ -24,6 +24,8 @@ struct FrameConsts {
     int   row_rank, row_world;  // tile-row ownership: row ty is owned iff (ty / row_group) % row_world == row_rank
     int   row_group;
     float eps_t;                // transmittance early-out threshold
+    int   depth_func;           // scene-depth occlusion: 0 none, 1 LESS, 2 LEQUAL (gsb_depth_func)
+    float depth_hr, depth_hm;   // window depth = (clip.z / clip.w) * depth_hr + depth_hm  ((far-near)/2, (far+near)/2)
 };
 
 // 2-D record written by project and gathered by blend: 48 bytes, three 16-byte chunks.
@@ -113,7 +115,8 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
 // evaluate SH, write the 48-byte record of live rank j to recs[j], its tile rectangle (tx0 | tx1 << 16, ty0 | ty1 << 16)
 // to tile_rects[j] and the number of live tiles it touches to counts[j] (sat: launch_live_sat, NULL = every tile live)
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, cudaStream_t s);
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth, cudaStream_t s);
+// zdepth (may be NULL): window depth of live rank j (scene-depth occlusion)
 
 // binning.cu
 // tile_done: saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) +
@@ -160,9 +163,12 @@ void launch_ingest_sh_rest(const float* rest, int64_t n, uint16_t* shx, uint16_t
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
 // chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done (bit map);
 // last: every remaining tile is finalised.  Finalised tiles are stored to fb_final (NULL = fb; may be peer memory).  *done_tiles counts the tiles flagged so far (early termination).
+// zdepth / scene_depth (both NULL unless fc.depth_func != 0): window depth per live rank and the scene's depth buffer;
+// a fragment whose depth fails fc.depth_func against the scene depth at its pixel is dropped.
 void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ranges, float4* fb, float4* fb_final,
                   FrameConsts fc, int first, int last, uint32_t* tile_done, uint32_t* tile_consumed,
-                  unsigned long long* consumed_total, unsigned long long* done_tiles, cudaStream_t s);
+                  unsigned long long* consumed_total, unsigned long long* done_tiles,
+                  const float* zdepth, const float* scene_depth, cudaStream_t s);
 
 // Packed tile rectangle carried through the depth sort: tx0:9 | ty0:9 | (tx1-tx0):7 | (ty1-ty0):7.  Extents of 127 tiles
 // or more saturate to 127 = "wide: read the exact pixel rectangle by splat index".  0xFFFFFFFF = culled.

@@ -126,6 +126,7 @@ struct Geom {
     float cx, cy, m00, m01, m10, m11, hx, hy;
     int   x0, x1, y0, y1;
     float psx[3];            // shader-side position (P - origin) + origin
+    float clipz, clipw;      // centre clip z and w: every fragment of the quad has depth clipz / clipw (SRC.h:278-282)
 };
 
 // Centre, cull, covariance chain, eigen axes, discard radius, pixel rectangle.  Returns false if culled.
@@ -257,7 +258,7 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
         for (int tyy = g.y0 / TILE; tyy <= g.y1 / TILE && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
         if (!any) return false;
     }
-    g.cx = cx; g.cy = cy;
+    g.cx = cx; g.cy = cy; g.clipz = clip[2]; g.clipw = cw;
     g.m00 = ex / s1; g.m01 = ey / s1;
     g.m10 = (-ey) / s2; g.m11 = ex / s2;
     g.hx = hx; g.hy = hy;
@@ -463,7 +464,8 @@ template <int ORDER>
 __global__ void __launch_bounds__(K2_THREADS)
 records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
                const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
-               Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts)
+               Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts,
+               float* __restrict__ zdepth)
 {
     __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
     constexpr int NCH = 2 + (ORDER == 0 ? 1 : (ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6)));     // chunks of the line this order reads
@@ -492,8 +494,10 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
         out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
         out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         tile_rects[j] = make_uint2(1u, 1u); counts[j] = 0u;
+        if (zdepth) zdepth[j] = 0.0f;
         return;
     }
+    if (zdepth) zdepth[j] = ((g.clipz / g.clipw) * F.depth_hr) + F.depth_hm;     // window depth of the whole quad
     // binning inputs of this live splat: its tile rectangle and the number of live tiles in it
     {
         const int tx0 = g.x0 / TILE, tx1 = g.x1 / TILE, ty0 = g.y0 / TILE, ty1 = g.y1 / TILE;
@@ -559,15 +563,15 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, cudaStream_t s)
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth, cudaStream_t s)
 {
     if (n_live <= 0) return;
     const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
     switch (fc.sh_order) {
-    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
-    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
-    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
-    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts); break;
+    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
+    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
+    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
+    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
     }
 }
 

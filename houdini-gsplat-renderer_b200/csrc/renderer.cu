@@ -118,6 +118,8 @@ struct gsb_context {
     // lkeys/lvals: the live splats of the current chunk (ping-pong of their depth sort); ltiles: their tile rectangles (K2).
     DevBuf keys, trects, lkeys[2], lvals[2], ltiles, recs, rects, counts, ikeys[2], ivals[2],
            ranges, tile_consumed, tile_done, live_sat, fb, plan, bucket_hist;
+    DevBuf zdepth, scene_depth_buf;                  // scene-depth occlusion: window depth per live rank; GL depth copy
+    struct cudaGraphicsResource* gl_depth_res = nullptr; uint32_t gl_depth_tex = 0; int gl_depth_w = 0, gl_depth_h = 0;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
@@ -216,6 +218,7 @@ int gsb_destroy(gsb_context* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->gl_res) cudaGraphicsUnregisterResource(ctx->gl_res);
+    if (ctx->gl_depth_res) cudaGraphicsUnregisterResource(ctx->gl_depth_res);
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
@@ -582,6 +585,10 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     if (fr->row_world < 1 || fr->row_rank < 0 || fr->row_rank >= fr->row_world)
         return fail(GSB_ERR_INVALID, "gsb_render: bad tile-row partition");
     if (fr->row_group < 0) return fail(GSB_ERR_INVALID, "gsb_render: row_group must be >= 0");
+    if (fr->depth_func < GSB_DEPTH_NONE || fr->depth_func > GSB_DEPTH_LEQUAL)
+        return fail(GSB_ERR_INVALID, "gsb_render: depth_func must be GSB_DEPTH_NONE, GSB_DEPTH_LESS or GSB_DEPTH_LEQUAL");
+    if (fr->depth_func != GSB_DEPTH_NONE && !fr->scene_depth && fr->gl_depth_texture == 0)
+        return fail(GSB_ERR_INVALID, "gsb_render: depth_func set but neither scene_depth nor gl_depth_texture given");
     CU(cudaSetDevice(ctx->device));
     (void)cudaGetLastError();            // a non-sticky error left by an earlier failed call (e.g. GL interop without a GL context) is not this frame's
     cudaStream_t s = ctx->stream;
@@ -598,6 +605,13 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     fc.sh_order = do_sh ? std::min(ctx->sh_order, 3) : 0;
     fc.row_rank = fr->row_rank; fc.row_world = fr->row_world; fc.row_group = fr->row_group > 1 ? fr->row_group : 1;
     fc.eps_t = ctx->eps_t;
+    // scene-depth occlusion (R.C:608-610; SRC.h:278-282): window depth = ndc_z * (far - near)/2 + (far + near)/2
+    fc.depth_func = fr->depth_func;
+    {
+        float dn = fr->depth_range[0], df = fr->depth_range[1];
+        if (dn == 0.0f && df == 0.0f) df = 1.0f;                            // unset -> glDepthRange default
+        fc.depth_hr = (df - dn) * 0.5f; fc.depth_hm = (df + dn) * 0.5f;
+    }
     const int num_tiles = fc.tiles_x * fc.tiles_y;
     const int64_t n = ctx->splat_count;
     const size_t  N = (size_t)n;
@@ -662,6 +676,30 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
             fb_final = static_cast<float4*>(pa.devicePointer);
             host_is_final = true;
         } else (void)cudaGetLastError();
+    }
+
+    const float* scene_depth = nullptr;
+    if (fc.depth_func != GSB_DEPTH_NONE) {
+        scene_depth = static_cast<const float*>(fr->scene_depth);
+        if (!scene_depth) {
+            // Houdini's depth attachment, copied by the shim into an R32F texture: map it and copy it device->device
+            if (ctx->gl_depth_res && (ctx->gl_depth_tex != fr->gl_depth_texture || ctx->gl_depth_w != fr->width || ctx->gl_depth_h != fr->height)) {
+                cudaGraphicsUnregisterResource(ctx->gl_depth_res); ctx->gl_depth_res = nullptr;
+            }
+            if (!ctx->gl_depth_res) {
+                CU(cudaGraphicsGLRegisterImage(&ctx->gl_depth_res, fr->gl_depth_texture, 0x0DE1u /* GL_TEXTURE_2D */,
+                                               cudaGraphicsRegisterFlagsReadOnly));
+                ctx->gl_depth_tex = fr->gl_depth_texture; ctx->gl_depth_w = fr->width; ctx->gl_depth_h = fr->height;
+            }
+            CU(ctx->scene_depth_buf.ensure((size_t)fr->width * fr->height * 4));
+            cudaArray_t arr = nullptr;
+            CU(cudaGraphicsMapResources(1, &ctx->gl_depth_res, s));
+            CU(cudaGraphicsSubResourceGetMappedArray(&arr, ctx->gl_depth_res, 0, 0));
+            CU(cudaMemcpy2DFromArrayAsync(ctx->scene_depth_buf.p, (size_t)fr->width * 4, arr, 0, 0, (size_t)fr->width * 4,
+                                          (size_t)fr->height, cudaMemcpyDeviceToDevice, s));
+            CU(cudaGraphicsUnmapResources(1, &ctx->gl_depth_res, s));
+            scene_depth = ctx->scene_depth_buf.as<float>();
+        }
     }
 
     unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D_c [2] sort/scan error [3] done tiles [4] D [5] L [6] scan total
@@ -756,6 +794,8 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         // depth sort of the live splats: stable LSD, ties keep ascending index
         for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
         CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16)); CU(ctx->ltiles.ensure((size_t)L * 8 + 16));
+        if (scene_depth) CU(ctx->zdepth.ensure((size_t)L * 4 + 16));
+        float* zdepth = scene_depth ? ctx->zdepth.as<float>() : nullptr;
         CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)std::max<uint64_t>(D, L))));
         ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), (size_t)L, 0, key_bits,
@@ -764,7 +804,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
-        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, s);
+        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
         // K4: live-tile counts (K2) -> offsets -> instances -> stable partition by tile -> tile ranges
@@ -779,7 +819,8 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         st.launches += (D ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][3], s));
         launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fb_final, fc,
-                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 1, cnt + 3, s);
+                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 1, cnt + 3,
+                     zdepth, scene_depth, s);
         st.launches += 1;
         if (tm) CU(cudaEventRecord(ctx->evc[c][4], s));
     }

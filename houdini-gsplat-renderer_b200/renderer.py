@@ -52,7 +52,11 @@ class FrameC(C.Structure):
                 ("inv_object", C.c_float * 16), ("obj_view", C.c_float * 16),
                 ("width", C.c_int32), ("height", C.c_int32), ("is_object_level", C.c_int32),
                 ("row_rank", C.c_int32), ("row_world", C.c_int32), ("row_group", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("depth_func", C.c_int32), ("gl_depth_texture", C.c_uint32), ("depth_range", C.c_float * 2),
+                ("scene_depth", C.c_void_p)]
+
+
+DEPTH_NONE, DEPTH_LESS, DEPTH_LEQUAL = 0, 1, 2
 
 
 class TargetC(C.Structure):
@@ -132,13 +136,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def frame_to_c(frame, row_rank: int = 0, row_world: int = 1, row_group: int = 1) -> FrameC:
+def frame_to_c(frame, row_rank: int = 0, row_world: int = 1, row_group: int = 1, scene_depth: int | None = None,
+               depth_func: int = 0, depth_range=(0.0, 1.0)) -> FrameC:
     f = FrameC()
     for name in ("view", "proj", "object", "inv_object", "obj_view"):
         getattr(f, name)[:] = np.asarray(getattr(frame, name), np.float32).reshape(16).tolist()
     f.width, f.height = int(frame.width), int(frame.height)
     f.is_object_level = int(bool(getattr(frame, "is_object_level", False)))
     f.row_rank, f.row_world, f.row_group = int(row_rank), int(row_world), int(row_group)
+    f.depth_func, f.gl_depth_texture, f.scene_depth = int(depth_func), 0, scene_depth
+    f.depth_range[:] = [float(depth_range[0]), float(depth_range[1])]
     return f
 
 
@@ -250,11 +257,15 @@ class GSplatRenderer:
         self._ck(self._lib.gsb_generate_render_geometry(self._h), "gsb_generate_render_geometry")
 
     def render(self, frame, host_rgba: np.ndarray | None = None, device_rgba: int | None = None,
-               row_rank: int = 0, row_world: int = 1, row_group: int = 1, final_rgba: int | None = None):
+               row_rank: int = 0, row_world: int = 1, row_group: int = 1, final_rgba: int | None = None,
+               scene_depth: int | None = None, depth_func: int = 0, depth_range=(0.0, 1.0)):
         """GSplatRenderer::render(r, isObjectLevel) (R.C:534-658).  ``frame`` supplies what the reference
         reads from RE_Render / glH_*; the finished frame goes to the library's device buffer, to
-        ``device_rgba`` (a CUDA pointer) and/or to ``host_rgba`` ([H,W,4] f32, D2H inside the call)."""
-        fc = frame if isinstance(frame, FrameC) else frame_to_c(frame, row_rank, row_world, row_group)
+        ``device_rgba`` (a CUDA pointer) and/or to ``host_rgba`` ([H,W,4] f32, D2H inside the call).
+        ``scene_depth`` (CUDA pointer to [H,W] f32 window depth) + ``depth_func``: the reference's depth test against the
+        scene already in the viewport (R.C:608-610)."""
+        fc = frame if isinstance(frame, FrameC) else frame_to_c(frame, row_rank, row_world, row_group, scene_depth,
+                                                                depth_func, depth_range)
         t = TargetC(device_rgba, None if host_rgba is None else host_rgba.ctypes.data, 0, 0, final_rgba)
         self._ck(self._lib.gsb_render(self._h, C.byref(fc), C.byref(t)), "gsb_render")
 

@@ -29,7 +29,7 @@ extern "C" {
 #define GSB_API
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 #define GSB_TILE 16                       /* screen tile edge in pixels */
 #define GSB_REFERENCE_SPLAT_CAP 8388607   /* GSPLAT_COUNT_MAX - 1, include/GSplatRenderer.h:26, src/GSplatRenderer.C:336 */
 #define GSB_ID_MAX 128                    /* bytes for a registry id string incl. NUL */
@@ -66,8 +66,24 @@ typedef struct gsb_frame {
     int32_t row_rank;        /* multi-GPU: this context blends tile rows ty with (ty / row_group) % row_world == row_rank */
     int32_t row_world;       /* 1 = whole frame */
     int32_t row_group;       /* tile rows per interleaved band; 0 or 1 = single rows.  Wider bands duplicate fewer splats */
-    int32_t reserved[2];
+    /* Scene-depth occlusion.  The reference draws with the depth test on and depth writes off
+     * (src/GSplatRenderer.C:608-610) and gives every vertex of a splat's quad the CENTRE's clip z and w
+     * (shaders/GSplatShaderSource.h:278-282), so a splat's fragments all carry one window depth
+     * zw = clip.z/clip.w * (far-near)/2 + (far+near)/2; a fragment is kept iff zw passes depth_func against the scene
+     * depth at its pixel.  Nothing is written to the depth buffer. */
+    int32_t depth_func;        /* enum gsb_depth_func; GSB_DEPTH_NONE (0) = no occlusion */
+    uint32_t gl_depth_texture; /* optional: an R32F / DEPTH_COMPONENT32F GL_TEXTURE_2D of the frame size holding the scene's
+                                  window depth; mapped read-only through CUDA<->GL interop (needs a current GL context).
+                                  Used when scene_depth is NULL */
+    float   depth_range[2];    /* glDepthRange near, far (glH_DepthRange, GSplatShaderSource.h:158); {0,0} is read as {0,1} */
+    const void* scene_depth;   /* device pointer, width*height floats, window depth in [0,1], row 0 = bottom scanline */
 } gsb_frame;
+
+enum gsb_depth_func {
+    GSB_DEPTH_NONE = 0,
+    GSB_DEPTH_LESS = 1,        /* GL_LESS   (OpenGL's default) */
+    GSB_DEPTH_LEQUAL = 2       /* GL_LEQUAL (what Houdini's viewport passes use) */
+};
 
 /* Where the finished frame goes.  All optional; with everything NULL the frame stays in the
  * library-owned device buffer (gsb_device_framebuffer). */

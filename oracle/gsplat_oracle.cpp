@@ -418,6 +418,32 @@ int64_t orc_project(const orc_frame* F, int64_t n,
     return nvis;
 }
 
+/* ---------------------------------------------------------------- scene-depth occlusion
+ * The reference draws with the depth test ON and depth writes OFF (R.C:608-610), and every vertex of a splat's quad
+ * carries the CENTRE's clip z and w (SRC.h:278-282: out_vertex = centerClipPos, only xy displaced), so all fragments of
+ * a splat have one window depth: zw = ndc_z * (far - near)/2 + (far + near)/2 with ndc_z = clip.z / clip.w and
+ * (near, far) = glDepthRange (glH_DepthRange, SRC.h:158).  A fragment survives iff zw passes the depth function against
+ * the scene depth already in the buffer at its pixel.  Spec: hr = (far - near) * 0.5f, hm = (far + near) * 0.5f,
+ * zw = (ndc_z * hr) + hm, fp32, no contraction.  zw[i] is defined for every splat whose clip.w > 0 (else 0). */
+void orc_window_depth(const orc_frame* F, int64_t n, const float* pos, const float depth_range[2], float* zw)
+{
+    const float hr = (depth_range[1] - depth_range[0]) * 0.5f, hm = (depth_range[1] + depth_range[0]) * 0.5f;
+    const float* OV = F->obj_view; const float* P = F->proj;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = pos + 3 * i;
+        float ps[3];
+        for (int k = 0; k < 3; ++k) { float t = p[k] - F->origin[k]; ps[k] = t + F->origin[k]; }
+        float vc[3];
+        for (int r = 0; r < 3; ++r)
+            vc[r] = ((MAT(OV, r, 0) * ps[0] + MAT(OV, r, 1) * ps[1]) + MAT(OV, r, 2) * ps[2]) + MAT(OV, r, 3);
+        float fy = -vc[1];
+        float cz = ((MAT(P, 2, 0) * vc[0] + MAT(P, 2, 1) * fy) + MAT(P, 2, 2) * vc[2]) + MAT(P, 2, 3);
+        float cw = ((MAT(P, 3, 0) * vc[0] + MAT(P, 3, 1) * fy) + MAT(P, 3, 2) * vc[2]) + MAT(P, 3, 3);
+        zw[i] = (cw > 0.0f) ? ((cz / cw) * hr) + hm : 0.0f;
+    }
+}
+
 /* ---------------------------------------------------------------- binning
  * Instances are emitted in global depth order and stably partitioned by tile id.
  * tile id = ty * TX + tx, origin bottom-left.  Only owned tile rows are emitted.
@@ -471,9 +497,19 @@ static inline int shade(const orc_record& s, float px, float py, float eps, floa
 
 /* tiled blend.  rgba: H*W*4 floats, row 0 = bottom (GL).  Un-owned tile rows are left as is.
  * consumed[t] (may be NULL) = instances traversed until every pixel of tile t saturated. */
-int64_t orc_blend(const orc_frame* F, const orc_record* recs, const int64_t* tile_start,
-                  const int32_t* inst, float* rgba, int64_t* consumed)
+enum { ORC_DEPTH_NONE = 0, ORC_DEPTH_LESS = 1, ORC_DEPTH_LEQUAL = 2 };
+static inline int depth_pass(int func, float zw, float sd)
 {
+    return func == ORC_DEPTH_LESS ? (zw < sd) : (func == ORC_DEPTH_LEQUAL ? (zw <= sd) : 1);
+}
+
+/* zw: window depth per splat (orc_window_depth), scene_depth: H*W floats, row 0 = bottom; depth_func = ORC_DEPTH_*.
+ * A fragment that fails the depth test is dropped (no colour, no transmittance change). */
+int64_t orc_blend_depth(const orc_frame* F, const orc_record* recs, const int64_t* tile_start,
+                        const int32_t* inst, float* rgba, int64_t* consumed,
+                        const float* zw, const float* scene_depth, int depth_func)
+{
+    if (!zw || !scene_depth) depth_func = ORC_DEPTH_NONE;
     const int W = F->width, H = F->height;
     const int TX = (W + ORC_TILE - 1) / ORC_TILE, TY = (H + ORC_TILE - 1) / ORC_TILE;
     const float eps = F->eps_t;
@@ -496,6 +532,10 @@ int64_t orc_blend(const orc_frame* F, const orc_record* recs, const int64_t* til
                 if (done[k]) continue;
                 float px = (float)(tx * ORC_TILE + (k % ORC_TILE)) + 0.5f;
                 float py = (float)(ty * ORC_TILE + (k / ORC_TILE)) + 0.5f;
+                if (depth_func != ORC_DEPTH_NONE) {
+                    int x = tx * ORC_TILE + (k % ORC_TILE), y = ty * ORC_TILE + (k / ORC_TILE);
+                    if (!depth_pass(depth_func, zw[inst[q]], scene_depth[(size_t)y * W + x])) continue;
+                }
                 if (shade(sp, px, py, eps, C[k], &T[k])) { done[k] = 1; --live; }
             }
             if (live == 0) { used = q - s + 1; break; }
@@ -509,6 +549,12 @@ int64_t orc_blend(const orc_frame* F, const orc_record* recs, const int64_t* til
         }
     }
     return total;
+}
+
+int64_t orc_blend(const orc_frame* F, const orc_record* recs, const int64_t* tile_start,
+                  const int32_t* inst, float* rgba, int64_t* consumed)
+{
+    return orc_blend_depth(F, recs, tile_start, inst, rgba, consumed, nullptr, nullptr, ORC_DEPTH_NONE);
 }
 
 /* brute force: every pixel walks every visible splat in depth order, no rectangles, no tiles.

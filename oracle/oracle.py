@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
         _lib.orc_project.restype = C.c_int64
         _lib.orc_bin.restype = C.c_int64
         _lib.orc_blend.restype = C.c_int64
+        _lib.orc_blend_depth.restype = C.c_int64
         _lib.orc_det_log.restype = C.c_double
         _lib.orc_det_log.argtypes = [C.c_double]
         _lib.orc_half_to_float.restype = C.c_float
@@ -157,6 +158,32 @@ def blend(F: OrcFrame, recs, tile_start, inst, rgba=None):
     return rgba, consumed, int(total)
 
 
+DEPTH_NONE, DEPTH_LESS, DEPTH_LEQUAL = 0, 1, 2
+
+
+def window_depth(F: OrcFrame, cloud, depth_range=(0.0, 1.0)) -> np.ndarray:
+    """Window-space depth of every splat's quad (the centre's, SRC.h:278-282) under glDepthRange = depth_range."""
+    pos = _c(cloud.pos, np.float32)
+    dr = np.asarray(depth_range, np.float32)
+    out = np.zeros(pos.shape[0], np.float32)
+    lib().orc_window_depth(C.byref(F), C.c_int64(pos.shape[0]), _p(pos), _p(dr), _p(out))
+    return out
+
+
+def blend_depth(F: OrcFrame, recs, tile_start, inst, zw, scene_depth, depth_func, rgba=None):
+    """orc_blend with the reference's depth test against an existing scene depth buffer (R.C:608-610)."""
+    tx = (F.width + TILE - 1) // TILE; ty = (F.height + TILE - 1) // TILE
+    if rgba is None:
+        rgba = np.zeros((F.height, F.width, 4), np.float32)
+    consumed = np.zeros(tx * ty, np.int64)
+    inst = _c(inst, np.int32) if inst.shape[0] else np.zeros(1, np.int32)
+    zw = _c(zw, np.float32); sd = _c(scene_depth, np.float32)
+    assert sd.shape == (F.height, F.width)
+    total = lib().orc_blend_depth(C.byref(F), _p(recs), _p(tile_start), _p(inst), _p(rgba), _p(consumed),
+                                  _p(zw), _p(sd), C.c_int(int(depth_func)))
+    return rgba, consumed, int(total)
+
+
 def blend_bruteforce(F: OrcFrame, order, vis, recs):
     rgba = np.zeros((F.height, F.width, 4), np.float32)
     order = _c(order, np.int32)
@@ -173,11 +200,15 @@ def render(F: OrcFrame, cloud, time_reference_sort: bool = False):
     return rgba, {k: getattr(st, k) for k, _ in OrcStats._fields_}
 
 
-def pipeline(F: OrcFrame, cloud):
-    """All intermediates, for stage-by-stage parity checks."""
+def pipeline(F: OrcFrame, cloud, scene_depth=None, depth_func=DEPTH_NONE, depth_range=(0.0, 1.0)):
+    """All intermediates, for stage-by-stage parity checks.  scene_depth ([H,W] f32) + depth_func: SURVEY 8f-3."""
     pr = project(F, cloud)
     order = sort(pr["keys"])
     ts, inst = bin_tiles(F, order, pr["vis"], pr["rects"])
+    if scene_depth is not None and depth_func != DEPTH_NONE:
+        zw = window_depth(F, cloud, depth_range)
+        rgba, consumed, total = blend_depth(F, pr["recs"], ts, inst, zw, scene_depth, depth_func)
+        return dict(pr, order=order, tile_start=ts, inst=inst, rgba=rgba, consumed=consumed, n_consumed=total, zw=zw)
     rgba, consumed, total = blend(F, pr["recs"], ts, inst)
     return dict(pr, order=order, tile_start=ts, inst=inst, rgba=rgba, consumed=consumed, n_consumed=total)
 

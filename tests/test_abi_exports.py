@@ -30,14 +30,14 @@ def test_library_exports_every_declared_symbol():
     assert sorted(R.EXPORTS) == syms
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.gsb_abi_version() == 1
+    assert lib.gsb_abi_version() == 2
     assert lib.gsb_last_error() is not None
 
 
 def test_struct_layouts_match_header():
     from houdini_gsplat_renderer_b200 import renderer as R
     assert C.sizeof(R.PrimKey) == 48
-    assert C.sizeof(R.FrameC) == 5 * 64 + 8 * 4
+    assert C.sizeof(R.FrameC) == 5 * 64 + 6 * 4 + 4 + 4 + 8 + 8      # matrices, ints, depth_func, gl tex, range, pointer
     assert C.sizeof(R.TargetC) == 32
     assert R.RECORD_DTYPE.itemsize == 48 and R.RECT_DTYPE.itemsize == 8
     assert C.sizeof(R.StatsC) == 4 * 8 + 10 * 4 + 6 * 4 + 8 * 4 + 8
