@@ -37,6 +37,8 @@ void toColumnMajorF(const UT_Matrix4D& m, float out[16])
 
 RE_Texture* theFrameTexture = nullptr;       // RGBA32F, viewport sized; CUDA writes it, a quad composites it
 int theFrameW = 0, theFrameH = 0;
+RE_Texture* theDepthTexture = nullptr;       // R32F copy of the beauty pass's depth attachment; CUDA reads it
+int theDepthW = 0, theDepthH = 0;
 
 }  // namespace
 
@@ -96,6 +98,22 @@ void GSplatRenderer::render(RE_RenderContext r, bool isObjectLevel)
         theFrameTexture->setTexture(r, nullptr);
         theFrameW = f.width; theFrameH = f.height;
     }
+    // Scene-depth occlusion (the reference draws its quads with the depth test on, R.C:608-610): copy the beauty pass's
+    // depth attachment into an R32F texture the library maps read-only (gsb_frame.gl_depth_texture); every fragment of a
+    // splat is tested with the splat centre's window depth, exactly what the reference's constant-z quads do.
+    if (!theDepthTexture || theDepthW != f.width || theDepthH != f.height) {
+        if (theDepthTexture) theDepthTexture->free();
+        theDepthTexture = RE_Texture::newTexture(RE_TEXTURE_2D);
+        theDepthTexture->setFormat(RE_GPU_FLOAT32, 1);
+        theDepthTexture->setResolution(f.width, f.height);
+        theDepthTexture->setTexture(r, nullptr);
+        theDepthW = f.width; theDepthH = f.height;
+    }
+    copyBoundDepthAttachmentTo(r, theDepthTexture);        // glCopyTexSubImage2D / a blit from the draw FBO's depth attachment
+    f.gl_depth_texture = theDepthTexture->getID();
+    f.depth_func = GSB_DEPTH_LEQUAL;                       // the viewport's depth function (RE_Render::getZFunction)
+    f.depth_range[0] = 0.0f; f.depth_range[1] = 1.0f;      // glH_DepthRange
+
     gsb_target t{};
     t.gl_texture = theFrameTexture->getID();
     if (gsb_render(theContext(), &f, &t) != GSB_OK) {
@@ -106,9 +124,10 @@ void GSplatRenderer::render(RE_RenderContext r, bool isObjectLevel)
     gsb_get_stats(theContext(), &st);
     if (!st.rendered) return;                              // same silent early-returns as the reference's render()
 
-    // composite the premultiplied frame under the beauty pass exactly like the reference's ROP state:
-    // depth test on, depth write off, ADD, (ONE_MINUS_DST_ALPHA, ONE) for colour and alpha
-    r->pushDepthState(); r->disableDepthBufferWriting();
+    // composite the premultiplied frame under the beauty pass exactly like the reference's ROP state: depth write off,
+    // ADD, (ONE_MINUS_DST_ALPHA, ONE) for colour and alpha.  The depth test already happened per fragment inside the
+    // library, so the full-screen quad itself is drawn with the test disabled.
+    r->pushDepthState(); r->disableDepthTest(); r->disableDepthBufferWriting();
     r->pushBlendState(); r->blend(1);
     r->setBlendFunction(RE_SBLEND_ONE_MINUS_DST_ALPHA, RE_DBLEND_ONE);
     r->setAlphaBlendFunction(RE_SBLEND_ONE_MINUS_DST_ALPHA, RE_DBLEND_ONE);
