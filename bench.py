@@ -46,7 +46,7 @@ REF_BUDGET_S = 150.0   # wall budget of the whole --impl reference run
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="20M_sh3_1080p")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -81,7 +81,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -190,6 +190,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     S, w, cloud, gen_s = load_workload(args.workload)
@@ -278,7 +280,7 @@ def run_ours(args):
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms, acc, cnt
 
-    # clocks are sampled (100 ms period) from before the warm-up to the end of the second timed region: the GPU is
+    # clocks are sampled (20 ms period) from before the warm-up to the end of the second timed region: the GPU is
     # under the same load throughout, so short timed regions still get a meaningful median
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.wait_first_sample()

@@ -41,6 +41,12 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// 2^t, t <= 0 and far above the denormal range here (t >= -ln(255) * log2(e) > -8): the bare MUFU.EX2 that __expf's
+// t >= -126 path executes, without the range test and the two predicated scalings around it (same bits)
+__device__ __forceinline__ float ex2_mufu(float t)
+{
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t)); return r;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -71,7 +77,8 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     const int bx = tx * TILE + (warp & 1) * 8, by = ty * TILE + (warp >> 1) * 4;
     const int px = bx + (lane & 7), py = by + (lane >> 3);
     const bool inside = px < F.width && py < F.height;
-    const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+    float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+    asm volatile("" : "+f"(fpx), "+f"(fpy));       // keep the pixel centre in registers (ptxas re-materialised fpx per visit)
     // pixel-centre box of this warp's 8x4 block
     const float wx_lo = (float)bx + 0.5f, wx_hi = (float)bx + 7.5f;
     const float wy_lo = (float)by + 0.5f, wy_hi = (float)by + 3.5f;
@@ -84,7 +91,9 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     if (tid == 0) s_consumed = 0u;
     __syncthreads();
 
-    float Cr = 0.0f, Cg = 0.0f, Cb = 0.0f, T = 1.0f;
+    // A pixel is live while T >= eps; pixels outside the image carry T = -1 (never live, never stored), so the
+    // transmittance itself is the "done" state and the inner loop needs no separate flag.
+    float Cr = 0.0f, Cg = 0.0f, Cb = 0.0f, T = inside ? 1.0f : -1.0f;
     if (!first && inside) {                                               // between chunks fb holds (C, T)
         const float4 st = fb[(size_t)py * F.width + px];
         Cr = st.x; Cg = st.y; Cb = st.z; T = st.w;
@@ -98,8 +107,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sd_max = fmaxf(sd_max, __shfl_xor_sync(0xffffffffu, sd_max, o));
     }
-    bool done = !inside || (T < eps);
-    bool warp_done = __all_sync(0xffffffffu, done);
+    bool warp_done = __all_sync(0xffffffffu, T < eps);
     uint32_t done_pos = 0;                       // instances traversed when this pixel saturated (0: it started saturated)
     const uint32_t nb = (len + BL_BATCH - 1) / BL_BATCH;
 
@@ -161,23 +169,23 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                     const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
                     bool zpass = true;
                     if (DEPTH) { const float zw = sz[b & 1][c + j]; zpass = lequal ? (zw <= sd) : (zw < sd); }
-                    if (!done && zpass) {
+                    if (T >= eps && zpass) {
                         const float dx = fpx - r0.x, dy = fpy - r0.y;
                         const float qx = fmaf(dy, r0.w, dx * r0.z);
                         const float qy = fmaf(dy, r1.y, dx * r1.x);
                         const float pw = fmaf(qy, qy, qx * qx);
                         if (fabsf(qx) <= 2.0f && fabsf(qy) <= 2.0f && pw <= r1.w) {
-                            const float A = fminf(r1.z * __expf(-pw), 1.0f);
+                            const float A = fminf(r1.z * ex2_mufu(pw * -1.4426950408889634f), 1.0f);   // alpha * exp(-pw)
                             const float w = T * A;
                             Cr = fmaf(w, r2.x, Cr); Cg = fmaf(w, r2.y, Cg); Cb = fmaf(w, r2.z, Cb);
                             T = T - w;
-                            if (T < eps) { done = true; done_pos = b * BL_BATCH + c + (uint32_t)j + 1u; }
+                            if (T < eps) done_pos = b * BL_BATCH + c + (uint32_t)j + 1u;
                         }
                     }
                 }
                 // early-out vote once per 32 instances, not per visit: a saturated warp may walk the rest of its group
                 // with every lane predicated off (no effect on the frame); done_pos keeps the exact position
-                warp_done = __all_sync(0xffffffffu, done);
+                warp_done = __all_sync(0xffffffffu, T < eps);
             }
         }
         // barrier: everyone is finished with buf before it is refilled; also the CTA-wide early-out vote
