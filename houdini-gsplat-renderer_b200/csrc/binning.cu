@@ -149,7 +149,9 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
     }
 }
 
-// one CTA: tile_base = exclusive scan of tile_l; *l_total, *d_total = grand totals
+// one CTA: tile_base = exclusive scan of tile_l; *l_total, *d_total = grand totals.  Every thread owns a run of
+// consecutive entries (sum, one block-wide scan of the 1024 sums, write-back), so the kernel is three short phases
+// instead of one barrier round per 1024 entries.
 __global__ void __launch_bounds__(1024)
 select_scan_kernel(const uint32_t* __restrict__ tile_l, const uint32_t* __restrict__ tile_d, uint32_t nt,
                    uint32_t* __restrict__ tile_base, unsigned long long* __restrict__ l_total,
@@ -157,36 +159,29 @@ select_scan_kernel(const uint32_t* __restrict__ tile_l, const uint32_t* __restri
 {
     __shared__ uint32_t s_w[32];
     __shared__ unsigned long long s_d[32];
-    __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0u;
+    const uint32_t per = (nt + 1023u) / 1024u;
+    const uint32_t b0 = min(threadIdx.x * per, nt), b1 = min(b0 + per, nt);
+    uint32_t mine = 0;
     unsigned long long dacc = 0;
-    __syncthreads();
-    for (uint32_t b0 = 0; b0 < nt; b0 += 1024) {
-        const uint32_t i = b0 + threadIdx.x;
-        const uint32_t v = (i < nt) ? tile_l[i] : 0u;
-        dacc += (i < nt) ? (unsigned long long)tile_d[i] : 0ull;
-        uint32_t inc = v;
+    for (uint32_t i = b0; i < b1; ++i) { mine += tile_l[i]; dacc += (unsigned long long)tile_d[i]; }
+    uint32_t inc = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        uint32_t woff = 0, btot = 0;
-#pragma unroll
-        for (int w = 0; w < 32; ++w) { woff += (w < warp) ? s_w[w] : 0u; btot += s_w[w]; }
-        if (i < nt) tile_base[i] = s_carry + woff + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += btot;
-        __syncthreads();
-    }
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if (lane == 31) s_w[warp] = inc;
     if (lane == 0) s_d[warp] = dacc;
     __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { woff += (w < warp) ? s_w[w] : 0u; total += s_w[w]; }
+    uint32_t run = woff + inc - mine;
+    for (uint32_t i = b0; i < b1; ++i) { tile_base[i] = run; run += tile_l[i]; }
     if (threadIdx.x == 0) {
         unsigned long long d = 0;
         for (int w = 0; w < 32; ++w) d += s_d[w];
-        *l_total = (unsigned long long)s_carry; *d_total = d;
+        *l_total = (unsigned long long)total; *d_total = d;
     }
 }
 
@@ -241,14 +236,31 @@ emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ o
     }
 }
 
+// ranges[t] = [first, last + 1) of tile t's run in the tile-sorted instance list; four ids per thread (one 16-byte
+// load plus the two neighbours)
 __global__ void __launch_bounds__(256)
 tile_range_kernel(const uint32_t* __restrict__ ids, uint64_t d, uint2* __restrict__ ranges)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d) return;
-    const uint32_t t = __ldg(ids + j);
-    if (j == 0 || __ldg(ids + j - 1) != t) ranges[t].x = (uint32_t)j;
-    if (j + 1 == d || __ldg(ids + j + 1) != t) ranges[t].y = (uint32_t)(j + 1);
+    const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= d) return;
+    uint32_t v[6];                                           // ids[j0 - 1 .. j0 + 4]; 0xFFFFFFFF outside the list
+    if (j0 + 4 <= d) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(ids + j0));
+        v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[1 + k] = (j0 + k < d) ? __ldg(ids + j0 + k) : 0xFFFFFFFFu;
+    }
+    v[0] = j0 > 0 ? __ldg(ids + j0 - 1) : 0xFFFFFFFFu;
+    v[5] = (j0 + 4 < d) ? __ldg(ids + j0 + 4) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t j = j0 + k;
+        if (j >= d) break;
+        const uint32_t t = v[1 + k];
+        if (v[k] != t) ranges[t].x = (uint32_t)j;
+        if (v[2 + k] != t) ranges[t].y = (uint32_t)(j + 1);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -312,7 +324,7 @@ void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* rang
 {
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s);
     if (d == 0) return;
-    tile_range_kernel<<<(unsigned)((d + 255) / 256), 256, 0, s>>>(sorted_tile_ids, d, ranges);
+    tile_range_kernel<<<(unsigned)((d + 1023) / 1024), 256, 0, s>>>(sorted_tile_ids, d, ranges);
 }
 
 void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,
