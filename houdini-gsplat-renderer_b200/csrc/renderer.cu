@@ -3,8 +3,9 @@
 // (/root/reference/gsplat_plugin/include/GSplatRenderer.h:29-131, src/GSplatRenderer.C:141-153,
 // 218-320, 322-378, 403-418, 534-563, 660-694).  What the reference does with GL textures, a CPU
 // argsort and one instanced draw is done here with CUDA launches on one stream:
-//   pack (on active-set change) | project+SH+key -> radix sort -> tile counts -> scan -> emit ->
-//   tile radix partition -> tile ranges -> blend | optional D2H.
+//   pack (on active-set change) | K1 cull+key+tile rect for every splat -> chunk plan | per depth chunk: live map SAT ->
+//   live selection -> depth radix sort -> K2 records+SH+tile rects+counts -> scan -> emit -> tile radix partition ->
+//   tile ranges -> blend (finished tiles straight to the device / pinned host / peer-GPU frame) | optional D2H, GL interop.
 // No CPU fallback exists: every entry point fails with GSB_ERR_CUDA if the device is unusable.
 #include "common.cuh"
 #include "../../include/gsplat_b200.h"
