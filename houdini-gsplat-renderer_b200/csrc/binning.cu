@@ -21,15 +21,21 @@ __device__ __forceinline__ TileRect tile_rect(uint2 r)
     return t;
 }
 
-// same, with the packed word already in a register (has_packed false: exact rectangle of splat i)
+// tile rectangle from the packed word (has_packed false: exact rectangle of splat i).  A saturated ("wide") extent is
+// resolved from the exact rectangle, or — bounded K1, which keeps no exact rectangles (rects == NULL) — widened to the
+// whole screen: still a superset.
 __device__ __forceinline__ TileRect tile_rect_packed(const bool has_packed, const uint32_t p, const uint2* __restrict__ rects,
-                                                     const int64_t i)
+                                                     const int64_t i, const int tiles_x, const int tiles_y)
 {
     if (!has_packed) return tile_rect(__ldg(rects + i));
     TileRect t;
     t.empty = p == TRECT_CULLED;
     const int w = (int)((p >> 18) & 127u), h = (int)((p >> 25) & 127u);
-    if (!t.empty && (w == 127 || h == 127)) return tile_rect(__ldg(rects + i));
+    if (!t.empty && (w == 127 || h == 127)) {
+        if (rects) return tile_rect(__ldg(rects + i));
+        t.tx0 = 0; t.tx1 = tiles_x - 1; t.ty0 = 0; t.ty1 = tiles_y - 1;
+        return t;
+    }
     t.tx0 = (int)(p & 511u); t.ty0 = (int)((p >> 9) & 511u); t.tx1 = t.tx0 + w; t.ty1 = t.ty0 + h;
     return t;
 }
@@ -97,7 +103,7 @@ constexpr int SEL_TILE    = SEL_THREADS * SEL_ITEMS;     // 2048 elements per CT
 __global__ void __launch_bounds__(SEL_THREADS)
 select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ trects,
                     const uint2* __restrict__ rects, int64_t n, const ChunkPlan* __restrict__ plan, const int chunk,
-                    int tiles_x, const uint32_t* __restrict__ sat,
+                    int tiles_x, int tiles_y, const uint32_t* __restrict__ sat,
                     uint32_t* __restrict__ stage_k, uint32_t* __restrict__ stage_v,
                     uint32_t* __restrict__ tile_l, uint32_t* __restrict__ tile_d)
 {
@@ -123,7 +129,7 @@ select_count_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
     for (int j = 0; j < SEL_ITEMS; ++j) {
         uint32_t c = 0;
         if (key[j] >= key_lo && key[j] < key_hi) {      // key_hi <= KEY_CULLED: culled splats never pass
-            const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane);
+            const TileRect t = tile_rect_packed(trects != nullptr, tr[j], rects, base + j * 32 + lane, tiles_x, tiles_y);
             if (!t.empty) c = live_tiles(t.tx0, t.tx1, t.ty0, t.ty1, tiles_x, sat);
         }
         dsum += c;
@@ -303,7 +309,7 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
     uint32_t* tile_l = static_cast<uint32_t*>(scratch);
     uint32_t* tile_d = tile_l + nt;
     uint32_t* tile_base = tile_d + nt;
-    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, sat,
+    select_count_kernel<<<nt, SEL_THREADS, 0, s>>>(keys, trects, rects, n, plan, chunk, fc.tiles_x, fc.tiles_y, sat,
                                                    stage_k, stage_v, tile_l, tile_d);
     select_scan_kernel<<<1, 1024, 0, s>>>(tile_l, tile_d, nt, tile_base, l_total, d_total);
     select_gather_kernel<<<(nt + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32), GATHER_THREADS, 0, s>>>(

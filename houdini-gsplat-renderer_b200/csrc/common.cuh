@@ -24,6 +24,9 @@ struct FrameConsts {
     int   row_rank, row_world;  // tile-row ownership: row ty is owned iff (ty / row_group) % row_world == row_rank
     int   row_group;
     float eps_t;                // transmittance early-out threshold
+    // bounded K1 (project_bound_kernel): constants of the covariance chain evaluated on the host with the spec's fp32
+    // operations (focal = W*P00/2, limX/Y = 1.3*tanFov) and the squared spectral norm of mat3(view), rounded up
+    float focal, lim_x, lim_y, wnorm2;
     int   depth_func;           // scene-depth occlusion: 0 none, 1 LESS, 2 LEQUAL (gsb_depth_func)
     float depth_hr, depth_hm;   // window depth = (clip.z / clip.w) * depth_hr + depth_hm  ((far-near)/2, (far+near)/2)
 };
@@ -48,12 +51,14 @@ static_assert(sizeof(Record) == 48, "Record must be 48 bytes");
 constexpr int ROW_U4 = 8;                      // uint4 per splat line
 //   cached per object matrix (launch_sigma): world-space covariance, upper triangle
 //     sigA[i] = (S00, S01, S02, S11), sigB[i] = (S12, S22)      24 B
+//     lam[i]  = upper bound of the largest eigenvalue of that covariance                       4 B   (bounded K1)
 struct PackedSplats {
     const float4* geomA;
     const uint4*  geomB;
     const uint4*  rows;
     const float4* sigA;
     const float2* sigB;
+    const float*  lam;
 };
 
 // Depth buckets: a monotone (non-decreasing) map from the depth key to [0, DEPTH_BUCKETS-2], linear in the distance;
@@ -99,13 +104,20 @@ void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, con
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
                  int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* rows, int has_sh, cudaStream_t s);
 // world-space covariance planes from geomB and the object matrix (run when the object matrix or the packed set changes)
-void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, cudaStream_t s);
+void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, float* lam, cudaStream_t s);
 // K1 (every submitted splat): cull, depth key (culled -> KEY_CULLED), packed tile rectangle (trects, may be NULL), exact
 // pixel rectangle (rects: every splat if rects_all, else only the "wide" ones the packed form cannot hold),
 // *n_visible += V, and (bucket_hist != NULL) the DEPTH_BUCKETS-bin histogram of depth_bucket(key).
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
                     unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
+// Bounded K1 (every submitted splat, GSB_OPT_LAZY_PROJECT): the cheap exact culls (alpha, clip.w, clip.z), the exact
+// depth key, and a CONSERVATIVE packed tile rectangle — a superset of the exact one, from the centre and the bound
+// h <= min(rr, 2 sqrt 2) * sqrt(2 (|J|^2 |W|^2 lambda_max(Sigma) + 0.3)) on the quad's half extent — in ~1/5 of the exact
+// kernel's instructions and half its bytes (20 B read per splat).  Splats the bound keeps but the exact projection (K2)
+// culls get no instances.  *n_visible += splats that pass the cheap culls with a non-empty bound (an upper bound of V).
+void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
+                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
 // chunk plan from the bucket histogram: chunk c (< nchunks - 1) ends at the first bucket whose exclusive count reaches
 // V * (2^(c+1) - 1) / 2^shift (the first chunk holds V / 2^shift splats, every further one doubles; the last takes the rest)
 // and the bucket boundaries are turned into key boundaries (plan->key_lo: the smallest key whose bucket belongs to the

@@ -385,17 +385,145 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
     }
 }
 
+// ---- bounded K1 (GSB_OPT_LAZY_PROJECT): persistent CTAs like project_kernel, 20 B streamed per splat.
+// Exact (the spec's operations): the alpha / clip.w / clip.z culls and the depth key.  Bounded: the pixel rectangle.
+// With T = J W (LIB.h:38-76), lambda_1 = lambda_max(T Sigma T^T) + 0.3 <= |J|_2^2 |W|_2^2 lambda_max(Sigma) + 0.3 and
+// |J|_2^2 = j0^2 (1 + rx^2 + ry^2) (J J^T = j0^2 I + j2 j2^T, j2 = -j0 (rx, ry) with the clamped ratios rx, ry), so
+// s1 = sqrt(2 lambda_1) is bounded; the exact half extents are hx = min(2(|u1x| + |u2x|), rr |(u1x, u2x)|)(1 + 1e-4) + 0.01
+// <= min(2 sqrt 2, rr) s1 (1 + 1e-4) + 0.01 because |(u1x, u2x)| <= s1 and |u1x| + |u2x| <= sqrt 2 s1.  Divisions
+// and the square root here are the approximate MUFU forms; every approximation and every rounding of the exact
+// chain is covered by the explicit margins (relative 2e-3 on the extent, 0.06 px + 2e-6 |c| on the position).
+// A splat the bound keeps and the exact projection culls (degenerate axes, empty exact rectangle) gets a zero live-tile
+// count in K2 and no instances.  NaN positions behave like the exact kernel's fmaxf/fminf: the rectangle opens up.
+__global__ void __launch_bounds__(K1_THREADS, 6)
+project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA, const float* __restrict__ lam,
+                     int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ trects,
+                     unsigned long long* __restrict__ n_visible, const DepthBuckets db, uint32_t* __restrict__ bucket_hist)
+{
+    __shared__ uint32_t sh_hist[DEPTH_BUCKETS];
+    if (bucket_hist) {
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) sh_hist[b] = 0u;
+        __syncthreads();
+    }
+    uint32_t nvis = 0;
+    const int64_t stride = (int64_t)gridDim.x * K1_THREADS;
+    int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
+    float4 ga_next = make_float4(0.f, 0.f, 0.f, -1.f); float lm_next = 0.f;
+    if (i < n) { ga_next = __ldg(geomA + i); lm_next = __ldg(lam + i); }
+    for (; i < n; i += stride) {
+        const float4 ga = ga_next; const float lm = lm_next;
+        if (i + stride < n) { ga_next = __ldg(geomA + i + stride); lm_next = __ldg(lam + i + stride); }
+        const float p[3] = { ga.x, ga.y, ga.z };
+        const float rr = ga.w;
+        uint32_t key = KEY_CULLED, tr = TRECT_CULLED;
+        bool vis = rr >= 0.0f;
+        float psx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; psx[k] = t + F.origin[k]; }
+        float vc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
+        const float fy = -vc[1];
+        float clip[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
+        const float cw = clip[3];
+        vis = vis && (cw > 0.0f) && (clip[2] >= -cw && clip[2] <= cw);
+        if (vis) {
+            const float iw = __fdividef(1.0f, cw);
+            const float cx = (clip[0] * iw + 1.0f) * 0.5f * F.W;
+            const float cy = ((-clip[1]) * iw + 1.0f) * 0.5f * F.H;
+            float t[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                t[r] = ((MAT(F.view, r, 0) * psx[0] + MAT(F.view, r, 1) * psx[1]) + MAT(F.view, r, 2) * psx[2]) + MAT(F.view, r, 3);
+            const float itz = __fdividef(1.0f, t[2]);
+            const float rx = fminf(fmaxf(t[0] * itz, -F.lim_x), F.lim_x) * 1.0001f;
+            const float ry = fminf(fmaxf(t[1] * itz, -F.lim_y), F.lim_y) * 1.0001f;
+            const float j0 = F.focal * itz;
+            const float nj2 = (j0 * j0) * ((1.0f + rx * rx) + ry * ry);
+            const float l1 = ((nj2 * F.wnorm2) * lm + 0.3f) * 1.002f;         // >= lambda_1 of the exact chain
+            float s1; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(2.0f * l1));
+            s1 = fminf(s1 * 1.0005f, 4096.0f);
+            float hb = (fminf(rr, 2.8284272f) * s1) * 1.001f + 0.06f;
+            if (!(hb <= 1.0e9f)) hb = 1.0e9f;                                   // inf / NaN bound: the whole screen
+            const float hbx = hb + 2.0e-6f * fabsf(cx), hby = hb + 2.0e-6f * fabsf(cy);
+            const float x0f = fmaxf(ceilf((cx - hbx) - 0.5f), 0.0f);
+            const float x1f = fminf(floorf((cx + hbx) - 0.5f), F.W - 1.0f);
+            const float y0f = fmaxf(ceilf((cy - hby) - 0.5f), 0.0f);
+            const float y1f = fminf(floorf((cy + hby) - 0.5f), F.H - 1.0f);
+            vis = (x0f <= x1f) && (y0f <= y1f);
+            if (vis) {
+                const int tx0 = (int)x0f / TILE, tx1 = (int)x1f / TILE, ty0 = (int)y0f / TILE, ty1 = (int)y1f / TILE;
+                if (F.row_world > 1) {
+                    bool any = false;
+                    for (int tyy = ty0; tyy <= ty1 && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
+                    vis = any;
+                }
+                if (vis) {
+                    const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
+                    key = __float_as_uint(dx * dx + dy * dy + dz * dz);
+                    tr = pack_trect(tx0, tx1, ty0, ty1);
+                    ++nvis;
+                }
+            }
+        }
+        keys[i] = key;
+        trects[i] = tr;
+        if (bucket_hist) atomicAdd(&sh_hist[depth_bucket(key, db)], 1u);
+    }
+    nvis = __reduce_add_sync(0xffffffffu, nvis);
+    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(n_visible, (unsigned long long)nvis);
+    if (bucket_hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) {
+            const uint32_t c = sh_hist[b];
+            if (c) atomicAdd(bucket_hist + b, c);
+        }
+    }
+}
+
+// Upper bound of the largest eigenvalue of the symmetric 3x3 matrix in sg (the fp32 values the exact kernels use), in
+// double: the trigonometric closed form lambda_max = q + 2 p cos(acos(det((A - qI)/p) / 2) / 3), falling back to
+// q + 2p (cos <= 1) when the argument degenerates; rounded up by 1e-6 relative before the conversion to fp32.
+// Not finite -> +inf (the bounded K1 then keeps the splat on the whole screen; the exact projection decides).
+__device__ __forceinline__ float lambda_max_upper(const Sigma& sg)
+{
+    const double a = sg.s[0], d = sg.s[1], e = sg.s[2], b = sg.s[3], f = sg.s[4], c = sg.s[5];
+    const double q = (a + b + c) / 3.0;
+    const double p1 = d * d + e * e + f * f;
+    const double p2 = (a - q) * (a - q) + (b - q) * (b - q) + (c - q) * (c - q) + 2.0 * p1;
+    double lmax = q;
+    if (p2 > 0.0) {
+        const double p = sqrt(p2 / 6.0);
+        const double ip = 1.0 / p;
+        const double b00 = (a - q) * ip, b11 = (b - q) * ip, b22 = (c - q) * ip, b01 = d * ip, b02 = e * ip, b12 = f * ip;
+        const double det = b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02);
+        double r = 0.5 * det;
+        double cs = 1.0;                                   // cos <= 1: always a valid bound
+        if (r > -1.0 && r < 1.0) cs = cos(acos(r) / 3.0);
+        else if (r <= -1.0) cs = 0.5;                      // phi = pi/3
+        lmax = q + 2.0 * p * cs;
+    }
+    lmax = fabs(lmax) * (1.0 + 1e-6) + 1e-300;
+    const float out = (float)lmax;
+    return (out >= 0.0f && out <= 3.0e38f) ? __fmul_ru(out, 1.0000002f) : __int_as_float(0x7f800000);
+}
+
 // ---- sigma planes: world-space covariance per splat, rebuilt when the object matrix changes
 struct ObjMat { float m[16]; };
 __global__ void __launch_bounds__(256)
 sigma_kernel(const __grid_constant__ ObjMat O, const uint4* __restrict__ geomB, int64_t n,
-             float4* __restrict__ sigA, float2* __restrict__ sigB)
+             float4* __restrict__ sigA, float2* __restrict__ sigB, float* __restrict__ lam)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Sigma sg = sigma_of(O.m, __ldg(geomB + i));
     sigA[i] = make_float4(sg.s[0], sg.s[1], sg.s[2], sg.s[3]);
     sigB[i] = make_float2(sg.s[4], sg.s[5]);
+    lam[i] = lambda_max_upper(sg);
 }
 
 // ---- chunk plan: one CTA of DEPTH_BUCKETS threads
@@ -525,11 +653,25 @@ void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, con
                                      geomA, geomB, rows, has_sh);
 }
 
-void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, cudaStream_t s)
+void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, float* lam, cudaStream_t s)
 {
     if (n <= 0) return;
     ObjMat O; for (int k = 0; k < 16; ++k) O.m[k] = object[k];
-    sigma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, geomB, n, sigA, sigB);
+    sigma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, geomB, n, sigA, sigB, lam);
+}
+
+void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
+                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s)
+{
+    if (n <= 0) return;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_bound_kernel, K1_THREADS, 0);
+        if (rc != cudaSuccess || per_sm < 1) per_sm = 6;
+    }
+    const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
+    project_bound_kernel<<<(unsigned)(want < cap ? want : cap), K1_THREADS, 0, s>>>(fc, ps.geomA, ps.lam, n, keys, trects,
+                                                                                   n_visible, db, bucket_hist);
 }
 
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,

@@ -107,11 +107,12 @@ struct gsb_context {
     bool    stage_timing = false, keep_intermediates = false;
     int     depth_chunks = 0;                                 // 0 = auto
     int     chunk_shift = 0;                                  // first chunk = V / 2^shift; 0 = auto (= depth_chunks)
+    bool    lazy_project = true;                              // bounded K1 (GSB_OPT_LAZY_PROJECT); keep_intermediates forces the exact K1
     bool    host_direct = true;                               // finished tiles go straight to pinned host targets
     int     compact_mode = 0;                                 // 0 = auto (when row-partitioned), 1 = always, 2 = never
 
     // packed render-layout attributes
-    DevBuf geomA, geomB, rows, sigA, sigB;
+    DevBuf geomA, geomB, rows, sigA, sigB, lam;
     bool   sigma_valid = false;                      // sigA/sigB match the packed set and sigma_object
     float  sigma_object[16] = {};
 
@@ -172,6 +173,23 @@ void camera_from_view(const float view[16], float cam[3])
     double det = m[0]*a[0] + m[1]*a[4] + m[2]*a[8] + m[3]*a[12];
     double r = 1.0 / det;
     cam[0] = (float)(a[12] * r); cam[1] = (float)(a[13] * r); cam[2] = (float)(a[14] * r);
+}
+
+// largest eigenvalue of the symmetric 3x3 matrix g (double; closed form, cos <= 1 fallback): |mat3(view)|_2^2 for the
+// bounded K1, rounded up
+double sym3_lambda_max(const double g[3][3])
+{
+    const double a = g[0][0], b = g[1][1], c = g[2][2], d = g[0][1], e = g[0][2], f = g[1][2];
+    const double q = (a + b + c) / 3.0;
+    const double p2 = (a - q) * (a - q) + (b - q) * (b - q) + (c - q) * (c - q) + 2.0 * (d * d + e * e + f * f);
+    if (!(p2 > 0.0)) return q;
+    const double p = std::sqrt(p2 / 6.0), ip = 1.0 / p;
+    const double b00 = (a - q) * ip, b11 = (b - q) * ip, b22 = (c - q) * ip, b01 = d * ip, b02 = e * ip, b12 = f * ip;
+    const double det = b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02);
+    const double r = 0.5 * det;
+    double cs = 1.0;
+    if (r > -1.0 && r < 1.0) cs = std::cos(std::acos(r) / 3.0); else if (r <= -1.0) cs = 0.5;
+    return q + 2.0 * p * cs;
 }
 
 int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
@@ -262,6 +280,7 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
         if (value < 0 || value > 2) return fail(GSB_ERR_INVALID, "GSB_OPT_COMPACT must be 0 (auto), 1 (always) or 2 (never)");
         ctx->compact_mode = (int)value; return GSB_OK;
     case GSB_OPT_HOST_DIRECT: ctx->host_direct = value != 0; return GSB_OK;
+    case GSB_OPT_LAZY_PROJECT: ctx->lazy_project = value != 0; return GSB_OK;
     case GSB_OPT_CHUNK_SHIFT:
         if (value < 0 || value > 16) return fail(GSB_ERR_INVALID, "GSB_OPT_CHUNK_SHIFT must be 0 (auto) .. 16");
         ctx->chunk_shift = (int)value; return GSB_OK;
@@ -613,6 +632,20 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         if (dn == 0.0f && df == 0.0f) df = 1.0f;                            // unset -> glDepthRange default
         fc.depth_hr = (df - dn) * 0.5f; fc.depth_hm = (df + dn) * 0.5f;
     }
+    {   // constants of the covariance chain for the bounded K1: the spec's fp32 operations (project_geom), on the host
+        const float p00 = fr->proj[0], p11 = fr->proj[5];
+        const float aspect = p00 / p11;
+        const float tan_x = 1.0f / p00, tan_y = 1.0f / (p11 * aspect);
+        fc.lim_x = 1.3f * tan_x; fc.lim_y = 1.3f * tan_y;
+        fc.focal = (fc.W * p00) / 2.0f;
+        double g[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            g[i][j] = 0.0;
+            for (int r = 0; r < 3; ++r) g[i][j] += (double)fr->view[i * 4 + r] * (double)fr->view[j * 4 + r];   // (W^T W)_ij
+        }
+        const double wn = sym3_lambda_max(g) * (1.0 + 1e-6);
+        fc.wnorm2 = std::nextafterf((float)wn, INFINITY);
+    }
     const int num_tiles = fc.tiles_x * fc.tiles_y;
     const int64_t n = ctx->splat_count;
     const size_t  N = (size_t)n;
@@ -654,9 +687,14 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     // buffers
     // packed tile rectangles ride along as a payload (screens up to 512 x 512 tiles); otherwise exact rectangles by index
     const bool use_trects = fc.tiles_x <= 512 && fc.tiles_y <= 512;
+    // bounded K1: conservative tile rectangles for every splat, the exact projection only in K2 for the splats a chunk
+    // selects.  The debug views (exact rectangles by splat index) and huge screens keep the exact K1.
+    const bool lazy = ctx->lazy_project && !ctx->keep_intermediates && use_trects &&
+                      std::isfinite(fc.lim_x) && std::isfinite(fc.lim_y) && std::isfinite(fc.focal) && std::isfinite(fc.wnorm2);
     CU(ctx->keys.ensure(N * 4));
     if (use_trects) CU(ctx->trects.ensure(N * 4));
-    CU(ctx->rects.ensure(N * 8)); CU(ctx->counts.ensure(N * 4 + 16));
+    if (!lazy) CU(ctx->rects.ensure(N * 8));
+    CU(ctx->counts.ensure(N * 4 + 16));
     CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N)));
     CU(ctx->scan_scratch.ensure(std::max(scan_scratch_bytes(N), select_scratch_bytes(n))));
     CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
@@ -710,18 +748,21 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
 
     // K1: cull + depth key + tile rectangle for every submitted splat (+ the depth-bucket histogram)
     if (!ctx->sigma_valid || memcmp(ctx->sigma_object, fr->object, 64) != 0) {      // the covariance cache follows the object matrix
-        CU(ctx->sigA.ensure(N * 16)); CU(ctx->sigB.ensure(N * 8));
-        launch_sigma(fr->object, ctx->geomB.as<uint4>(), n, ctx->sigA.as<float4>(), ctx->sigB.as<float2>(), s);
+        CU(ctx->sigA.ensure(N * 16)); CU(ctx->sigB.ensure(N * 8)); CU(ctx->lam.ensure(N * 4));
+        launch_sigma(fr->object, ctx->geomB.as<uint4>(), n, ctx->sigA.as<float4>(), ctx->sigB.as<float2>(), ctx->lam.as<float>(), s);
         memcpy(ctx->sigma_object, fr->object, 64);
         ctx->sigma_valid = true;
         st.launches += 1;
     }
-    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), ctx->sigA.as<float4>(), ctx->sigB.as<float2>() };
+    PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), ctx->sigA.as<float4>(),
+                     ctx->sigB.as<float2>(), ctx->lam.as<float>() };
     uint32_t* bucket_hist = nchunks > 1 ? ctx->bucket_hist.as<uint32_t>() : nullptr;
     if (bucket_hist) CU(cudaMemsetAsync(bucket_hist, 0, DEPTH_BUCKETS * 4, s));
-    launch_project(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->rects.as<uint2>(),
-                   (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects.as<uint32_t>() : nullptr,
-                   cnt + 0, db, bucket_hist, s);
+    if (lazy) launch_project_bound(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->trects.as<uint32_t>(), cnt + 0, db, bucket_hist, s);
+    else launch_project(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->rects.as<uint2>(),
+                        (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects.as<uint32_t>() : nullptr,
+                        cnt + 0, db, bucket_hist, s);
+    const uint2* exact_rects = lazy ? nullptr : ctx->rects.as<uint2>();
     st.launches += 1;
     // The depth order is cut into chunks WITHOUT sorting or moving the cloud: the chunk plan maps every depth bucket to
     // a chunk; each chunk then selects its own live splats with one 4-byte-per-splat scan of the keys.
@@ -774,7 +815,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         }
         // live selection, one pass over the keys: the splats of the chunk that still touch a live tile, compacted in
         // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
-        launch_select_live(pkeys, ptrects, ctx->rects.as<uint2>(), n, chunk_plan, c, fc,
+        launch_select_live(pkeys, ptrects, exact_rects, n, chunk_plan, c, fc,
                            sat, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                            ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
         st.launches += 3;
@@ -786,7 +827,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         // the last chunk that has work, or the last chunk at all, finalises the un-saturated tiles
         const bool last = (c == nchunks - 1) || all_done;
         if (D > 0x3fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^30-1 tile instances in one depth chunk");
-        D_total += D; L_total += L;
+        L_total += L;
         chunks_run = c + 1;
         if (all_done && !first) {                                        // every tile was finalised when it saturated
             if (tm) for (int e = 1; e < 5; ++e) CU(cudaEventRecord(ctx->evc[c][e], s));
@@ -810,6 +851,14 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
         // K4: live-tile counts (K2) -> offsets -> instances -> stable partition by tile -> tile ranges
         exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cnt + 6, s, &st.launches);
+        if (lazy && L) {
+            // the selection counted instances with the bound's rectangles (an upper bound that sized the buffers);
+            // the exact number comes from K2's counts
+            CU(cudaMemcpyAsync(ctx->counters_h + 6, cnt + 6, 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            D = ctx->counters_h[6];
+        }
+        D_total += D;
         launch_emit(ctx->ltiles.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
         st.launches += (L ? 1 : 0);
@@ -978,6 +1027,7 @@ int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, 
     case GSB_DBG_INSTANCES:     src = ctx->dbg_inst.p; need = ctx->keep_intermediates ? d * 4 : 0; break;
     case GSB_DBG_FRAMEBUFFER:   src = ctx->last_fb; need = (uint64_t)ctx->last_w * ctx->last_h * 16; break;
     case GSB_DBG_TILE_CONSUMED: src = ctx->tile_consumed.p; need = t * 4; break;
+    case GSB_DBG_TRECTS:        src = ctx->trects.p; need = (ctx->trects.p && ctx->last_w <= 8192 && ctx->last_h <= 8192) ? n * 4 : 0; break;
     default: return fail(GSB_ERR_INVALID, "gsb_debug_fetch: unknown buffer");
     }
     if (bytes_needed) *bytes_needed = need;

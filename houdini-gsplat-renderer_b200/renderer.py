@@ -19,9 +19,9 @@ LIB_PATH = HERE / "libgsplat_b200.so"
 ID_MAX = 128
 REFERENCE_SPLAT_CAP = 8388607
 
-OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS, OPT_COMPACT, OPT_CHUNK_SHIFT, OPT_HOST_DIRECT = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_SPLAT_CAP, OPT_EPS_T, OPT_STAGE_TIMING, OPT_KEEP_INTERMEDIATES, OPT_DEPTH_CHUNKS, OPT_COMPACT, OPT_CHUNK_SHIFT, OPT_HOST_DIRECT, OPT_LAZY_PROJECT = 1, 2, 3, 4, 5, 6, 7, 8, 9
 (DBG_KEYS_UNSORTED, DBG_ORDER, DBG_RECORDS, DBG_RECTS, DBG_TILE_RANGES, DBG_INSTANCES,
- DBG_FRAMEBUFFER, DBG_KEYS_SORTED, DBG_TILE_CONSUMED) = range(9)
+ DBG_FRAMEBUFFER, DBG_KEYS_SORTED, DBG_TILE_CONSUMED, DBG_TRECTS) = range(10)
 
 RECORD_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("m00", "f4"), ("m01", "f4"),
                          ("m10", "f4"), ("m11", "f4"), ("alpha", "f4"), ("pmax", "f4"),

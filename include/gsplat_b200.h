@@ -103,7 +103,7 @@ typedef struct gsb_target {
 
 typedef struct gsb_stats {
     int64_t n_submitted;     /* N: splats in the packed active set */
-    int64_t n_visible;       /* V: survive cull */
+    int64_t n_visible;       /* V: survive cull; an upper bound with GSB_OPT_LAZY_PROJECT (see there) */
     int64_t n_instances;     /* D: tile instances emitted (summed over depth chunks; saturated tiles receive none) */
     int64_t n_consumed;      /* D_c: instances traversed before every pixel of their tile saturated */
     int32_t rendered;        /* 1 if the last gsb_render drew, 0 if it early-returned like R.C:536-549 */
@@ -138,6 +138,13 @@ enum gsb_option {
                                     (cudaHostAlloc / cudaHostRegister), the blend kernel stores finished tiles straight into it
                                     over PCIe while later depth chunks are still being binned (no separate D2H pass);
                                     pageable memory always takes the staged copy.  0: always cudaMemcpyAsync.  Same bytes */
+    GSB_OPT_LAZY_PROJECT = 9,    /* 1 (default): K1 computes, for every submitted splat, the exact cheap culls, the exact depth key and a
+                                    conservative bound of its tile rectangle (1/5 of the exact kernel's instructions); the exact
+                                    projection runs only in K2 for the splats a depth chunk selects.  Same frame.  gsb_stats then
+                                    reports upper bounds: n_visible = splats that pass the cheap culls with a non-empty bound,
+                                    n_live = splats selected by the bound.  0: exact projection of every splat in K1 (exact
+                                    n_visible / n_live; always used with GSB_OPT_KEEP_INTERMEDIATES and on screens wider than
+                                    8192 px) */
     GSB_OPT_DEPTH_CHUNKS = 5     /* bin+blend in this many front-to-back depth chunks, skipping saturated tiles in later
                                     chunks; 1 = single pass (full tile lists, what the parity tests fetch); 0 = auto */
 };
@@ -154,7 +161,10 @@ enum gsb_debug_buffer {
                                     needs KEEP_INTERMEDIATES) */
     GSB_DBG_FRAMEBUFFER = 6,     /* float[4] x W x H */
     GSB_DBG_KEYS_SORTED = 7,     /* uint32[L]  keys in the order of GSB_DBG_ORDER */
-    GSB_DBG_TILE_CONSUMED = 8    /* uint32 x tiles  instances traversed per tile */
+    GSB_DBG_TILE_CONSUMED = 8,   /* uint32 x tiles  instances traversed per tile */
+    GSB_DBG_TRECTS = 9           /* uint32[N]  K1's packed tile rectangle per splat, tx0:9 | ty0:9 | (tx1-tx0):7 | (ty1-ty0):7
+                                    (extent 127 = "127 or more"), 0xFFFFFFFF = culled: exact, or with GSB_OPT_LAZY_PROJECT the
+                                    conservative bound (a superset of the exact rectangle); screens up to 8192 px */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------- */

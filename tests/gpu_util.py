@@ -27,6 +27,24 @@ def gpu_pipeline(cloud, frame, sh_order, eps_t=1e-5, row_rank=0, row_world=1, ca
                recs=r.fetch(R.DBG_RECORDS), rects=r.fetch(R.DBG_RECTS), ranges=r.fetch(R.DBG_TILE_RANGES),
                inst=r.fetch(R.DBG_INSTANCES), consumed=r.fetch(R.DBG_TILE_CONSUMED),
                fb=r.fetch(R.DBG_FRAMEBUFFER).reshape(frame.height, frame.width, 4))
+    # the production path (GSB_OPT_LAZY_PROJECT: bounded K1, exact projection only for selected splats) must give the
+    # same frame, the same instances and the same consumed counts as the exact-K1 path whose intermediates were fetched
+    r.set_option(R.OPT_KEEP_INTERMEDIATES, 0)
+    r.includeInRenderPass(rid)
+    if explicit_cam is not None:
+        r.setExplicitCameraPos(explicit_cam)
+    r.generateRenderGeometry()
+    host2 = np.full_like(host, -1.0)
+    r.render(frame, host_rgba=host2, row_rank=row_rank, row_world=row_world, row_group=row_group)
+    st2 = r.stats()
+    r.postRender()
+    assert np.array_equal(host2, host), "bounded-K1 frame differs from the exact-K1 frame"
+    assert st2["n_consumed"] == st["n_consumed"], (st2, st)
+    if depth_chunks == 1:                                # (with several chunks the plan, and with it D, follows the histogram)
+        assert st2["n_instances"] == st["n_instances"], (st2, st)
+    assert st2["n_visible"] >= st["n_visible"] and st2["n_live"] >= st["n_live"]
+    out["stats_lazy"] = st2
+    r.set_option(R.OPT_KEEP_INTERMEDIATES, 1)
     if renderer is None:
         r.close()
     return out

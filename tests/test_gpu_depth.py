@@ -52,7 +52,7 @@ def test_depth_occlusion_matches_oracle(oracle, scene, func, chunks):
     assert np.abs(o["rgba"] - plain["rgba"]).max() > 0.05          # the occluder really hides something
     got, st = _gpu(R, cl, fr, sd, func, chunks)
     assert np.abs(got.astype(np.float64) - o["rgba"]).max() <= 2e-5
-    assert st["n_visible"] == o["n_visible"]
+    assert st["n_visible"] >= o["n_visible"]                       # production path: the bounded K1 reports an upper bound
     if chunks == 1:
         assert st["n_instances"] == int(o["tile_start"][-1])
         assert abs(st["n_consumed"] - o["n_consumed"]) <= 0.01 * o["n_consumed"]

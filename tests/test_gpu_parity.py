@@ -308,3 +308,69 @@ def test_wide_splats_use_the_exact_rectangle(oracle, scene):
     r.draw([rid], fr, host_rgba=host)
     assert np.array_equal(host, g["rgba"])
     r.close()
+
+
+def _unpack_trects(t):
+    culled = t == 0xFFFFFFFF
+    tx0 = (t & 511).astype(np.int64); ty0 = ((t >> 9) & 511).astype(np.int64)
+    w = ((t >> 18) & 127).astype(np.int64); h = ((t >> 25) & 127).astype(np.int64)
+    return culled, tx0, ty0, w, h
+
+
+@pytest.mark.parametrize("case", ["cloud", "aniso", "bigsplats", "closeup", "objmat", "8k"])
+def test_bounded_k1_rectangles_contain_the_exact_ones(oracle, scene, case):
+    """GSB_OPT_LAZY_PROJECT: for every splat the exact projection keeps, the bounded K1 keeps it too and its tile
+    rectangle contains the exact one (otherwise a chunk could fail to select a splat that changes a pixel).  Checked
+    on a million splats per case, including strongly anisotropic, huge, close-up and object-transformed ones, and
+    the depth keys of the kept splats are the exact keys."""
+    from houdini_gsplat_renderer_b200 import renderer as R
+    O, S = oracle, scene
+    rng = np.random.default_rng(77)
+    n, w, h, theta, mult = 1_000_000, 1920, 1080, 40.0, 1.0
+    if case == "8k":
+        w, h = 7680, 4320
+    if case == "bigsplats":
+        n, mult = 20_000, 40.0                                               # screen-filling splats (D stays bounded)
+    if case == "closeup":
+        n, mult, theta = 50_000, 6.0, 0.0
+    if case == "aniso":
+        n = 100_000
+    cl = S.make_cloud(n, 4321, sh=False, scale_mult=mult)
+    if case == "aniso":                                                      # needles and flakes with |q| != 1
+        sc = cl.scale_h.astype(np.float32); sc[:, 0] *= 30.0; sc[:, 2] *= 0.05; cl.scale_h = sc.astype(np.float16)
+        cl.orient_h[:] = (cl.orient_h.astype(np.float32) * rng.uniform(0.8, 1.25, (cl.n, 1))).astype(np.float16)
+    if case == "closeup":
+        cl.pos[:, 2] = cl.pos[:, 2] * np.float32(0.2) + np.float32(2.6)      # a slab right in front of the camera
+    fr = S.orbit_frame(w, h, theta)
+    if case == "objmat":                                                     # non-rigid object matrix
+        a = 0.7; obj = np.eye(4)
+        obj[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) @ np.diag([1.7, 0.6, 1.1])
+        obj[:3, 3] = [0.1, 0.05, -0.1]
+        fr = S.Frame(w, h, fr.view, fr.proj, S.colmajor(obj), S.colmajor(np.linalg.inv(obj)))
+    r = R.GSplatRenderer(0)
+    r.set_option(R.OPT_SPLAT_CAP, 0); r.set_option(R.OPT_DEPTH_CHUNKS, 1)
+    rid = r.registerUpdate(0x51, (1, 0, 0, 0), 0, cl)
+    r.set_option(R.OPT_KEEP_INTERMEDIATES, 1)                                # exact K1
+    r.draw([rid], fr)
+    exact = r.fetch(R.DBG_RECTS); keys_exact = r.fetch(R.DBG_KEYS_UNSORTED); fb_exact = r.fetch(R.DBG_FRAMEBUFFER)
+    r.set_option(R.OPT_KEEP_INTERMEDIATES, 0)                                # bounded K1
+    r.draw([rid], fr)
+    bound = r.fetch(R.DBG_TRECTS); keys_bound = r.fetch(R.DBG_KEYS_UNSORTED); fb_bound = r.fetch(R.DBG_FRAMEBUFFER)
+    assert np.array_equal(fb_exact, fb_bound)
+    vis = exact["x0"] <= exact["x1"]
+    assert vis.sum() > 0.2 * n
+    culled, tx0, ty0, bw, bh = _unpack_trects(bound)
+    assert not culled[vis].any(), f"{int(culled[vis].sum())} visible splats dropped by the bound"
+    assert np.array_equal(keys_bound[vis], keys_exact[vis])
+    assert np.all(keys_bound[culled] == 0xFFFFFFFF)
+    ex0 = exact["x0"][vis].astype(np.int64) // 16; ex1 = exact["x1"][vis].astype(np.int64) // 16
+    ey0 = exact["y0"][vis].astype(np.int64) // 16; ey1 = exact["y1"][vis].astype(np.int64) // 16
+    bx0, by0, bw, bh = tx0[vis], ty0[vis], bw[vis], bh[vis]
+    assert np.all(bx0 <= ex0) and np.all(by0 <= ey0)
+    assert np.all((bx0 + bw >= ex1) | (bw == 127)) and np.all((by0 + bh >= ey1) | (bh == 127))
+    # the bound is not vacuous: on the plain cloud it keeps well under twice the tiles the exact rectangles touch
+    if case == "cloud":
+        t_exact = ((ex1 - ex0 + 1) * (ey1 - ey0 + 1)).sum()
+        t_bound = ((bw + 1) * (bh + 1)).sum()
+        assert t_bound < 2.0 * t_exact, (t_bound, t_exact)
+    r.close()
