@@ -61,18 +61,18 @@ struct PackedSplats {
     const float*  lam;
 };
 
-// Depth buckets: a monotone (non-decreasing) map from the depth key to [0, DEPTH_BUCKETS-2], linear in the distance;
-// culled splats (KEY_CULLED) take the last bucket.  Used to cut the depth order into chunks without sorting or moving
-// the cloud: every step (sqrt, subtract, scale, clamp, truncate) is monotone in fp32, so bucket boundaries are key boundaries.
+// Depth buckets: a monotone (non-decreasing) map from the depth key to [0, DEPTH_BUCKETS-2]: the key's offset from the
+// smallest possible key of the packed set, shifted so the whole key range spans the buckets; culled splats (KEY_CULLED)
+// take the last bucket.  Used to cut the depth order into chunks without sorting or moving the cloud: the chunk plan
+// only needs counts per bucket (quantiles), so any monotone map works, and this one is two integer instructions.
 constexpr int DEPTH_BUCKETS = 512;
 constexpr int MAX_CHUNKS    = 16;
-struct DepthBuckets { float dmin, scale; };
+struct DepthBuckets { uint32_t key_min; int shift; };
 __device__ __forceinline__ uint32_t depth_bucket(uint32_t key, DepthBuckets db)
 {
     if (key == KEY_CULLED) return (uint32_t)(DEPTH_BUCKETS - 1);
-    float t = (sqrtf(__uint_as_float(key)) - db.dmin) * db.scale;
-    t = fminf(fmaxf(t, 0.0f), (float)(DEPTH_BUCKETS - 2));
-    return (uint32_t)t;
+    const uint32_t o = key > db.key_min ? key - db.key_min : 0u;
+    return min(o >> db.shift, (uint32_t)(DEPTH_BUCKETS - 2));
 }
 // Chunk plan chosen on the device from the bucket histogram (choose_chunks).
 struct ChunkPlan {

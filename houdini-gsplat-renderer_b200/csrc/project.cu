@@ -432,31 +432,35 @@ project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __rest
         const float cw = clip[3];
         vis = vis && (cw > 0.0f) && (clip[2] >= -cw && clip[2] <= cw);
         if (vis) {
+            // (from here on nothing has to match the exact chain bit for bit: fused multiply-adds, MUFU approximations)
             const float iw = __fdividef(1.0f, cw);
-            const float cx = (clip[0] * iw + 1.0f) * 0.5f * F.W;
-            const float cy = ((-clip[1]) * iw + 1.0f) * 0.5f * F.H;
+            const float hw = 0.5f * F.W, hh = 0.5f * F.H;
+            const float cx = fmaf(clip[0] * iw, hw, hw);
+            const float cy = fmaf((-clip[1]) * iw, hh, hh);
             float t[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
-                t[r] = ((MAT(F.view, r, 0) * psx[0] + MAT(F.view, r, 1) * psx[1]) + MAT(F.view, r, 2) * psx[2]) + MAT(F.view, r, 3);
+                t[r] = fmaf(MAT(F.view, r, 0), psx[0], fmaf(MAT(F.view, r, 1), psx[1], fmaf(MAT(F.view, r, 2), psx[2], MAT(F.view, r, 3))));
             const float itz = __fdividef(1.0f, t[2]);
             const float rx = fminf(fmaxf(t[0] * itz, -F.lim_x), F.lim_x) * 1.0001f;
             const float ry = fminf(fmaxf(t[1] * itz, -F.lim_y), F.lim_y) * 1.0001f;
             const float j0 = F.focal * itz;
-            const float nj2 = (j0 * j0) * ((1.0f + rx * rx) + ry * ry);
-            const float l1 = ((nj2 * F.wnorm2) * lm + 0.3f) * 1.002f;         // >= lambda_1 of the exact chain
+            const float nj2 = (j0 * j0) * fmaf(ry, ry, fmaf(rx, rx, 1.0f));
+            const float l1 = fmaf((nj2 * F.wnorm2) * 1.002f, lm, 0.3006f);       // >= lambda_1 of the exact chain
             float s1; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(2.0f * l1));
             s1 = fminf(s1 * 1.0005f, 4096.0f);
             float hb = (fminf(rr, 2.8284272f) * s1) * 1.001f + 0.06f;
             if (!(hb <= 1.0e9f)) hb = 1.0e9f;                                   // inf / NaN bound: the whole screen
-            const float hbx = hb + 2.0e-6f * fabsf(cx), hby = hb + 2.0e-6f * fabsf(cy);
+            const float hbx = fmaf(2.0e-6f, fabsf(cx), hb), hby = fmaf(2.0e-6f, fabsf(cy), hb);
             const float x0f = fmaxf(ceilf((cx - hbx) - 0.5f), 0.0f);
             const float x1f = fminf(floorf((cx + hbx) - 0.5f), F.W - 1.0f);
             const float y0f = fmaxf(ceilf((cy - hby) - 0.5f), 0.0f);
             const float y1f = fminf(floorf((cy + hby) - 0.5f), F.H - 1.0f);
             vis = (x0f <= x1f) && (y0f <= y1f);
             if (vis) {
-                const int tx0 = (int)x0f / TILE, tx1 = (int)x1f / TILE, ty0 = (int)y0f / TILE, ty1 = (int)y1f / TILE;
+                static_assert(TILE == 16, "tile shift");
+                const int tx0 = (int)((unsigned)x0f >> 4), tx1 = (int)((unsigned)x1f >> 4);       // 0 <= x <= 65535
+                const int ty0 = (int)((unsigned)y0f >> 4), ty1 = (int)((unsigned)y1f >> 4);
                 if (F.row_world > 1) {
                     bool any = false;
                     for (int tyy = ty0; tyy <= ty1 && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);

@@ -662,7 +662,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     // (25 instead of 32 for the benchmark cloud => 3 passes instead of 4) and gives the identical order.  The same
     // bound makes the depth buckets (chunk partition) linear in the distance over [dmin, dmax].
     uint32_t key_min = 0u, key_span = 0xFFFFFFFFu;
-    DepthBuckets db{ 0.0f, 0.0f };
+    DepthBuckets db{ 0u, 0 };
     bool range_ok = false;
     if (ctx->bbox_valid) {
         double dmin2 = 0.0, dmax2 = 0.0;
@@ -677,8 +677,10 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         if (std::isfinite(fmin) && std::isfinite(fmax) && fmin >= 0.0f && fmax >= fmin) {
             uint32_t bmin, bmax; memcpy(&bmin, &fmin, 4); memcpy(&bmax, &fmax, 4);
             key_min = bmin; key_span = bmax - bmin + 1u;      // valid keys squeeze to [0, span-1], culled to span
-            const float d0 = std::sqrt(fmin), d1 = std::sqrt(fmax);
-            if (d1 > d0) { db.dmin = d0; db.scale = (float)(DEPTH_BUCKETS - 1) / (d1 - d0); range_ok = std::isfinite(db.scale); }
+            // buckets: (key - key_min) >> shift, the shift that maps the span onto [0, DEPTH_BUCKETS - 2]
+            db.key_min = bmin; db.shift = 0;
+            while (((key_span - 1u) >> db.shift) > (uint32_t)(DEPTH_BUCKETS - 2)) ++db.shift;
+            range_ok = key_span > 1u;
         }
     }
     if (!range_ok) nchunks = 1;                               // no finite depth range: a single chunk needs no buckets
