@@ -110,14 +110,18 @@ void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4*
 // *n_visible += V, and (bucket_hist != NULL) the DEPTH_BUCKETS-bin histogram of depth_bucket(key).
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
-                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
+                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
+                    cudaStream_t s);
+// owned_rows (every K1/K2 launcher): NULL for a whole frame; for a row-partitioned frame owned_rows[y] = number of tile
+// rows < y this rank owns (tiles_y + 1 entries), so the ownership cull is two look-ups.
 // Bounded K1 (every submitted splat, GSB_OPT_LAZY_PROJECT): the cheap exact culls (alpha, clip.w, clip.z), the exact
 // depth key, and a CONSERVATIVE packed tile rectangle — a superset of the exact one, from the centre and the bound
 // h <= min(rr, 2 sqrt 2) * sqrt(2 (|J|^2 |W|^2 lambda_max(Sigma) + 0.3)) on the quad's half extent — in ~1/5 of the exact
 // kernel's instructions and half its bytes (20 B read per splat).  Splats the bound keeps but the exact projection (K2)
 // culls get no instances.  *n_visible += splats that pass the cheap culls with a non-empty bound (an upper bound of V).
 void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
-                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s);
+                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
+                          cudaStream_t s);
 // chunk plan from the bucket histogram: chunk c (< nchunks - 1) ends at the first bucket whose exclusive count reaches
 // V * (2^(c+1) - 1) / 2^shift (the first chunk holds V / 2^shift splats, every further one doubles; the last takes the rest)
 // and the bucket boundaries are turned into key boundaries (plan->key_lo: the smallest key whose bucket belongs to the
@@ -127,7 +131,8 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
 // evaluate SH, write the 48-byte record of live rank j to recs[j], its tile rectangle (tx0 | tx1 << 16, ty0 | ty1 << 16)
 // to tile_rects[j] and the number of live tiles it touches to counts[j] (sat: launch_live_sat, NULL = every tile live)
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth, cudaStream_t s);
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
+                    const uint32_t* owned_rows, cudaStream_t s);
 // zdepth (may be NULL): window depth of live rank j (scene-depth occlusion)
 
 // binning.cu

@@ -166,8 +166,10 @@ __device__ __forceinline__ Sigma sigma_of(const float* __restrict__ object, cons
 }
 
 // rr = sqrt(pmax) (or negative: never passes the discard, see rr_of_alpha)
+// owned_rows (row-partitioned frames only, else NULL): owned_rows[y] = tile rows < y this rank owns, so "does the
+// rectangle touch an owned row" is two look-ups instead of a loop of integer divisions
 __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p[3], const float rr,
-                                             const Sigma& sig, Geom& g)
+                                             const Sigma& sig, Geom& g, const uint32_t* __restrict__ owned_rows)
 {
     if (!(rr >= 0.0f)) return false;             // alpha < 1/255
 #pragma unroll
@@ -253,10 +255,8 @@ __device__ __forceinline__ bool project_geom(const FrameConsts& F, const float p
     const float y1f = fminf(floorf((cy + hy) - 0.5f), F.H - 1.0f);
     if (!(x0f <= x1f) || !(y0f <= y1f)) return false;
     g.x0 = (int)x0f; g.x1 = (int)x1f; g.y0 = (int)y0f; g.y1 = (int)y1f;
-    if (F.row_world > 1) {
-        bool any = false;
-        for (int tyy = g.y0 / TILE; tyy <= g.y1 / TILE && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
-        if (!any) return false;
+    if (owned_rows) {
+        if (__ldg(owned_rows + g.y1 / TILE + 1) == __ldg(owned_rows + g.y0 / TILE)) return false;
     }
     g.cx = cx; g.cy = cy; g.clipz = clip[2]; g.clipw = cw;
     g.m00 = ex / s1; g.m01 = ey / s1;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(K1_THREADS, MIN_CTAS)
 project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA,
                const float4* __restrict__ sigA, const float2* __restrict__ sigB, int64_t n, uint32_t* __restrict__ keys, uint2* __restrict__ rects,
                const int rects_all, uint32_t* __restrict__ trects, unsigned long long* __restrict__ n_visible,
-               const DepthBuckets db, uint32_t* __restrict__ bucket_hist)
+               const DepthBuckets db, uint32_t* __restrict__ bucket_hist, const uint32_t* __restrict__ owned_rows)
 {
     __shared__ uint32_t sh_hist[DEPTH_BUCKETS];
     if (bucket_hist) {
@@ -356,7 +356,7 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
         const float p[3] = { ga.x, ga.y, ga.z };
         const Sigma sig{ { sa.x, sa.y, sa.z, sa.w, sb.x, sb.y } };
         Geom g;
-        const bool vis = project_geom(F, p, ga.w, sig, g);
+        const bool vis = project_geom(F, p, ga.w, sig, g, owned_rows);
         uint32_t key = KEY_CULLED, tr = TRECT_CULLED;
         uint2 rect = make_uint2(1u, 1u);                     // x0=1,x1=0,y0=1,y1=0 : empty
         bool wide = false;
@@ -398,7 +398,8 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
 __global__ void __launch_bounds__(K1_THREADS, 6)
 project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA, const float* __restrict__ lam,
                      int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ trects,
-                     unsigned long long* __restrict__ n_visible, const DepthBuckets db, uint32_t* __restrict__ bucket_hist)
+                     unsigned long long* __restrict__ n_visible, const DepthBuckets db, uint32_t* __restrict__ bucket_hist,
+                     const uint32_t* __restrict__ owned_rows)
 {
     __shared__ uint32_t sh_hist[DEPTH_BUCKETS];
     if (bucket_hist) {
@@ -461,11 +462,7 @@ project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __rest
                 static_assert(TILE == 16, "tile shift");
                 const int tx0 = (int)((unsigned)x0f >> 4), tx1 = (int)((unsigned)x1f >> 4);       // 0 <= x <= 65535
                 const int ty0 = (int)((unsigned)y0f >> 4), ty1 = (int)((unsigned)y1f >> 4);
-                if (F.row_world > 1) {
-                    bool any = false;
-                    for (int tyy = ty0; tyy <= ty1 && !any; ++tyy) any = owns_row(tyy, F.row_rank, F.row_world, F.row_group);
-                    vis = any;
-                }
+                if (owned_rows) vis = __ldg(owned_rows + ty1 + 1) != __ldg(owned_rows + ty0);
                 if (vis) {
                     const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
                     key = __float_as_uint(dx * dx + dy * dy + dz * dz);
@@ -597,7 +594,7 @@ __global__ void __launch_bounds__(K2_THREADS)
 records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
                const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
                Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts,
-               float* __restrict__ zdepth)
+               float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows)
 {
     __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
     constexpr int NCH = 2 + (ORDER == 0 ? 1 : (ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6)));     // chunks of the line this order reads
@@ -622,7 +619,7 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     Geom g;
     float4* out = reinterpret_cast<float4*>(recs + j);
     const float pmax = pmax_of_alpha(alpha);
-    if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g)) {  // cannot happen (K1 kept it)
+    if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g, owned_rows)) {  // cannot happen (K1 kept it)
         out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
         out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         tile_rects[j] = make_uint2(1u, 1u); counts[j] = 0u;
@@ -665,7 +662,8 @@ void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4*
 }
 
 void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
-                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s)
+                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
+                          cudaStream_t s)
 {
     if (n <= 0) return;
     static int per_sm = 0;
@@ -675,12 +673,13 @@ void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t
     }
     const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
     project_bound_kernel<<<(unsigned)(want < cap ? want : cap), K1_THREADS, 0, s>>>(fc, ps.geomA, ps.lam, n, keys, trects,
-                                                                                   n_visible, db, bucket_hist);
+                                                                                   n_visible, db, bucket_hist, owned_rows);
 }
 
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
-                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, cudaStream_t s)
+                    unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
+                    cudaStream_t s)
 {
     if (n <= 0) return;
     // resident CTAs per SM: 4 (54 registers), 5 (48) or 6 (40, a few spill bytes); GSB_K1_OCC overrides for experiments
@@ -698,7 +697,7 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
     const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
 #define GSB_K1(M) project_kernel<M><<<grid, K1_THREADS, 0, s>>>(fc, ps.geomA, ps.sigA, ps.sigB, n, keys, rects, rects_all, trects, \
-                                                                n_visible, db, bucket_hist)
+                                                                n_visible, db, bucket_hist, owned_rows)
     if (occ == 4) GSB_K1(4); else if (occ == 5) GSB_K1(5); else GSB_K1(6);
 #undef GSB_K1
 }
@@ -709,15 +708,16 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth, cudaStream_t s)
+                    const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
+                    const uint32_t* owned_rows, cudaStream_t s)
 {
     if (n_live <= 0) return;
     const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
     switch (fc.sh_order) {
-    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
-    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
-    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
-    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth); break;
+    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
     }
 }
 

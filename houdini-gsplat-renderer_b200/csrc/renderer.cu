@@ -119,7 +119,7 @@ struct gsb_context {
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
     // lkeys/lvals: the live splats of the current chunk (ping-pong of their depth sort); ltiles: their tile rectangles (K2).
     DevBuf keys, trects, lkeys[2], lvals[2], ltiles, recs, rects, counts, ikeys[2], ivals[2],
-           ranges, tile_consumed, tile_done, live_sat, fb, plan, bucket_hist;
+           ranges, tile_consumed, tile_done, live_sat, owned_rows, fb, plan, bucket_hist;
     DevBuf zdepth, scene_depth_buf;                  // scene-depth occlusion: window depth per live rank; GL depth copy
     struct cudaGraphicsResource* gl_depth_res = nullptr; uint32_t gl_depth_tex = 0; int gl_depth_w = 0, gl_depth_h = 0;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
@@ -756,14 +756,25 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         ctx->sigma_valid = true;
         st.launches += 1;
     }
+    // row-partitioned frame: prefix count of the tile rows this rank owns (the ownership cull of K1 / K2)
+    const uint32_t* owned_rows = nullptr;
+    if (fr->row_world > 1) {
+        std::vector<uint32_t> pre((size_t)fc.tiles_y + 1, 0u);
+        for (int ty = 0; ty < fc.tiles_y; ++ty) pre[ty + 1] = pre[ty] + (owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1u : 0u);
+        CU(ctx->owned_rows.ensure(pre.size() * 4));
+        CU(cudaMemcpyAsync(ctx->owned_rows.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));                   // pre is a local: the copy must have left it
+        owned_rows = ctx->owned_rows.as<uint32_t>();
+    }
     PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), ctx->sigA.as<float4>(),
                      ctx->sigB.as<float2>(), ctx->lam.as<float>() };
     uint32_t* bucket_hist = nchunks > 1 ? ctx->bucket_hist.as<uint32_t>() : nullptr;
     if (bucket_hist) CU(cudaMemsetAsync(bucket_hist, 0, DEPTH_BUCKETS * 4, s));
-    if (lazy) launch_project_bound(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->trects.as<uint32_t>(), cnt + 0, db, bucket_hist, s);
+    if (lazy) launch_project_bound(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->trects.as<uint32_t>(), cnt + 0, db, bucket_hist,
+                                   owned_rows, s);
     else launch_project(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->rects.as<uint2>(),
                         (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects.as<uint32_t>() : nullptr,
-                        cnt + 0, db, bucket_hist, s);
+                        cnt + 0, db, bucket_hist, owned_rows, s);
     const uint2* exact_rects = lazy ? nullptr : ctx->rects.as<uint2>();
     st.launches += 1;
     // The depth order is cut into chunks WITHOUT sorting or moving the cloud: the chunk plan maps every depth bucket to
@@ -792,9 +803,9 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     if (fr->row_world > 1 && fb_final == fb) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));   // rows this rank does not own stay zero
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
     // tiles this rank owns: when all of them are saturated no deeper splat can change a pixel and the frame is done
-    int owned_rows = 0;
-    for (int ty = 0; ty < fc.tiles_y; ++ty) owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
-    const uint64_t owned_tiles = (uint64_t)owned_rows * (uint64_t)fc.tiles_x;
+    int n_owned_rows = 0;
+    for (int ty = 0; ty < fc.tiles_y; ++ty) n_owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
+    const uint64_t owned_tiles = (uint64_t)n_owned_rows * (uint64_t)fc.tiles_x;
     uint64_t D_total = 0, L_total = 0, V = 0, D = 0, L = 0;
     int chunks_run = 0;
     // upper bound of a chunk's live splats: the visible splats of the chunk (all of them for the first chunk); the
@@ -848,7 +859,7 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
         const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
-        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, s);
+        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
         // K4: live-tile counts (K2) -> offsets -> instances -> stable partition by tile -> tile ranges
