@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-A step = one full frame of the hot path (cull + key + tile rectangle for every splat -> per depth chunk: live-splat
-selection, depth sort, records + SH, tile binning, blend) over
+A step = one full frame of the hot path (cull + key + bounded tile rectangle for every splat -> per depth chunk:
+live-splat selection, depth sort, exact projection + records + SH, tile binning, blend) over
 the synthetic cloud of SURVEY.md §8d.  Default workload: the north-star target, 20 M splats, SH degree 3,
 1920x1080, one B200 (fits one GPU: 2.6 GB of attributes).  Prints ONE JSON line (rank 0).
 
@@ -339,8 +339,9 @@ def run_ours(args):
     Nw = N * world
     chunks = max(1.0, cnt["depth_chunks"] / K / world)
     stage_bytes = {
-        # K1: cull-phase read (SURVEY: 30 B per submitted splat) + (key, packed tile rectangle) written for every splat
-        "project": Nw * 30 + Nw * 8,
+        # K1 (bounded, the library default): position + discard radius (16 B) + covariance eigenvalue bound (4 B) read,
+        # (key, packed tile rectangle) written, for every submitted splat.  (SURVEY's unit for an exact cull phase is 30 B.)
+        "project": Nw * 20 + Nw * 8,
         # per depth chunk: live selection streams key + tile rectangle of every splat (8 B) and writes/reads one ballot bit
         # per splat; the L selected (key, index, rect) triples are gathered (8 B) and written (12 B), then LSD-sorted
         # (histogram read + passes x 24 B)
