@@ -100,3 +100,45 @@ def test_ingested_prim_renders_like_a_registered_one(scene):
     f2 = np.zeros_like(f1); r.draw([rid], fr, host_rgba=f2)
     assert f1[..., 3].max() > 0.3 and np.array_equal(f1, f2)
     r.close()
+
+
+def test_config1_simple_scene_cook(oracle, scene):
+    """BASELINE config 1 (hip/GSplatPlugin_simpleScene_v001.hip: GSplatSOP builds prims from 10 k synthetic points, no
+    render), SURVEY.md §8d: the 10 000-point seed-1001 SH-3 cloud -> HDK-free model of cookMySop/build (one prim, vertex i
+    <-> point i, barycentre = sequential fp32 sum / N, GEO_GSplat.C:338-351,413-431) -> update()-equivalent extraction
+    on the GPU (fp16 quantisation, GR_GSplat.C:302-372) -> registry.  Vertex wiring, barycentre bits and every
+    quantised array equal the oracle's; the cook is timed (reported, no roofline claim)."""
+    import time
+    from houdini_gsplat_renderer_b200 import renderer as R
+    O, S = oracle, scene
+    w = S.WORKLOADS["10k_sh3_cook"]
+    cl = S.make_cloud(w["n"], w["seed"], sh=True)
+    n = cl.n
+    assert n == 10_000
+    v2p, bary, bbox = O.build_prim(cl.pos)                      # cookMySop / GEO_PrimGsplat::build model
+    assert np.array_equal(v2p, np.arange(n, dtype=np.int32))
+    assert np.array_equal(bbox, np.r_[cl.pos.min(axis=0), cl.pos.max(axis=0)].astype(np.float32))
+    f32 = np.float32
+    sh = np.stack([cl.shx_h[:, :15].astype(f32), cl.shy_h[:, :15].astype(f32), cl.shz_h[:, :15].astype(f32)], axis=2)
+    a = {"P": cl.pos, "Cd": cl.cd_h.astype(f32), "opacity": cl.alpha, "scale": cl.scale_h.astype(f32),
+         "orient": cl.orient_h.astype(f32), "sh_coefficients": np.ascontiguousarray(sh)}
+    ref = I.update(a)
+    r = R.GSplatRenderer(0)
+    r.update(0xC1, (1, 0, 0, 0), 0, a)                            # warm-up (allocations)
+    t0 = time.perf_counter()
+    res = r.update(0xC1, (2, 0, 0, 0), 0, a)                      # a new version evicts the old entry (R.C:246-265)
+    dt = time.perf_counter() - t0
+    assert r.registry_size() == 1
+    assert res["sh_data_found"] and res["sh_order"] == 3 and not res["sh_order_invalid"]
+    assert np.array_equal(res["barycentre"], bary) and np.array_equal(ref["barycentre"], bary)
+    rid = res["id"]
+    assert np.array_equal(r.fetch_entry(rid, 0).reshape(n, 3), cl.pos)
+    assert np.array_equal(r.fetch_entry(rid, 1).reshape(n, 3), cl.cd_h.view(np.uint16))
+    assert np.array_equal(r.fetch_entry(rid, 2), cl.alpha)
+    assert np.array_equal(r.fetch_entry(rid, 3).reshape(n, 3), cl.scale_h.view(np.uint16))
+    assert np.array_equal(r.fetch_entry(rid, 4).reshape(n, 4), cl.orient_h.view(np.uint16))
+    for which, arr in ((5, cl.shx_h), (6, cl.shy_h), (7, cl.shz_h)):
+        got = r.fetch_entry(rid, which).reshape(n, 16)
+        assert np.array_equal(got[:, :15], arr.view(np.uint16)[:, :15])
+    print(f"config 1: cook of {n} points (H2D of raw fp32 attributes + GPU quantisation + registry) {dt * 1e6:.0f} us")
+    r.close()
