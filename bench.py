@@ -393,6 +393,8 @@ def run_ours(args):
                      "formula": "D_c*(4+48) + W*H*16"},
         "stages": stages,
         "counters_per_frame": {"N": N, "V": V, "L": L, "D": D, "D_c": Dc},
+        "counters_note": "bounded K1 (library default): V = splats that pass the cheap culls with a non-empty rectangle bound and "
+                         "L = splats the depth chunks selected are upper bounds of the exact counts; D and D_c are exact",
         "clocks": clocks,
         "combine": (args.combine if world > 1 else None), "verify": verify,
         "scene_gen_s": gen_s,
@@ -401,7 +403,7 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as O
         cores = O.num_threads()
-        n_sample = min(N, 2_000_000)
+        n_sample = min(N, 20_000_000)      # the whole frame for every BASELINE config: ~5 s on 16 host cores at 20 M
         t, st, ns = cpu_frame(O, S, w, cloud, n_sample)
         line["cpu_baseline"] = {
             "value": ns / t / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
