@@ -451,28 +451,52 @@ void orc_window_depth(const orc_frame* F, int64_t n, const float* pos, const flo
 int64_t orc_bin(const orc_frame* F, int64_t n, const int32_t* order, const uint8_t* vis,
                 const orc_rect* rects, int64_t* tile_start, int32_t* inst)
 {
+    /* parallel stable counting sort: the depth order is cut into one contiguous range per thread; per-thread tile
+     * counts, then for every tile the exclusive prefix over threads gives each thread its write cursor, so every
+     * tile's list keeps the global depth order.  Same output as the obvious serial loop. */
     const int TX = (F->width + ORC_TILE - 1) / ORC_TILE, TY = (F->height + ORC_TILE - 1) / ORC_TILE;
     const int64_t NT = (int64_t)TX * TY;
-    std::vector<int64_t> cnt((size_t)NT + 1, 0);
-    for (int64_t r = 0; r < n; ++r) {
-        int32_t i = order[r]; if (!vis[i]) continue;
-        const orc_rect& q = rects[i];
-        for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
-            if (!orc_owns_row(F, ty)) continue;
-            for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) cnt[(size_t)ty * TX + tx] += 1;
+    int T = omp_get_max_threads();
+    if (T < 1) T = 1;
+    if ((int64_t)T * NT > (int64_t)64 << 20) T = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / NT);   /* bound the table */
+    std::vector<int64_t> cnt((size_t)T * (size_t)NT, 0);
+    auto range = [&](int t, int64_t& r0, int64_t& r1) { r0 = n * t / T; r1 = n * (t + 1) / T; };
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        int64_t r0, r1; range(t, r0, r1);
+        int64_t* c = cnt.data() + (size_t)t * (size_t)NT;
+        for (int64_t r = r0; r < r1; ++r) {
+            int32_t i = order[r]; if (!vis[i]) continue;
+            const orc_rect& q = rects[i];
+            for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
+                if (!orc_owns_row(F, ty)) continue;
+                for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) c[(size_t)ty * TX + tx] += 1;
+            }
         }
     }
+    /* tile totals -> tile_start; per-thread counts -> per-thread cursors (in place) */
     int64_t acc = 0;
-    for (int64_t t = 0; t < NT; ++t) { tile_start[t] = acc; acc += cnt[(size_t)t]; }
+    for (int64_t tile = 0; tile < NT; ++tile) {
+        tile_start[tile] = acc;
+        for (int t = 0; t < T; ++t) {
+            int64_t c = cnt[(size_t)t * (size_t)NT + (size_t)tile];
+            cnt[(size_t)t * (size_t)NT + (size_t)tile] = acc;
+            acc += c;
+        }
+    }
     tile_start[NT] = acc;
     if (!inst) return acc;
-    std::vector<int64_t> cur(tile_start, tile_start + NT);
-    for (int64_t r = 0; r < n; ++r) {
-        int32_t i = order[r]; if (!vis[i]) continue;
-        const orc_rect& q = rects[i];
-        for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
-            if (!orc_owns_row(F, ty)) continue;
-            for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) inst[cur[(size_t)ty * TX + tx]++] = i;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        int64_t r0, r1; range(t, r0, r1);
+        int64_t* cur = cnt.data() + (size_t)t * (size_t)NT;
+        for (int64_t r = r0; r < r1; ++r) {
+            int32_t i = order[r]; if (!vis[i]) continue;
+            const orc_rect& q = rects[i];
+            for (int ty = q.y0 / ORC_TILE; ty <= q.y1 / ORC_TILE; ++ty) {
+                if (!orc_owns_row(F, ty)) continue;
+                for (int tx = q.x0 / ORC_TILE; tx <= q.x1 / ORC_TILE; ++tx) inst[cur[(size_t)ty * TX + tx]++] = i;
+            }
         }
     }
     return acc;
