@@ -4,6 +4,7 @@ The reference draws its quads with the depth test on and depth writes off (src/G
 all vertices of a quad the centre's clip z and w (shaders/GSplatShaderSource.h:278-282): one window depth per splat,
 tested per fragment against the scene depth already in the viewport."""
 import numpy as np
+import pytest
 
 from test_oracle_kat import frame, one
 
@@ -84,3 +85,35 @@ def test_occluder_between_two_layers(oracle, scene):
     ref = O.pipeline(Fn, near_only)["rgba"]
     assert np.array_equal(got, ref)
     assert got[..., 1].max() == 0.0 and got[..., 0].max() > 0.3
+
+
+@pytest.mark.parametrize("objmat", [False, True])
+def test_window_depth_matches_the_literal_vertex_shader(oracle, scene, objmat):
+    """The literal emulation of the reference's vertex shader (oracle/glsl_literal.py, SRC.h:190-288) gives all four
+    corners of a quad the SAME gl_Position.z / gl_Position.w, and that ratio, mapped through glDepthRange, is the oracle's
+    window depth: the "one depth per splat" the occlusion test relies on."""
+    from oracle import glsl_literal as L
+    O, S = oracle, scene
+    cl = S.make_cloud(400, 23, sh=True, scale_mult=3.0)
+    fr = S.orbit_frame(320, 180, 57.0)
+    if objmat:
+        a = 0.4; obj = np.eye(4)
+        obj[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) @ np.diag([1.2, 0.8, 1.1])
+        obj[:3, 3] = [0.05, -0.02, 0.1]
+        fr = S.Frame(320, 180, fr.view, fr.proj, S.colmajor(obj), S.colmajor(np.linalg.inv(obj)))
+    cam = O.camera_from_view(fr.view); origin = cl.barycentre()
+    F = O.make_frame(fr, cam, origin, 3)
+    zw = O.window_depth(F, cl, (0.0, 1.0))
+    zr = O.window_depth(F, cl, (0.1, 0.9))
+    pr = O.project(F, cl)
+    checked = 0
+    for i in range(cl.n):
+        vs = [L.vertex_shader(i, v, cl, fr, cam, origin, 3) for v in range(6)]
+        if vs[0] is None or pr["vis"][i] == 0:
+            continue
+        ndc = [v["gl_Position"][2] / v["gl_Position"][3] for v in vs]
+        assert max(ndc) - min(ndc) == 0.0                        # every vertex of the quad: the centre's z and w
+        assert abs(zw[i] - (0.5 * ndc[0] + 0.5)) < 2e-6
+        assert abs(zr[i] - (0.4 * ndc[0] + 0.5)) < 2e-6
+        checked += 1
+    assert checked > 100
