@@ -196,6 +196,13 @@ int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
 
 }  // namespace
 
+// Nothing may throw across the C ABI (std::bad_alloc from the registry's containers, std::length_error, ...): every
+// entry point that can allocate is a function-try-block ending in this handler.
+#define GSB_CATCH_ALL                                                                                      \
+    catch (const std::bad_alloc&) { return fail(GSB_ERR_NOMEM, "out of host memory"); }                   \
+    catch (const std::exception& e_) { return fail(GSB_ERR_INVALID, std::string("internal error: ") + e_.what()); } \
+    catch (...) { return fail(GSB_ERR_INVALID, "internal error: unknown exception"); }
+
 // ============================================================================== C ABI
 extern "C" {
 
@@ -204,7 +211,7 @@ int gsb_abi_version(void) { return GSB_ABI_VERSION; }
 const char* gsb_last_error(void) { return g_err.c_str(); }
 
 int gsb_create(int cuda_device, gsb_context** out)
-{
+try {
     if (!out) return fail(GSB_ERR_INVALID, "gsb_create: out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -229,10 +236,10 @@ int gsb_create(int cuda_device, gsb_context** out)
     CU(c->plan.ensure(sizeof(ChunkPlan))); CU(c->bucket_hist.ensure(DEPTH_BUCKETS * 4));
     *out = c.release();
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_destroy(gsb_context* ctx)
-{
+try {
     if (!ctx) return GSB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -245,26 +252,26 @@ int gsb_destroy(gsb_context* ctx)
     delete ctx;
     if (s) cudaStreamDestroy(s);
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_set_stream(gsb_context* ctx, void* cuda_stream)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_synchronize(gsb_context* ctx)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_set_option(gsb_context* ctx, int option, double value)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     switch (option) {
     case GSB_OPT_SPLAT_CAP:
@@ -289,7 +296,7 @@ int gsb_set_option(gsb_context* ctx, int option, double value)
         ctx->depth_chunks = (int)value; return GSB_OK;
     default: return fail(GSB_ERR_INVALID, "unknown option");
     }
-}
+} GSB_CATCH_ALL
 
 int gsb_registry_size(gsb_context* ctx) { return ctx ? (int)ctx->registry.size() : 0; }
 
@@ -298,7 +305,7 @@ int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat
                         const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                         const uint16_t* orient_h, const uint16_t* shx_h, const uint16_t* shy_h,
                         const uint16_t* shz_h, char* id_out)
-{
+try {
     if (!ctx || !key || !origin) return fail(GSB_ERR_INVALID, "gsb_register_update: NULL argument");
     if (splat_count < 0 || splat_count > 0x3fffffffLL) return fail(GSB_ERR_INVALID, "gsb_register_update: bad splat_count");
     if (splat_count > 0 && (!pos || !cd_h || !alpha || !scale_h || !orient_h))
@@ -354,11 +361,11 @@ int gsb_register_update(gsb_context* ctx, const gsb_prim_key* key, int64_t splat
     ctx->active_set.erase(id);
     if (id_out) { strncpy(id_out, id.c_str(), GSB_ID_MAX - 1); id_out[GSB_ID_MAX - 1] = 0; }
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 // ------------------------------------------------------------------ GR_PrimGsplat::update, GR.C:191-458 (SURVEY f-1)
 int gsb_update_from_attributes(gsb_context* ctx, const gsb_prim_key* key, const gsb_raw_attributes* a, gsb_update_result* out)
-{
+try {
     if (!ctx || !key || !a || !out) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: NULL argument");
     if (a->count < 0 || a->count > 0x3fffffffLL) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: bad count");
     if (a->count > 0 && !a->P) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: P is required");
@@ -450,10 +457,10 @@ int gsb_update_from_attributes(gsb_context* ctx, const gsb_prim_key* key, const 
     memcpy(out->explicit_camera, a->explicit_camera, 12);
     memcpy(out->barycentre, bary, 12);
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_debug_fetch_entry(gsb_context* ctx, const char* id, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed)
-{
+try {
     if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
     auto it = ctx->registry.find(id);
     if (it == ctx->registry.end()) return fail(GSB_ERR_NOT_FOUND, "gsb_debug_fetch_entry: unknown id");
@@ -479,19 +486,19 @@ int gsb_debug_fetch_entry(gsb_context* ctx, const char* id, int which, void* dst
         CU(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     }
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_include_in_render_pass(gsb_context* ctx, const char* id)      // R.C:313-320
-{
+try {
     if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
     auto it = ctx->registry.find(id);
     if (it == ctx->registry.end()) return GSB_OK;      // the reference silently ignores unknown ids
     it->second->active = true;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_flush_entries_for_matching_detail(gsb_context* ctx, const char* id)   // R.C:293-311
-{
+try {
     if (!ctx || !id) return fail(GSB_ERR_INVALID, "NULL argument");
     auto it = ctx->registry.find(id);
     if (it == ctx->registry.end()) return GSB_OK;
@@ -502,27 +509,27 @@ int gsb_flush_entries_for_matching_detail(gsb_context* ctx, const char* id)   //
         if (j->second->gdp == gdp) j = ctx->registry.erase(j); else ++j;
     }
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_set_rendering_enabled(gsb_context* ctx, int enabled)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     ctx->render_enabled = enabled != 0; return GSB_OK;
-}
+} GSB_CATCH_ALL
 int gsb_set_explicit_camera_pos(gsb_context* ctx, const float pos[3])
-{
+try {
     if (!ctx || !pos) return fail(GSB_ERR_INVALID, "NULL argument");
     ctx->explicit_cam_set = true; memcpy(ctx->explicit_cam, pos, 12); return GSB_OK;
-}
+} GSB_CATCH_ALL
 int gsb_set_spherical_harmonics_order(gsb_context* ctx, int sh_order)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     ctx->sh_order = sh_order; return GSB_OK;       // validation (0..3) is the caller's, GR_GSplat.C:444-457
-}
+} GSB_CATCH_ALL
 
 // ------------------------------------------------------------------ generateRenderGeometry, R.C:322-532
 int gsb_generate_render_geometry(gsb_context* ctx)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     ctx->stats.repacked = 0;
     // isRenderStateRegistryCurrent (R.C:141-153)
@@ -588,11 +595,11 @@ int gsb_generate_render_geometry(gsb_context* ctx)
     ctx->can_render = true;
     ctx->stats.repacked = 1;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 // ------------------------------------------------------------------ render, R.C:534-658
 int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
-{
+try {
     if (!ctx || !fr) return fail(GSB_ERR_INVALID, "gsb_render: NULL argument");
     gsb_stats& st = ctx->stats;
     st.rendered = 0; st.launches = 0;
@@ -936,11 +943,11 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
     st.tiles_x = fc.tiles_x; st.tiles_y = fc.tiles_y;
     memcpy(st.camera, fc.cam, 12); memcpy(st.origin, fc.origin, 12);
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 // ------------------------------------------------------------------ postRender, R.C:660-678
 int gsb_post_render(gsb_context* ctx)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     for (auto& kv : ctx->registry) {
         Entry& e = *kv.second;
@@ -951,10 +958,10 @@ int gsb_post_render(gsb_context* ctx)
     }
     ctx->explicit_cam_set = false;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
-{
+try {
     if (!ctx || !out) return fail(GSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -976,13 +983,13 @@ int gsb_get_stats(gsb_context* ctx, gsb_stats* out)
     }
     *out = st;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 void* gsb_device_framebuffer(gsb_context* ctx) { return ctx ? (void*)ctx->last_fb : nullptr; }
 
 int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height, unsigned char handle_out[GSB_IPC_HANDLE_BYTES],
                          void** local_ptr_out)
-{
+try {
     if (!ctx || !handle_out || !local_ptr_out || width < 1 || height < 1) return fail(GSB_ERR_INVALID, "gsb_ipc_export_frame: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == GSB_IPC_HANDLE_BYTES, "IPC handle size");
     CU(cudaSetDevice(ctx->device));
@@ -992,10 +999,10 @@ int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height, unsign
     memcpy(handle_out, &h, GSB_IPC_HANDLE_BYTES);
     *local_ptr_out = ctx->shared_frame.p;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYTES], void** peer_ptr_out)
-{
+try {
     if (!ctx || !handle || !peer_ptr_out) return fail(GSB_ERR_INVALID, "gsb_ipc_open: NULL argument");
     CU(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h; memcpy(&h, handle, GSB_IPC_HANDLE_BYTES);
@@ -1003,28 +1010,28 @@ int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYT
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));     // maps the peer GPU's memory (NVLink P2P)
     *peer_ptr_out = p;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_ipc_close(gsb_context* ctx, void* peer_ptr)
-{
+try {
     if (!ctx || !peer_ptr) return fail(GSB_ERR_INVALID, "gsb_ipc_close: NULL argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaIpcCloseMemHandle(peer_ptr));
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_copy_to_host(gsb_context* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes)
-{
+try {
     if (!ctx || !device_ptr || !host_ptr) return fail(GSB_ERR_INVALID, "gsb_copy_to_host: NULL argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(host_ptr, device_ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, uint64_t* bytes_needed)
-{
+try {
     if (!ctx) return fail(GSB_ERR_INVALID, "ctx is NULL");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1050,11 +1057,11 @@ int gsb_debug_fetch(gsb_context* ctx, int which, void* dst, uint64_t dst_bytes, 
         CU(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
     }
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_debug_sort_pairs(gsb_context* ctx, const uint32_t* keys, const uint32_t* vals, uint64_t n,
                          int begin_bit, int end_bit, uint32_t* keys_out, uint32_t* vals_out)
-{
+try {
     if (!ctx || (n && (!keys || !vals || !keys_out || !vals_out))) return fail(GSB_ERR_INVALID, "NULL argument");
     if (begin_bit < 0 || end_bit > 32 || end_bit < begin_bit) return fail(GSB_ERR_INVALID, "bad bit range");
     CU(cudaSetDevice(ctx->device));
@@ -1072,10 +1079,10 @@ int gsb_debug_sort_pairs(gsb_context* ctx, const uint32_t* keys, const uint32_t*
     CU(cudaMemcpyAsync(vals_out, v[r].p, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 int gsb_debug_exclusive_scan(gsb_context* ctx, const uint32_t* in, uint64_t n, uint32_t* out, uint64_t* total)
-{
+try {
     if (!ctx || (n && (!in || !out))) return fail(GSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     DevBuf a, b, scr, tot;
@@ -1091,6 +1098,6 @@ int gsb_debug_exclusive_scan(gsb_context* ctx, const uint32_t* in, uint64_t n, u
     CU(cudaStreamSynchronize(s));
     if (total) *total = t;
     return GSB_OK;
-}
+} GSB_CATCH_ALL
 
 }  // extern "C"
