@@ -59,3 +59,20 @@ def test_product_does_not_touch_oracle():
         txt = p.read_text()
         code = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith(("//", "#", "*", "/*")))
         assert "import oracle" not in code and "from oracle" not in code and "gsplat_oracle" not in code, p
+
+
+def test_python_constants_match_the_header_enums():
+    """renderer.py mirrors the option / debug-buffer / depth-function enums of include/gsplat_b200.h by value."""
+    import re
+    from houdini_gsplat_renderer_b200 import renderer as R
+    txt = (ROOT / "include" / "gsplat_b200.h").read_text()
+    enums = {m.group(1): int(m.group(2))                    # enumerator lines only (comments quote some of them too)
+             for m in re.finditer(r"^\s+(GSB_[A-Z0-9_]+)\s*=\s*(\d+)\s*,?\s*(?:/\*.*)?$", txt, re.M)}
+    for name, val in enums.items():
+        for prefix in ("GSB_OPT_", "GSB_DBG_", "GSB_DEPTH_"):
+            if name.startswith(prefix):
+                py = name[4:]                                  # GSB_OPT_EPS_T -> OPT_EPS_T
+                assert hasattr(R, py), f"renderer.py lacks {py}"
+                assert getattr(R, py) == val, (name, val, getattr(R, py))
+    assert enums["GSB_OPT_LAZY_PROJECT"] == 9 and enums["GSB_DBG_TRECTS"] == 9 and enums["GSB_DEPTH_LEQUAL"] == 2
+    assert int(re.search(r"#define GSB_ABI_VERSION (\d+)", txt).group(1)) == 2
