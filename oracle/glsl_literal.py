@@ -191,13 +191,18 @@ def splat_quad(i, cloud, frame, cam, origin, sh_order):
     ax = (c10 - c00) / 4.0       # d(window)/d(qx)
     ay = (c01 - c00) / 4.0       # d(window)/d(qy)
     centre = c00 + 2.0 * ax + 2.0 * ay
-    return dict(centre=centre, ax=ax, ay=ay, color=base["color"], opacity=base["opacity"])
+    g = base["gl_Position"]
+    return dict(centre=centre, ax=ax, ay=ay, color=base["color"], opacity=base["opacity"], ndc_z=g[2] / g[3])
 
 
-def render(cloud, frame, cam, origin, sh_order, order, edge_tol=1e-4):
+def render(cloud, frame, cam, origin, sh_order, order, edge_tol=1e-4, scene_depth=None, depth_func=0,
+           depth_range=(0.0, 1.0), depth_tol=3e-7):
     """Full-frame literal render in the given submission order (front to back, R.C:613-621).
     Returns (rgba [H,W,4] f64, unsafe [H,W] bool) where unsafe marks pixels that came within
-    edge_tol of a coverage / discard discontinuity for some splat (excluded from comparisons)."""
+    edge_tol of a coverage / discard discontinuity for some splat (excluded from comparisons).
+    scene_depth ([H,W]) + depth_func (1 = GL_LESS, 2 = GL_LEQUAL): the fixed-function depth test the reference leaves on
+    (R.C:608-610) with depth writes off; a fragment's window depth is the quad's constant z/w mapped by glDepthRange.
+    Pixels whose scene depth lies within depth_tol of a splat's depth are marked unsafe as well."""
     H, W = frame.height, frame.width
     dst = np.zeros((H, W, 4))
     unsafe = np.zeros((H, W), bool)
@@ -216,6 +221,11 @@ def render(cloud, frame, cam, origin, sh_order, order, edge_tol=1e-4):
         power = -(qx * qx + qy * qy)
         alpha = np.clip(np.exp(power) * q["opacity"], 0.0, 1.0)       # FS SRC.h:306-307
         keep = inside & ~(alpha < 1.0 / 255.0)                        # discard SRC.h:308-309
+        if scene_depth is not None and depth_func:
+            n_, f_ = depth_range
+            zw = q["ndc_z"] * (f_ - n_) / 2.0 + (f_ + n_) / 2.0
+            keep &= (zw < scene_depth) if depth_func == 1 else (zw <= scene_depth)
+            unsafe |= inside & (np.abs(zw - scene_depth) < depth_tol)
         near_edge = (np.abs(np.abs(qx) - 2.0) < edge_tol) | (np.abs(np.abs(qy) - 2.0) < edge_tol)
         near_disc = inside & (np.abs(alpha - 1.0 / 255.0) < edge_tol * (1.0 / 255.0) * 4)
         unsafe |= near_edge & (alpha >= 0.5 / 255.0) | near_disc

@@ -117,3 +117,27 @@ def test_window_depth_matches_the_literal_vertex_shader(oracle, scene, objmat):
         assert abs(zr[i] - (0.4 * ndc[0] + 0.5)) < 2e-6
         checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize("func", [1, 2])
+def test_occluded_frame_matches_the_literal_render(oracle, scene, func):
+    """Whole frames with a scene depth buffer: the oracle's depth-tested blend against the literal emulation of the
+    reference's shaders + fixed-function depth test (R.C:608-621), no early-out, <= 1e-4 away from coverage edges."""
+    from oracle import glsl_literal as L
+    O, S = oracle, scene
+    cl = S.make_cloud(400, 3, sh=True, scale_mult=4.0)
+    fr = S.orbit_frame(96, 54, 20.0)
+    cam = O.camera_from_view(fr.view); origin = cl.barycentre()
+    F = O.make_frame(fr, cam, origin, 3, eps_t=0.0)
+    zw = O.window_depth(F, cl)
+    lo, hi = np.quantile(zw[zw > 0], [0.2, 0.8])
+    x = np.linspace(0.0, 1.0, 96)[None, :]; y = np.linspace(0.0, 1.0, 54)[:, None]
+    sd = (lo + (hi - lo) * (0.5 * x + 0.5 * y)).astype(np.float32)           # a tilted surface through the cloud
+    p = O.pipeline(F, cl, sd, func)
+    plain = O.pipeline(F, cl)
+    assert np.abs(p["rgba"] - plain["rgba"]).max() > 0.05                    # the surface hides something
+    lit, unsafe = L.render(cl, fr, cam, origin, 3, p["order"], scene_depth=sd.astype(np.float64), depth_func=func)
+    diff = np.abs(lit - p["rgba"].astype(np.float64))
+    diff[unsafe] = 0.0                                                        # (incl. pixels within 3e-7 of a depth tie)
+    assert unsafe.mean() < 0.12
+    assert diff.max() < 1e-4, diff.max()
