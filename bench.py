@@ -133,6 +133,20 @@ def frame_for(S, w, step):
     return S.orbit_frame(w["width"], w["height"], theta)
 
 
+def probe_software_gl() -> dict:
+    """is there a software OpenGL on this box that could run the reference's GLSL unmodified
+    (Mesa llvmpipe through OSMesa / EGL)?  dlopen only; the result is reported in cpu_baseline (expected: nothing)."""
+    import ctypes
+    found = {}
+    for lib in ("libOSMesa.so.8", "libOSMesa.so", "libEGL.so.1", "libGL.so.1"):
+        try:
+            ctypes.CDLL(lib)
+            found[lib] = True
+        except OSError:
+            found[lib] = False
+    return found
+
+
 # ------------------------------------------------------------------------------------ reference arm (CPU)
 def cpu_frame(O, S, w, cloud, n_sample, threads_note=True, time_ref_sort=True, step=0):
     sub = cloud if n_sample >= cloud.n else cloud.subset(slice(0, n_sample))
@@ -172,7 +186,8 @@ def run_reference(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": args.workload, "splats": cloud.n, "sample_splats": n_sample,
                                             "sh_degree": 3 if w["sh"] else 0, "width": w["width"], "height": w["height"]},
-            "cpu_baseline": {"value": val, "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": sample,
+                             "software_gl_probe": probe_software_gl()},
             "e2e": {"value": val, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -410,7 +425,8 @@ def run_ours(args):
             "sample": (f"one frame, first {ns} of {N} splats of {args.workload}, same camera/resolution, {cores} host threads; "
                        f"reference-style CPU argsort {st['ms_sort_reference']:.0f} ms + project {st['ms_project']:.0f} + sort "
                        f"{st['ms_sort']:.0f} + bin {st['ms_bin']:.0f} + blend {st['ms_blend']:.0f} ms "
-                       f"(oracle restatement; the reference's GLSL cannot run here: no OpenGL/llvmpipe in the image)")}
+                       f"(oracle restatement; the reference's GLSL cannot run here: no OpenGL/llvmpipe in the image)"),
+            "software_gl_probe": probe_software_gl()}
     print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
