@@ -40,7 +40,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 RECORD_BYTES = 48
-REF_BUDGET_S = 240.0   # wall budget of the whole --impl reference run (a few minutes; larger per-step samples are more representative)
+REF_BUDGET_S = 270.0   # wall budget of the whole --impl reference run (a few minutes)
 
 
 def parse():
@@ -52,11 +52,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth-chunks", type=int, default=0, help="0 = library default (auto)")
-    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl", "host"],
                     help="N>1: p2p = the blend kernel stores finished tiles straight into rank 0's frame over NVLink peer "
                          "memory (CUDA IPC) + a 4-byte NCCL all-reduce as the per-frame completion fence; "
                          "nccl = every rank renders into its own frame and one NCCL reduction combines them")
-    ap.add_argument("--verify", action="store_true", help="N>1: check the combined frame against a single-rank render")
+    ap.add_argument("--verify", action="store_true", help="(accepted for compatibility: N>1 runs are always verified)")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="seconds of back-to-back frames for the sustained pass reported beside the burst (0 = skip)")
     ap.add_argument("--host-direct", type=int, default=1, choices=[0, 1],
                     help="e2e leg: 1 = finished tiles are stored straight into the pinned host frame by the blend kernel "
                          "(GSB_OPT_HOST_DIRECT, library default), 0 = staged cudaMemcpyAsync after the frame")
@@ -147,14 +149,33 @@ def probe_software_gl() -> dict:
     return found
 
 
+# ------------------------------------------------------------------------------------ shared by both arms
+def config_of(args, w, n_splats):
+    """The workload description: identical keys and values in both arms (the driver compares them)."""
+    return {"workload": args.workload, "splats": n_splats, "sh_degree": 3 if w["sh"] else 0,
+            "width": w["width"], "height": w["height"], "camera": "orbit 1 deg/frame" if w["orbit"] else "static",
+            "tile": 16, "eps_t": 1e-5, "splat_cap": "lifted (reference caps at 8388607)",
+            "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (n_splats * 160 / 1e9),
+            "full_pipeline_every_frame": True}
+
+
 # ------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_frame(O, S, w, cloud, n_sample, threads_note=True, time_ref_sort=True, step=0):
+def cpu_frame(O, S, w, cloud, n_sample, step=0):
+    """One frame of the CPU port: the reference's own CPU stage (fp32 distances of every splat + parallel comparison
+    argsort, R.C:176-216) supplies the depth order, then software vertex + fragment + blend stages over screen tiles."""
     sub = cloud if n_sample >= cloud.n else cloud.subset(slice(0, n_sample))
     fr = frame_for(S, w, step)
     F = O.make_frame(fr, O.camera_from_view(fr.view), sub.barycentre(), 3 if w["sh"] else 0, eps_t=1e-5)
     t0 = time.time()
-    _, st = O.render(F, sub, time_reference_sort=time_ref_sort)
-    return time.time() - t0, st, sub.n
+    rgba, st = O.render(F, sub, time_reference_sort=True)
+    return time.time() - t0, st, sub.n, rgba
+
+
+def cpu_sample_note(st, ns, n, workload, w, cores):
+    return (f"first {ns} of {n} splats of workload {workload}, same camera and {w['width']}x{w['height']} frame, {cores} host "
+            f"threads (OpenMP, set explicitly); per frame: reference-style CPU argsort of every splat {st['ms_sort_reference']:.0f} ms "
+            f"(R.C:176-216; its order is the one used) + project {st['ms_project']:.0f} + bin {st['ms_bin']:.0f} + blend "
+            f"{st['ms_blend']:.0f} ms; oracle restatement with tiles and early-out, not the GLSL under llvmpipe (no OpenGL in the image)")
 
 
 def run_reference(args):
@@ -162,31 +183,26 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
+    cores = O.set_num_threads()          # every core of the box, whatever OMP_NUM_THREADS torchrun exported
     S, w, cloud, gen_s = load_workload(args.workload)
-    cores = O.num_threads()
-    # size the per-step sample so warmup+steps fit the budget
-    probe_n = min(cloud.n, 200_000)
-    t_probe, _, _ = cpu_frame(O, S, w, cloud, probe_n)
-    per_step = REF_BUDGET_S / max(1, args.steps + args.warmup)
-    n_sample = int(min(cloud.n, max(100_000, probe_n * per_step / max(t_probe, 1e-3) * 0.7)))
+    # the whole cloud every step; only if warmup+steps of it cannot fit the budget is the sample cut (and said so)
+    t_full, _, _, _ = cpu_frame(O, S, w, cloud, cloud.n)
+    per_step = REF_BUDGET_S / max(1, args.steps + args.warmup + 1)
+    n_sample = cloud.n if t_full <= per_step else int(max(100_000, cloud.n * per_step / t_full * 0.8))
     for i in range(args.warmup):
         cpu_frame(O, S, w, cloud, n_sample, step=i)
     times, st = [], None
     for i in range(args.steps):
-        t, st, _ = cpu_frame(O, S, w, cloud, n_sample, step=args.warmup + i)
+        t, st, _, _ = cpu_frame(O, S, w, cloud, n_sample, step=args.warmup + i)
         times.append(t)
     ms = 1e3 * sum(times) / len(times)
     val = n_sample / (ms * 1e-3) / 1e6
-    sample = (f"first {n_sample} of {cloud.n} splats of workload {args.workload}, same camera and {w['width']}x{w['height']} "
-              f"frame, {cores} host threads (OpenMP); per frame: reference-style CPU argsort {st['ms_sort_reference']:.0f} ms "
-              f"(R.C:176-216) + project {st['ms_project']:.0f} + stable sort {st['ms_sort']:.0f} + bin {st['ms_bin']:.0f} + "
-              f"blend {st['ms_blend']:.0f} ms; reference GLSL under llvmpipe unavailable (no GL in the image)")
     line = {"impl": "reference", "metric": "Msplats/sec at %dx%d" % (w["width"], w["height"]), "value": val,
             "unit": "Msplats/s", "fps": 1e3 / ms, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "splats": cloud.n, "sample_splats": n_sample,
-                                            "sh_degree": 3 if w["sh"] else 0, "width": w["width"], "height": w["height"]},
-            "cpu_baseline": {"value": val, "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": sample,
+            "data": "synthetic", "config": config_of(args, w, cloud.n), "sample_splats": n_sample,
+            "cpu_baseline": {"value": val, "unit": "Msplats/s", "cores": cores, "kind": "port",
+                             "sample": cpu_sample_note(st, n_sample, cloud.n, args.workload, w, cores),
                              "software_gl_probe": probe_software_gl()},
             "e2e": {"value": val, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -198,6 +214,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from houdini_gsplat_renderer_b200 import renderer as R
+    from houdini_gsplat_renderer_b200 import multigpu as M
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,7 +232,7 @@ def run_ours(args):
     r = R.GSplatRenderer(local)
     r.set_option(R.OPT_SPLAT_CAP, 0)          # the reference's 2^23-1 cap lifted for the 20 M configs
     r.set_option(R.OPT_DEPTH_CHUNKS, args.depth_chunks)
-    r.set_option(R.OPT_HOST_DIRECT, args.host_direct)
+    r.set_option(R.OPT_HOST_DIRECT, args.host_direct if world == 1 else 1)
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
     r.setSphericalHarmonicsOrder(sh_order)
@@ -228,47 +245,15 @@ def run_ours(args):
     cold_upload_ms = (time.time() - t0) * 1e3
     h2d_cold = N * (132 if w["sh"] else 36)
 
-    from houdini_gsplat_renderer_b200 import multigpu as M
-    row_group = M.default_row_group(H, world)
-    fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-    host = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
-    host_np = host.numpy()
+    # the row partition, the shared frames, the fence and the hand-off live in the package (multigpu.py)
+    mg = M.RowPartitionedRenderer(r, W, H, rank, world, combine=args.combine, stream=stream)
+    row_group = mg.row_group
     frame_bytes = W * H * 16
 
-    shared = None
-    fence = torch.zeros(1, dtype=torch.int32, device="cuda")
-    if world > 1 and args.combine == "p2p":
-        hbuf = torch.zeros(64, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            handle, shared = r.ipc_export_frame(W, H)
-            hbuf.copy_(torch.tensor(list(handle), dtype=torch.uint8))
-        dist.broadcast(hbuf, 0)
-        if rank != 0:
-            shared = r.ipc_open(bytes(hbuf.cpu().numpy().tobytes()))
-
     def step(i, to_host):
-        fr = frame_for(S, w, i)
         r.includeInRenderPass(rid)
         r.generateRenderGeometry()
-        if world == 1:
-            if to_host:
-                r.render(fr, host_rgba=host_np)
-            else:
-                r.render(fr, device_rgba=fb.data_ptr())
-        elif shared is not None:
-            # fused blend + gather: finished tiles go straight to rank 0's frame; the tiny all-reduce is the frame fence
-            r.render(fr, final_rgba=shared, row_rank=rank, row_world=world, row_group=row_group)
-            dist.all_reduce(fence)
-            if to_host:
-                stream.synchronize()
-                if rank == 0:
-                    r.copy_to_host(shared, host_np)
-        else:
-            r.render(fr, device_rgba=fb.data_ptr(), row_rank=rank, row_world=world, row_group=row_group)
-            dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)      # rows of the other ranks are zeros: exact
-            if to_host and rank == 0:
-                host.copy_(fb, non_blocking=True)
-                stream.synchronize()
+        mg.render(frame_for(S, w, i), to_host=to_host)
         r.postRender()
 
     def barrier():
@@ -276,9 +261,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    STAGES = ("ms_project", "ms_sort", "ms_records", "ms_bin", "ms_blend", "ms_copy")
+    COUNTS = ("n_visible", "n_instances", "n_consumed", "n_live", "launches", "depth_chunks")
+
     def timed(K, to_host, collect):
-        acc = {k: 0.0 for k in ("ms_project", "ms_sort", "ms_records", "ms_bin", "ms_blend", "ms_copy")}
-        cnt = {"n_visible": 0, "n_instances": 0, "n_consumed": 0, "n_live": 0, "launches": 0, "depth_chunks": 0}
+        acc = {k: 0.0 for k in STAGES}
+        cnt = {k: 0 for k in COUNTS}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -295,7 +283,7 @@ def run_ours(args):
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms, acc, cnt
 
-    # clocks are sampled (20 ms period) from before the warm-up to the end of the second timed region: the GPU is
+    # clocks are sampled (20 ms period) from before the warm-up to the end of the timed regions: the GPU is
     # under the same load throughout, so short timed regions still get a meaningful median
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.wait_first_sample()
@@ -312,6 +300,17 @@ def run_ours(args):
     _, acc, cnt = timed(args.steps, False, True)
     r.set_option(R.OPT_STAGE_TIMING, 0)
     clocks = sampler.stop() if sampler else None
+    # sustained pass: >= args.sustain_s seconds of back-to-back frames (the burst above lasts tens of milliseconds, and for an
+    # issue-bound pipeline the SM clock is the result), clocks sampled over exactly this region
+    sustained = None
+    if args.sustain_s > 0:
+        Ks = max(args.steps, int(args.sustain_s * 1e3 / max(ms_dev / args.steps, 1e-3)) + 1)
+        s2 = ClockSampler(local) if rank == 0 else None
+        if s2: s2.wait_first_sample()
+        ms_sus, _, _ = timed(Ks, False, False)
+        c2 = s2.stop() if s2 else None
+        sustained = {"seconds": ms_sus * 1e-3, "frames": Ks, "ms_per_step": ms_sus / Ks,
+                     "value": N / (ms_sus / Ks * 1e-3) / 1e6, "unit": "Msplats/s", "fps": 1e3 * Ks / ms_sus, "clocks": c2}
 
     K = args.steps
     ms_step = ms_dev / K
@@ -319,69 +318,93 @@ def run_ours(args):
     e2e_ms = ms_e2e / K
     e2e_val = N / (e2e_ms * 1e-3) / 1e6
 
-    if world > 1:   # stage times / counters: sum counters over ranks, max stage times
-        t = torch.tensor([cnt[k] for k in cnt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t); cnt = dict(zip(cnt.keys(), [int(x) for x in t.tolist()]))
-        t = torch.tensor([acc[k] for k in acc], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); acc = dict(zip(acc.keys(), t.tolist()))
-    verify = None
-    if world > 1 and args.verify:
-        step(0, True)
-        barrier()
-        if rank == 0:
-            solo = np.zeros_like(host_np)
-            r.includeInRenderPass(rid); r.generateRenderGeometry()
-            r.render(frame_for(S, w, 0), host_rgba=solo); r.postRender()
-            verify = "bit-identical to the single-rank frame" if np.array_equal(solo, host_np) else \
-                     "MISMATCH max|d|=%g" % float(np.abs(solo - host_np).max())
-        barrier()
-    if rank != 0:
-        if shared is not None: r.ipc_close(shared)
-        r.close()
-        if world > 1: dist.destroy_process_group()
-        return
-
     peak, peak_src = peaks()
-    V, D, Dc, L = cnt["n_visible"] / K, cnt["n_instances"] / K, cnt["n_consumed"] / K, cnt["n_live"] / K
-    # algorithmic (compulsory) bytes per frame: what each stage must read and write once, with the per-unit figures of
-    # SURVEY.md §8d (30 B cull read per submitted splat, 6+SH colour bytes and R = 48-byte record per splat that gets one,
-    # 4+R per consumed instance); counters from gsb_stats.  N is replicated on every rank (each rank culls all splats);
-    # V, L (splats that reach a live tile), D, D_c are summed over ranks.
     sh_bytes = {0: 0, 1: 18, 2: 48, 3: 90}[sh_order]
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     tile_passes = max(1, -(-max(1, (tiles - 1).bit_length()) // 8))
     key_passes = 3                                        # 25 significant key bits at these camera distances: 9+8+8
-    Nw = N * world
-    chunks = max(1.0, cnt["depth_chunks"] / K / world)
-    stage_bytes = {
-        # K1 (bounded, the library default): position + discard radius (16 B) + covariance eigenvalue bound (4 B) read,
-        # (key, packed tile rectangle) written, for every submitted splat.  (SURVEY's unit for an exact cull phase is 30 B.)
-        "project": Nw * 20 + Nw * 8,
-        # per depth chunk: live selection streams key + tile rectangle of every splat (8 B) and writes/reads one ballot bit
-        # per splat; the L selected (key, index, rect) triples are gathered (8 B) and written (12 B), then LSD-sorted
-        # (histogram read + passes x 24 B)
-        "sort": chunks * Nw * (8 + 0.25) + L * (8 + 12) + L * (4 + key_passes * 24),
-        # K2: index + 30 B geometry + colour/SH read, record written, per live splat
-        "records": L * (4 + 30 + 6 + sh_bytes) + L * RECORD_BYTES,
-        # K4: counts (rect read, count write, scan), emit (offset + rect + index read, 8 B per instance written), stable tile
-        # partition (histogram read + passes x 16 B), tile ranges (tile id read, table write)
-        "bin": L * (8 + 12 + 12) + D * 8 + D * 4 + tile_passes * D * 16 + D * 4 + tiles * 8,
-        "blend": Dc * (4 + RECORD_BYTES) + (W * H * 16),
-    }
-    stage_ms = {"project": acc["ms_project"] / K, "sort": acc["ms_sort"] / K, "records": acc["ms_records"] / K,
-                "bin": acc["ms_bin"] / K, "blend": acc["ms_blend"] / K}
-    stages = {k: {"ms": stage_ms[k], "algorithmic_bytes": stage_bytes[k],
-                  "achieved_GBps": stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None,
-                  "frac_of_peak": stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 / peak if stage_ms[k] > 0 else None}
-              for k in stage_ms}
+
+    def stage_table(acc, cnt):
+        """Algorithmic (compulsory) bytes of ONE rank per frame, SURVEY.md §8d per-unit figures, and that rank's stage
+        times: every fraction is one GPU's bytes over one GPU's time against one GPU's peak."""
+        V, D, Dc, L = cnt["n_visible"] / K, cnt["n_instances"] / K, cnt["n_consumed"] / K, cnt["n_live"] / K
+        chunks = max(1.0, cnt["depth_chunks"] / K)
+        owned_px = W * H / world
+        sb = {
+            # K1 (bounded, the library default): position + discard radius (16 B) + covariance eigenvalue bound (4 B) read,
+            # (key, packed tile rectangle) written, for every submitted splat.  (SURVEY's unit for an exact cull phase is 30 B.)
+            "project": N * 20 + N * 8,
+            # per depth chunk: live selection streams key + tile rectangle of every splat (8 B); the L selected (key, index)
+            # pairs are staged and gathered (8 + 12 B), then LSD-sorted (histogram read + passes x 24 B)
+            "sort": chunks * N * (8 + 0.25) + L * (8 + 12) + L * (4 + key_passes * 24),
+            # K2: index + 30 B geometry + colour/SH read, record written, per live splat
+            "records": L * (4 + 30 + 6 + sh_bytes) + L * RECORD_BYTES,
+            # K4: counts, emit (8 B per instance written), stable tile partition (histogram read + passes x 16 B), tile ranges
+            "bin": L * (8 + 12 + 12) + D * 8 + D * 4 + tile_passes * D * 16 + D * 4 + tiles * 8,
+            "blend": Dc * (4 + RECORD_BYTES) + owned_px * 16,
+        }
+        sm = {"project": acc["ms_project"] / K, "sort": acc["ms_sort"] / K, "records": acc["ms_records"] / K,
+              "bin": acc["ms_bin"] / K, "blend": acc["ms_blend"] / K}
+        out = {k: {"ms": sm[k], "algorithmic_bytes": sb[k],
+                   "achieved_GBps": sb[k] / (sm[k] * 1e-3) / 1e9 if sm[k] > 0 else None,
+                   "frac_of_peak": sb[k] / (sm[k] * 1e-3) / 1e9 / peak if sm[k] > 0 else None} for k in sm}
+        return out, {"N": N, "V": V, "L": L, "D": D, "D_c": Dc, "depth_chunks": chunks, "launches": cnt["launches"] / K}
+
+    my_stages, my_counters = stage_table(acc, cnt)
+    per_rank = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"rank": rank, "stages": my_stages, "counters": my_counters})
+        per_rank = gathered
+
+    # multi-GPU frames are checked on every run: the combined frame against a single-rank render of the same frame
+    verify = None
+    if world > 1:
+        step(0, True)
+        barrier()
+        if rank == 0:
+            combined = np.array(mg.host_frame(), copy=True)
+            solo = np.zeros_like(combined)
+            r.includeInRenderPass(rid); r.generateRenderGeometry()
+            r.render(frame_for(S, w, 0), host_rgba=solo); r.postRender()
+            verify = "bit-identical to the single-rank frame" if np.array_equal(solo, combined) else \
+                     "MISMATCH max|d|=%g" % float(np.abs(solo - combined).max())
+        barrier()
+    # the production frame of the benchmarked workload (frame 0, host target), kept for the parity check below
+    gpu_frame0, gpu_stats0 = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step(0, True)
+        gpu_frame0 = np.array(mg.host_frame(), copy=True)
+        gpu_stats0 = r.stats()
+    if rank != 0:
+        mg.close(); r.close()
+        if world > 1: dist.destroy_process_group()
+        return
+
+    stages, counters = my_stages, my_counters
     blend_ach = stages["blend"]["achieved_GBps"] or 0.0
     # measured DRAM traffic of the blend launches of one frame, from the committed ncu --set full capture of this workload
     traffic, traffic_src = None, None
     try:
-        tj = json.loads((ROOT / "profiles" / "r01_final_ncu_traffic.json").read_text()).get(args.workload)
-        if tj and world == 1 and abs(tj["depth_chunks"] - chunks) < 1e-9:
+        tj = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text()).get(args.workload)
+        if tj and world == 1:
             traffic = tj["blend_kernel"]["dram_bytes_per_frame"]
-            traffic_src = "profiles/r01_final_ncu_full_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, blend launches of one frame)"
+            traffic_src = tj.get("source", "profiles/r02_ncu_full_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, blend launches of one frame)")
+    except Exception:
+        pass
+    # second roof of the blend: it is issue bound, not HBM bound (DESIGN.md §5): warp instructions per frame from the same
+    # ncu capture (smsp__inst_executed.sum) against 148 SMs x 4 schedulers x 1 warp instruction per clock at the sampled SM clock
+    issue = None
+    try:
+        ij = json.loads((ROOT / "profiles" / "r02_ncu_traffic.json").read_text()).get(args.workload)
+        if ij and world == 1 and clocks and clocks.get("sm_mhz") and stages["blend"]["ms"] > 0:
+            winst = float(ij["blend_kernel"]["warp_instructions_per_frame"])
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+            ach = winst / (stages["blend"]["ms"] * 1e-3)
+            issue = {"bound": "issue", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
+                     "frac": ach / peak_issue, "warp_instructions_per_frame": winst,
+                     "note": "warp instructions from the committed ncu capture; time = CUDA events of this run; peak = 148 SMs x 4 "
+                             "issue slots x the median SM clock sampled during this run"}
     except Exception:
         pass
 
@@ -389,45 +412,56 @@ def run_ours(args):
         "metric": "Msplats/sec at %dx%d" % (W, H), "value": value, "unit": "Msplats/s", "fps": 1e3 / ms_step,
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "splats": N, "sh_degree": sh_order, "width": W, "height": H,
-                   "camera": "orbit 1 deg/frame" if w["orbit"] else "static", "tile": 16, "eps_t": 1e-5,
-                   "splat_cap": "lifted (reference caps at 8388607)", "parallelism": f"tile-row bands of {row_group} x16 px interleaved over {world} GPU(s)",
-                   "l2_policy": "inputs larger than L2 (%.2f GB packed attributes vs 126 MB L2)" % (N * 160 / 1e9),
-                   "full_pipeline_every_frame": True, "depth_chunks": cnt["depth_chunks"] / K / world},
+        "config": config_of(args, w, N),
+        "parallelism": f"tile-row bands of {row_group} x16 px interleaved over {world} GPU(s)",
+        "depth_chunks": counters["depth_chunks"],
         "e2e": {"value": e2e_val, "unit": "Msplats/s", "fps": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 368, "d2h_bytes_per_step": frame_bytes,
-                "host_direct": bool(args.host_direct) and world == 1,
-                "note": "gsb_render with host target: gsb_frame in, RGBA32F frame to pinned host memory, the call returns when "
-                        "the frame is there; geometry resident (the reference also re-uploads only on active-set change)"},
+                "h2d_bytes_per_step": 368 * world, "d2h_bytes_per_step": frame_bytes,
+                "host_direct": True if world > 1 else bool(args.host_direct),
+                "note": "gsb_render with a pinned host target: gsb_frame in, RGBA32F frame stored into host memory by the blend "
+                        "kernels (every rank over its own PCIe link; N>1: one shared frame + a 4-byte all-reduce fence), the call "
+                        "returns when the frame is there; geometry resident (the reference also re-uploads only on active-set change)"},
         "e2e_cold_ms": cold_upload_ms, "e2e_cold_h2d_bytes": h2d_cold,
+        "e2e_cold_GBps": h2d_cold / (cold_upload_ms * 1e-3) / 1e9,
         "gpu_launches": cnt["launches"],
         "roofline": {"kernel": "blend_kernel", "bound": "hbm", "achieved": blend_ach, "peak": peak, "unit": "GB/s",
                      "frac": blend_ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": stage_bytes["blend"], "ms_per_launch": stage_ms["blend"],
-                     "launch": "the blend launches of one frame (one per depth chunk), bytes and time summed",
+                     "algorithmic_bytes_per_launch": stages["blend"]["algorithmic_bytes"], "ms_per_launch": stages["blend"]["ms"],
+                     "launch": "the blend launches of one frame (one per depth chunk), bytes and time summed"
+                               + ("; rank 0's share" if world > 1 else ""),
                      "formula": "D_c*(4+48) + W*H*16"},
+        "roofline_issue": issue,
         "stages": stages,
-        "counters_per_frame": {"N": N, "V": V, "L": L, "D": D, "D_c": Dc},
+        "stages_per_rank": per_rank,
+        "counters_per_frame": counters,
         "counters_note": "bounded K1 (library default): V = splats that pass the cheap culls with a non-empty rectangle bound and "
-                         "L = splats the depth chunks selected are upper bounds of the exact counts; D and D_c are exact",
+                         "L = splats the depth chunks selected are upper bounds of the exact counts; D and D_c are exact"
+                         + ("; rank 0's share" if world > 1 else ""),
         "clocks": clocks,
+        "sustained": sustained,
         "combine": (args.combine if world > 1 else None), "verify": verify,
         "scene_gen_s": gen_s,
     }
 
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as O
-        cores = O.num_threads()
-        n_sample = min(N, 20_000_000)      # the whole frame for every BASELINE config: ~5 s on 16 host cores at 20 M
-        t, st, ns = cpu_frame(O, S, w, cloud, n_sample)
+        cores = O.set_num_threads()
+        t, st, ns, ref_rgba = cpu_frame(O, S, w, cloud, N)     # the whole frame of the benchmarked workload
         line["cpu_baseline"] = {
             "value": ns / t / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
-            "sample": (f"one frame, first {ns} of {N} splats of {args.workload}, same camera/resolution, {cores} host threads; "
-                       f"reference-style CPU argsort {st['ms_sort_reference']:.0f} ms + project {st['ms_project']:.0f} + sort "
-                       f"{st['ms_sort']:.0f} + bin {st['ms_bin']:.0f} + blend {st['ms_blend']:.0f} ms "
-                       f"(oracle restatement; the reference's GLSL cannot run here: no OpenGL/llvmpipe in the image)"),
+            "sample": "one whole frame: " + cpu_sample_note(st, ns, N, args.workload, w, cores),
             "software_gl_probe": probe_software_gl()}
+        # parity of THIS run's production frame (auto depth chunks, bounded K1, host-direct delivery) against the oracle's
+        # frame of the same workload and camera; outside every timed region
+        d = np.abs(gpu_frame0.astype(np.float64) - ref_rgba.astype(np.float64))
+        line["parity"] = {"against": "oracle frame of the same workload, frame 0 (the cpu_baseline render)",
+                          "max_abs": float(d.max()), "pixels_over_1e-3": int((d.max(axis=2) > 1e-3).sum()),
+                          "pixels_over_2e-5": int((d.max(axis=2) > 2e-5).sum()), "tolerance": 1e-3,
+                          "D_c_gpu": int(gpu_stats0["n_consumed"]), "D_c_oracle": int(st["n_consumed"]),
+                          "D_c_equal": int(gpu_stats0["n_consumed"]) == int(st["n_consumed"]),
+                          "ok": bool(d.max() <= 1e-3)}
     print(json.dumps(line), flush=True)
+    mg.close()
     r.close()
     if world > 1:
         dist.destroy_process_group()

@@ -53,7 +53,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // DEPTH: scene-depth occlusion (R.C:608-610 depth test on / writes off, SRC.h:278-282 one depth per quad):
 // the window depth of every staged instance rides along in shared memory, each pixel keeps the scene depth at its
 // position in a register, and a fragment that fails F.depth_func is dropped (no colour, no transmittance change).
-template <bool OBB_CULL, bool DEPTH>
+template <bool OBB_CULL, bool DEPTH, bool QUEUE>
 __global__ void __launch_bounds__(BL_THREADS)
 blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
              const uint2* __restrict__ ranges, float4* __restrict__ fb, float4* __restrict__ fb_final,
@@ -66,6 +66,7 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
     __shared__ __align__(16) Record srec[2][BL_BATCH];
     __shared__ float sz[DEPTH ? 2 : 1][DEPTH ? BL_BATCH : 1];
     __shared__ uint32_t s_consumed;
+    __shared__ uint32_t swq[QUEUE ? BL_THREADS / 32 : 1][QUEUE ? 32 : 1];
 
     const int tile = blockIdx.x;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
@@ -162,6 +163,39 @@ blend_kernel(const Record* __restrict__ recs, const uint32_t* __restrict__ inst,
                     }
                 }
                 unsigned mask = __ballot_sync(0xffffffffu, ov);
+                if (QUEUE) {
+                    // the survivors' shared-memory byte offsets are compacted into a small per-warp queue, so the visit loop
+                    // reads its record address with one broadcast load instead of recomputing it from the ballot mask
+                    // (bit reverse + find-leading-one + two integer multiply-adds per visit in the SASS of the mask walk)
+                    const int nq = __popc(mask);
+                    if (ov) swq[warp][__popc(mask & ((1u << lane) - 1u))] = (uint32_t)((c + lane) * (uint32_t)sizeof(Record));
+                    __syncwarp();
+                    const char* bufc = reinterpret_cast<const char*>(buf);
+                    uint32_t done_off = 0xffffffffu;          // queue entry that saturated this pixel (converted after the loop)
+                    for (int i = 0; i < nq; ++i) {
+                        const uint32_t off = swq[warp][i];
+                        const float4* rp = reinterpret_cast<const float4*>(bufc + off);
+                        const float4 r0 = rp[0], r1 = rp[1];
+                        bool zpass = true;
+                        if (DEPTH) { const float zw = sz[b & 1][off / (uint32_t)sizeof(Record)]; zpass = lequal ? (zw <= sd) : (zw < sd); }
+                        if (T >= eps && zpass) {
+                            const float dx = fpx - r0.x, dy = fpy - r0.y;
+                            const float qx = fmaf(dy, r0.w, dx * r0.z);
+                            const float qy = fmaf(dy, r1.y, dx * r1.x);
+                            const float pw = fmaf(qy, qy, qx * qx);
+                            if (fabsf(qx) <= 2.0f && fabsf(qy) <= 2.0f && pw <= r1.w) {
+                                const float4 r2 = rp[2];
+                                const float A = fminf(r1.z * ex2_mufu(pw * -1.4426950408889634f), 1.0f);   // alpha * exp(-pw)
+                                const float w = T * A;
+                                Cr = fmaf(w, r2.x, Cr); Cg = fmaf(w, r2.y, Cg); Cb = fmaf(w, r2.z, Cb);
+                                T = T - w;
+                                if (T < eps) done_off = off;
+                            }
+                        }
+                    }
+                    if (done_off != 0xffffffffu) done_pos = b * BL_BATCH + done_off / (uint32_t)sizeof(Record) + 1u;
+                    __syncwarp();
+                } else
                 while (mask) {
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -220,11 +254,15 @@ void launch_blend(const Record* recs, const uint32_t* inst_vals, const uint2* ra
     if (tiles <= 0) return;
     const char* e = getenv("GSB_BLEND_OBB");   // GSB_BLEND_OBB=0 turns the eigen-space cull off (experiments)
     const int obb = (e && atoi(e) == 0) ? 0 : 1;
+    const char* eq = getenv("GSB_BLEND_QUEUE"); // GSB_BLEND_QUEUE=0: walk the ballot mask instead of the survivor queue
+    const int queue = (eq && atoi(eq) == 0) ? 0 : 1;
     const bool depth = fc.depth_func != 0 && zdepth && scene_depth;
-#define GSB_BLEND(O, D) blend_kernel<O, D><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, \
+#define GSB_BLEND(O, D, Q) blend_kernel<O, D, Q><<<tiles, BL_THREADS, 0, s>>>(recs, inst_vals, ranges, fb, fb_final ? fb_final : fb, fc, first, \
                             last, tile_done, tile_consumed, consumed_total, done_tiles, zdepth, scene_depth)
-    if (depth) { if (obb) GSB_BLEND(true, true); else GSB_BLEND(false, true); }
-    else       { if (obb) GSB_BLEND(true, false); else GSB_BLEND(false, false); }
+#define GSB_BLEND_Q(O, D) do { if (queue) GSB_BLEND(O, D, true); else GSB_BLEND(O, D, false); } while (0)
+    if (depth) { if (obb) GSB_BLEND_Q(true, true); else GSB_BLEND_Q(false, true); }
+    else       { if (obb) GSB_BLEND_Q(true, false); else GSB_BLEND_Q(false, false); }
+#undef GSB_BLEND_Q
 #undef GSB_BLEND
 }
 

@@ -19,6 +19,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gsb;
@@ -79,6 +80,70 @@ struct Entry {
     DevBuf   pos, cd, alpha, scale, orient, shx, shy, shz;
 };
 
+// ---- cold path (geometry change): host -> device through pinned, double-buffered staging.  A cudaMemcpyAsync from
+// pageable memory is staged by the driver through one small bounce buffer (r01: 2.64 GB in 0.64 s, 4 GB/s); here a few
+// host threads fill one pinned slot while the DMA engine drains the other, so the rate is min(host memcpy, PCIe).
+int host_threads()
+{
+    static int n = 0;
+    if (!n) { unsigned h = std::thread::hardware_concurrency(); n = (int)std::min(16u, std::max(1u, h)); }
+    return n;
+}
+
+template <class F> void parallel_ranges(size_t n, size_t grain, F&& f)      // f(begin, end) on disjoint ranges
+{
+    int t = (int)std::min<size_t>((size_t)host_threads(), (n + grain - 1) / std::max<size_t>(grain, 1));
+    if (t <= 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)t);
+    for (int k = 0; k < t; ++k) {
+        const size_t a = n * (size_t)k / (size_t)t, b = n * (size_t)(k + 1) / (size_t)t;
+        th.emplace_back([&f, a, b] { f(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
+
+struct Stager {
+    static constexpr size_t SLOT = (size_t)32 << 20;
+    char* slot[2] = { nullptr, nullptr };
+    cudaEvent_t done[2] = { nullptr, nullptr };
+    bool busy[2] = { false, false };
+    int next = 0;
+    ~Stager()
+    {
+        for (int i = 0; i < 2; ++i) { if (slot[i]) cudaFreeHost(slot[i]); if (done[i]) cudaEventDestroy(done[i]); }
+    }
+    cudaError_t init()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (!slot[i]) { cudaError_t e = cudaMallocHost(&slot[i], SLOT); if (e != cudaSuccess) return e; }
+            if (!done[i]) { cudaError_t e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        }
+        return cudaSuccess;
+    }
+    // stream-ordered copy of a pageable host range; returns before the last DMA finishes (the slots are ours)
+    cudaError_t copy(void* dst, const void* src, size_t bytes, cudaStream_t s)
+    {
+        cudaError_t e = init();
+        if (e != cudaSuccess) return e;
+        const char* sp = static_cast<const char*>(src);
+        char* dp = static_cast<char*>(dst);
+        for (size_t off = 0; off < bytes; off += SLOT) {
+            const size_t len = std::min(SLOT, bytes - off);
+            const int k = next; next ^= 1;
+            if (busy[k]) { e = cudaEventSynchronize(done[k]); if (e != cudaSuccess) return e; busy[k] = false; }
+            char* buf = slot[k];
+            parallel_ranges(len, (size_t)1 << 20, [&](size_t a, size_t b) { memcpy(buf + a, sp + off + a, b - a); });
+            e = cudaMemcpyAsync(dp + off, buf, len, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(done[k], s);
+            if (e != cudaSuccess) return e;
+            busy[k] = true;
+        }
+        return cudaSuccess;
+    }
+};
+
 enum { EV_START = 0, EV_PROJECT, EV_SORT, EV_BIN, EV_BLEND, EV_COPY, EV_COUNT };
 
 }  // namespace
@@ -90,6 +155,8 @@ struct gsb_context {
     // registry + state machine (names follow the reference's members)
     std::map<std::string, std::unique_ptr<Entry>> registry;   // myRenderStateRegistry (ordered: deterministic iteration)
     std::set<std::string> active_set;                         // myActiveRegistries
+    bool    pack_dirty = false;                               // a packed prim was re-registered / the cap changed: re-pack even if
+                                                              // the requested set equals active_set (which stays the packed set)
     bool    render_enabled = true;                            // myIsRenderEnabled
     bool    can_render = false;                               // myCanRender
     bool    sh_present = false;                               // myIsShDataPresent
@@ -125,6 +192,7 @@ struct gsb_context {
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
+    Stager stager;                                   // pinned double-buffered staging of the cold-path uploads
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
     unsigned long long* counters_h = nullptr;        // pinned mirror
@@ -151,11 +219,65 @@ std::string make_id(const gsb_prim_key& k)
     return oss.str();
 }
 
-int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s)
+int upload(Stager& st, DevBuf& b, const void* src, size_t bytes, cudaStream_t s)
 {
     CU(b.ensure(bytes ? bytes : 16));
-    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    if (!bytes) return GSB_OK;
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (pinned || bytes < ((size_t)4 << 20)) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    else CU(st.copy(b.p, src, bytes, s));
     return GSB_OK;
+}
+
+struct DevBufView { char* p; };
+int upload_into(Stager& st, void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    if (!bytes) return GSB_OK;
+    if (bytes < ((size_t)4 << 20)) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    else CU(st.copy(dst, src, bytes, s));
+    return GSB_OK;
+}
+
+// bounding box + finiteness of n xyz triples, over the host threads
+void bbox_of(const float* pos, size_t n, float lo[3], float hi[3], bool& finite)
+{
+    const int T = host_threads();
+    std::vector<float> part((size_t)T * 6, 0.0f);
+    std::vector<char> fin((size_t)T, 1), used((size_t)T, 0);
+    std::vector<std::thread> th;
+    const int t = (int)std::min<size_t>((size_t)T, (n + 65535) / 65536);
+    auto work = [&](int k, size_t a, size_t b) {
+        float l[3] = { pos[3 * a], pos[3 * a + 1], pos[3 * a + 2] }, h[3] = { l[0], l[1], l[2] };
+        bool f = true;
+        for (size_t i = a; i < b; ++i)
+            for (int c = 0; c < 3; ++c) {
+                const float v = pos[3 * i + c];
+                f = f && std::isfinite(v);
+                l[c] = v < l[c] ? v : l[c]; h[c] = v > h[c] ? v : h[c];
+            }
+        for (int c = 0; c < 3; ++c) { part[(size_t)k * 6 + c] = l[c]; part[(size_t)k * 6 + 3 + c] = h[c]; }
+        fin[(size_t)k] = f ? 1 : 0; used[(size_t)k] = 1;
+    };
+    if (t <= 1) work(0, 0, n);
+    else {
+        for (int k = 0; k < t; ++k) {
+            const size_t a = n * (size_t)k / (size_t)t, b = n * (size_t)(k + 1) / (size_t)t;
+            if (b > a) th.emplace_back(work, k, a, b);
+        }
+        for (auto& x : th) x.join();
+    }
+    finite = true; bool first = true;
+    for (int k = 0; k < T; ++k) {
+        if (!used[(size_t)k]) continue;
+        finite = finite && fin[(size_t)k];
+        for (int c = 0; c < 3; ++c) {
+            const float l = part[(size_t)k * 6 + c], h = part[(size_t)k * 6 + 3 + c];
+            lo[c] = first ? l : (l < lo[c] ? l : lo[c]); hi[c] = first ? h : (h > hi[c] ? h : hi[c]);
+        }
+        first = false;
+    }
 }
 
 // camera = (0,0,0,1) * inverse(view) in double, rounded to f32 (R.C:558-562): 4th column of the
@@ -276,7 +398,7 @@ try {
     switch (option) {
     case GSB_OPT_SPLAT_CAP:
         if (value < 0) return fail(GSB_ERR_INVALID, "GSB_OPT_SPLAT_CAP must be >= 0");
-        if (ctx->cap != (int64_t)value) ctx->active_set.clear();     // force a re-pack under the new budget
+        if (ctx->cap != (int64_t)value) ctx->pack_dirty = true;      // force a re-pack under the new budget
         ctx->cap = (int64_t)value; return GSB_OK;
     case GSB_OPT_EPS_T:
         if (!(value >= 0.0 && value < 1.0)) return fail(GSB_ERR_INVALID, "GSB_OPT_EPS_T must be in [0,1)");
@@ -316,49 +438,47 @@ try {
     CU(cudaSetDevice(ctx->device));
     const std::string id = make_id(*key);
 
-    // same gdp, different version -> erase (R.C:246-265)
-    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {
-        Entry& e = *it->second;
-        if (e.gdp == key->gdp && memcmp(e.version, key->version, sizeof e.version) != 0) it = ctx->registry.erase(it);
-        else ++it;
-    }
-    auto& slot = ctx->registry[id];
-    if (!slot) slot.reset(new Entry);
-    Entry& e = *slot;
+    // The new entry is built on the side and enters the registry only when every upload has succeeded: a failed call
+    // (GSB_ERR_NOMEM at 20 M splats ...) leaves the registry exactly as it was.
+    std::unique_ptr<Entry> ne(new Entry);
+    Entry& e = *ne;
     e.gdp = key->gdp; e.vtx0 = key->vtx0; memcpy(e.version, key->version, sizeof e.version);
     e.count = splat_count; memcpy(e.origin, origin, sizeof e.origin);
     e.active = false; e.age = -1; e.age_since_last_active = -1;
     e.has_sh = has_sh && splat_count > 0;
     const size_t n = (size_t)splat_count;
-    // bounding box of the prim (host pass over the positions; used to bound the depth keys, see gsb_render)
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = upload(ctx->stager, e.pos, pos, n * 12, s))) return rc;
+    // bounding box of the prim (bounds the depth keys, see gsb_render): host threads, while the first DMA runs
     e.bbox_valid = n > 0;
     if (n > 0) {
-        float lo[3] = { pos[0], pos[1], pos[2] }, hi[3] = { pos[0], pos[1], pos[2] };
-        bool finite = true;
-        for (size_t i = 0; i < n; ++i)
-            for (int k = 0; k < 3; ++k) {
-                const float v = pos[3 * i + k];
-                finite = finite && std::isfinite(v);
-                lo[k] = v < lo[k] ? v : lo[k]; hi[k] = v > hi[k] ? v : hi[k];
-            }
+        float lo[3], hi[3]; bool finite = true;
+        bbox_of(pos, n, lo, hi, finite);
         e.bbox_valid = finite;
         for (int k = 0; k < 3; ++k) { e.bbox[k] = lo[k]; e.bbox[3 + k] = hi[k]; }
     }
-    cudaStream_t s = ctx->stream;
-    int rc;
-    if ((rc = upload(e.pos, pos, n * 12, s))) return rc;
-    if ((rc = upload(e.cd, cd_h, n * 6, s))) return rc;
-    if ((rc = upload(e.alpha, alpha, n * 4, s))) return rc;
-    if ((rc = upload(e.scale, scale_h, n * 6, s))) return rc;
-    if ((rc = upload(e.orient, orient_h, n * 8, s))) return rc;
+    if ((rc = upload(ctx->stager, e.cd, cd_h, n * 6, s))) return rc;
+    if ((rc = upload(ctx->stager, e.alpha, alpha, n * 4, s))) return rc;
+    if ((rc = upload(ctx->stager, e.scale, scale_h, n * 6, s))) return rc;
+    if ((rc = upload(ctx->stager, e.orient, orient_h, n * 8, s))) return rc;
     if (e.has_sh) {
-        if ((rc = upload(e.shx, shx_h, n * 32, s))) return rc;
-        if ((rc = upload(e.shy, shy_h, n * 32, s))) return rc;
-        if ((rc = upload(e.shz, shz_h, n * 32, s))) return rc;
+        if ((rc = upload(ctx->stager, e.shx, shx_h, n * 32, s))) return rc;
+        if ((rc = upload(ctx->stager, e.shy, shy_h, n * 32, s))) return rc;
+        if ((rc = upload(ctx->stager, e.shz, shz_h, n * 32, s))) return rc;
     }
     CU(cudaStreamSynchronize(s));      // the caller's arrays are not borrowed past this call
-    // a re-registered id with new data must be re-packed even if the active set looks unchanged
-    ctx->active_set.erase(id);
+
+    // same gdp, different version -> erase (R.C:246-265); then the entry replaces any older one under the same id
+    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {
+        Entry& o = *it->second;
+        if (o.gdp == key->gdp && memcmp(o.version, key->version, sizeof o.version) != 0) it = ctx->registry.erase(it);
+        else ++it;
+    }
+    ctx->registry[id] = std::move(ne);
+    // a re-registered id carries new data: re-pack even if the active set looks unchanged (active_set itself stays the
+    // packed set, so the comparison of R.C:141-153 keeps its meaning)
+    if (ctx->active_set.count(id)) ctx->pack_dirty = true;
     if (id_out) { strncpy(id_out, id.c_str(), GSB_ID_MAX - 1); id_out[GSB_ID_MAX - 1] = 0; }
     return GSB_OK;
 } GSB_CATCH_ALL
@@ -381,44 +501,37 @@ try {
     if (!sh_kind) { bool all = true; for (int j = 0; j < 45; ++j) all = all && a->f_rest[j]; if (all) sh_kind = 3; }
     const bool sh_found = sh_kind != 0 && n > 0;
 
-    // barycentre + bounding box on the host (sequential fp32 sum, GEO_GSplat.C:338-351: the order of additions matters)
+    // barycentre: sequential fp32 sum / count (GEO_GSplat.C:338-351 — the order of the additions is the spec, so this
+    // one pass stays serial; it runs on its own thread beside the uploads), bounding box over the host threads
     float sum[3] = { 0, 0, 0 }, lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
     bool finite = n > 0;
-    for (size_t i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const float v = a->P[3 * i + k];
-            sum[k] += v;
-            finite = finite && std::isfinite(v);
-            if (i == 0) { lo[k] = hi[k] = v; } else { lo[k] = v < lo[k] ? v : lo[k]; hi[k] = v > hi[k] ? v : hi[k]; }
-        }
-    float bary[3] = { 0, 0, 0 };
-    if (n > 0) { const float fn = (float)a->count; for (int k = 0; k < 3; ++k) bary[k] = sum[k] / fn; }
+    std::thread bary_thread([&] {
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        const float* P = a->P;
+        for (size_t i = 0; i < n; ++i) { sx += P[3 * i]; sy += P[3 * i + 1]; sz += P[3 * i + 2]; }
+        sum[0] = sx; sum[1] = sy; sum[2] = sz;
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ bary_thread };
 
     const std::string id = make_id(*key);
-    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {          // same eviction as registerUpdate
-        Entry& e = *it->second;
-        if (e.gdp == key->gdp && memcmp(e.version, key->version, sizeof e.version) != 0) it = ctx->registry.erase(it);
-        else ++it;
-    }
-    auto& slot = ctx->registry[id];
-    if (!slot) slot.reset(new Entry);
-    Entry& e = *slot;
+    std::unique_ptr<Entry> ne(new Entry);          // enters the registry only after every upload and kernel was issued
+    Entry& e = *ne;
     e.gdp = key->gdp; e.vtx0 = key->vtx0; memcpy(e.version, key->version, sizeof e.version);
-    e.count = a->count; memcpy(e.origin, bary, sizeof bary);
+    e.count = a->count;
     e.active = false; e.age = -1; e.age_since_last_active = -1;
     e.has_sh = sh_found;
-    e.bbox_valid = finite;
-    for (int k = 0; k < 3; ++k) { e.bbox[k] = lo[k]; e.bbox[3 + k] = hi[k]; }
 
     // raw fp32 -> device staging, then quantise on the GPU
     DevBuf dP, dCd, dA, dS, dO, dSH;
     int rc;
+    Stager& sg = ctx->stager;
     const float* alpha_src = a->Alpha ? a->Alpha : a->opacity;                     // Alpha wins when both exist (GR.C:246-257)
-    if ((rc = upload(dP, a->P, n * 12, s))) return rc;
-    if (a->Cd && (rc = upload(dCd, a->Cd, n * 12, s))) return rc;
-    if (alpha_src && (rc = upload(dA, alpha_src, n * 4, s))) return rc;
-    if (a->scale && (rc = upload(dS, a->scale, n * 12, s))) return rc;
-    if (a->orient && (rc = upload(dO, a->orient, n * 16, s))) return rc;
+    if ((rc = upload(sg, dP, a->P, n * 12, s))) return rc;
+    if (n > 0) bbox_of(a->P, n, lo, hi, finite);
+    if (a->Cd && (rc = upload(sg, dCd, a->Cd, n * 12, s))) return rc;
+    if (alpha_src && (rc = upload(sg, dA, alpha_src, n * 4, s))) return rc;
+    if (a->scale && (rc = upload(sg, dS, a->scale, n * 12, s))) return rc;
+    if (a->orient && (rc = upload(sg, dO, a->orient, n * 16, s))) return rc;
     CU(e.pos.ensure(n * 12 + 16)); CU(e.cd.ensure(n * 6 + 16)); CU(e.alpha.ensure(n * 4 + 16));
     CU(e.scale.ensure(n * 6 + 16)); CU(e.orient.ensure(n * 8 + 16));
     launch_ingest_core(dP.as<float>(), a->Cd ? dCd.as<float>() : nullptr, alpha_src ? dA.as<float>() : nullptr,
@@ -428,23 +541,40 @@ try {
         CU(e.shx.ensure(n * 32)); CU(e.shy.ensure(n * 32)); CU(e.shz.ensure(n * 32));
         if (sh_kind == 1) {
             const size_t len = (size_t)a->sh_coefficients_len;
-            if ((rc = upload(dSH, a->sh_coefficients, n * len * 12, s))) return rc;
+            if ((rc = upload(sg, dSH, a->sh_coefficients, n * len * 12, s))) return rc;
             launch_ingest_sh_vec3(dSH.as<float>(), a->count, (int)len, 0, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
         } else if (sh_kind == 2) {
             CU(dSH.ensure(n * 15 * 12));
-            for (int j = 0; j < 15; ++j)
-                CU(cudaMemcpyAsync(dSH.as<char>() + (size_t)j * n * 12, a->sh[j], n * 12, cudaMemcpyHostToDevice, s));
+            for (int j = 0; j < 15; ++j) {
+                DevBufView v{ dSH.as<char>() + (size_t)j * n * 12 };
+                if ((rc = upload_into(sg, v.p, a->sh[j], n * 12, s))) return rc;
+            }
             launch_ingest_sh_vec3(dSH.as<float>(), a->count, 15, 1, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
         } else {
             CU(dSH.ensure(n * 45 * 4));
-            for (int j = 0; j < 45; ++j)
-                CU(cudaMemcpyAsync(dSH.as<char>() + (size_t)j * n * 4, a->f_rest[j], n * 4, cudaMemcpyHostToDevice, s));
+            for (int j = 0; j < 45; ++j) {
+                DevBufView v{ dSH.as<char>() + (size_t)j * n * 4 };
+                if ((rc = upload_into(sg, v.p, a->f_rest[j], n * 4, s))) return rc;
+            }
             launch_ingest_sh_rest(dSH.as<float>(), a->count, e.shx.as<uint16_t>(), e.shy.as<uint16_t>(), e.shz.as<uint16_t>(), s);
         }
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));          // staging buffers die here; the caller's arrays are not borrowed
-    ctx->active_set.erase(id);
+    bary_thread.join();
+    float bary[3] = { 0, 0, 0 };
+    if (n > 0) { const float fn = (float)a->count; for (int k = 0; k < 3; ++k) bary[k] = sum[k] / fn; }
+    memcpy(e.origin, bary, sizeof bary);
+    e.bbox_valid = finite;
+    for (int k = 0; k < 3; ++k) { e.bbox[k] = lo[k]; e.bbox[3 + k] = hi[k]; }
+
+    for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {          // same eviction as registerUpdate
+        Entry& o = *it->second;
+        if (o.gdp == key->gdp && memcmp(o.version, key->version, sizeof o.version) != 0) it = ctx->registry.erase(it);
+        else ++it;
+    }
+    ctx->registry[id] = std::move(ne);
+    if (ctx->active_set.count(id)) ctx->pack_dirty = true;
 
     strncpy(out->id, id.c_str(), GSB_ID_MAX - 1);
     out->sh_data_found = sh_found ? 1 : 0;
@@ -535,7 +665,8 @@ try {
     // isRenderStateRegistryCurrent (R.C:141-153)
     std::set<std::string> requested;
     for (auto& kv : ctx->registry) if (kv.second->active) requested.insert(kv.first);
-    if (requested == ctx->active_set) return GSB_OK;
+    if (requested == ctx->active_set && !ctx->pack_dirty) return GSB_OK;
+    ctx->pack_dirty = false;
 
     CU(cudaSetDevice(ctx->device));
     const int64_t cap = ctx->cap > 0 ? ctx->cap : INT64_MAX;
@@ -718,7 +849,7 @@ try {
     // A pinned, device-addressable host target receives the finished tiles directly from the blend kernel (zero-copy
     // stores over PCIe, overlapped with the binning of the deeper chunks) instead of a D2H pass after the frame.
     bool host_is_final = false;
-    if (target && target->host_rgba && !target->final_rgba && ctx->host_direct && fr->row_world == 1) {
+    if (target && target->host_rgba && !target->final_rgba && ctx->host_direct) {
         cudaPointerAttributes pa{};
         if (cudaPointerGetAttributes(&pa, target->host_rgba) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
             fb_final = static_cast<float4*>(pa.devicePointer);
@@ -906,6 +1037,8 @@ try {
         if (!host_is_final) CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
         if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
         CU(cudaStreamSynchronize(s));                  // the call returns when the frame is in host memory
+        if (ctx->counters_h[2] != 0ull)                // bounded look-back spin of a radix-sort pass timed out: the frame is not valid
+            return fail(GSB_ERR_CUDA, "radix sort look-back timed out (internal error); the delivered frame is invalid");
     } else if (tm) CU(cudaEventRecord(ctx->ev[EV_COPY], s));
     if (target && target->gl_texture != 0) {
         // hand the frame to the viewport without a host round trip: device->device copy into the mapped
@@ -1018,6 +1151,23 @@ try {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaIpcCloseMemHandle(peer_ptr));
+    return GSB_OK;
+} GSB_CATCH_ALL
+
+int gsb_host_register(gsb_context* ctx, void* host_ptr, uint64_t bytes)
+try {
+    if (!ctx || !host_ptr || !bytes) return fail(GSB_ERR_INVALID, "gsb_host_register: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return GSB_OK;
+} GSB_CATCH_ALL
+
+int gsb_host_unregister(gsb_context* ctx, void* host_ptr)
+try {
+    if (!ctx || !host_ptr) return fail(GSB_ERR_INVALID, "gsb_host_unregister: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaHostUnregister(host_ptr));
     return GSB_OK;
 } GSB_CATCH_ALL
 

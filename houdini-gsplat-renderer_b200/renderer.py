@@ -36,7 +36,7 @@ EXPORTS = ["gsb_abi_version", "gsb_create", "gsb_destroy", "gsb_last_error", "gs
            "gsb_get_stats", "gsb_set_stream", "gsb_synchronize", "gsb_device_framebuffer",
            "gsb_registry_size", "gsb_debug_fetch", "gsb_debug_sort_pairs", "gsb_debug_exclusive_scan",
            "gsb_ipc_export_frame", "gsb_ipc_open", "gsb_ipc_close", "gsb_copy_to_host",
-           "gsb_update_from_attributes", "gsb_debug_fetch_entry"]
+           "gsb_update_from_attributes", "gsb_debug_fetch_entry", "gsb_host_register", "gsb_host_unregister"]
 
 
 class GsbError(RuntimeError):
@@ -126,6 +126,8 @@ def load_library() -> C.CDLL:
         lib.gsb_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         lib.gsb_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.gsb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.gsb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.gsb_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         lib.gsb_update_from_attributes.argtypes = [C.c_void_p, C.POINTER(PrimKey), C.POINTER(RawAttributesC), C.POINTER(UpdateResultC)]
         lib.gsb_debug_fetch_entry.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = lib
@@ -315,6 +317,13 @@ class GSplatRenderer:
 
     def copy_to_host(self, device_ptr: int, host: np.ndarray):
         self._ck(self._lib.gsb_copy_to_host(self._h, device_ptr, host.ctypes.data, host.nbytes), "gsb_copy_to_host")
+
+    def host_register(self, arr: np.ndarray):
+        """Page-lock + map a page-aligned host array (cudaHostRegister) so the blend kernel can store finished tiles into it."""
+        self._ck(self._lib.gsb_host_register(self._h, arr.ctypes.data, arr.nbytes), "gsb_host_register")
+
+    def host_unregister(self, arr: np.ndarray):
+        self._ck(self._lib.gsb_host_unregister(self._h, arr.ctypes.data), "gsb_host_unregister")
 
     def stats(self) -> dict:
         s = StatsC()

@@ -29,7 +29,7 @@ extern "C" {
 #define GSB_API
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 3
 #define GSB_TILE 16                       /* screen tile edge in pixels */
 #define GSB_REFERENCE_SPLAT_CAP 8388607   /* GSPLAT_COUNT_MAX - 1, include/GSplatRenderer.h:26, src/GSplatRenderer.C:336 */
 #define GSB_ID_MAX 128                    /* bytes for a registry id string incl. NUL */
@@ -90,7 +90,9 @@ enum gsb_depth_func {
 typedef struct gsb_target {
     void*    device_rgba;    /* caller-owned device buffer, width*height*16 bytes; NULL = library buffer */
     void*    host_rgba;      /* if non-NULL the frame is delivered here (D2H inside the call, call returns when done); see
-                                GSB_OPT_HOST_DIRECT for pinned memory */
+                                GSB_OPT_HOST_DIRECT for pinned memory.  Row-partitioned frames (row_world > 1): a pinned target
+                                receives only the tiles this rank owns (the rest is left untouched, so every rank can write
+                                into one shared host frame); a pageable target receives the whole local frame (zeros elsewhere) */
     uint32_t gl_texture;     /* CUDA<->GL interop target: an RGBA32F GL_TEXTURE_2D of the frame size; the frame is copied into it
                                 device->device (cudaGraphicsGLRegisterImage).  Needs a current GL context on the calling thread
                                 (Houdini's main thread); without one the call fails with GSB_ERR_CUDA.  0 = none */
@@ -253,6 +255,12 @@ GSB_API int gsb_ipc_export_frame(gsb_context* ctx, int32_t width, int32_t height
 GSB_API int gsb_ipc_open(gsb_context* ctx, const unsigned char handle[GSB_IPC_HANDLE_BYTES], void** peer_ptr_out);
 GSB_API int gsb_ipc_close(gsb_context* ctx, void* peer_ptr);
 GSB_API int gsb_copy_to_host(gsb_context* ctx, const void* device_ptr, void* host_ptr, uint64_t bytes);  /* stream-ordered, synchronous */
+/* Page-lock a host range the caller owns (e.g. a frame in POSIX shared memory mapped by every rank of a row-partitioned
+ * job) and map it into this context's device: cudaHostRegister(Portable | Mapped).  Passed as gsb_target.host_rgba it
+ * then receives this rank's finished tiles straight from the blend kernel over the rank's own PCIe link
+ * (GSB_OPT_HOST_DIRECT); tile rows the rank does not own are left untouched.  ptr and bytes must be page aligned. */
+GSB_API int gsb_host_register(gsb_context* ctx, void* host_ptr, uint64_t bytes);
+GSB_API int gsb_host_unregister(gsb_context* ctx, void* host_ptr);
 
 /* Test hook: the arrays a registered prim holds (what registerUpdate received / update quantised). */
 enum gsb_entry_array { GSB_ENT_POS = 0, GSB_ENT_CD = 1, GSB_ENT_ALPHA = 2, GSB_ENT_SCALE = 3, GSB_ENT_ORIENT = 4,

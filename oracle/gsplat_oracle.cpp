@@ -190,8 +190,10 @@ void orc_sort(const uint32_t* keys, int64_t n, int32_t* order)
         [keys](int32_t a, int32_t b) { return keys[a] < keys[b]; });
 }
 
-/* the reference's own per-camera-move CPU stage, restated literally (R.C:188-208):
- * iota, fp32 squared distances, unstable parallel comparison sort through the index. */
+/* the reference's own per-camera-move CPU stage, restated (R.C:188-208): iota, fp32 squared distances of EVERY splat,
+ * parallel comparison sort through the index (tbb::parallel_sort there, __gnu_parallel::sort here).  The reference's
+ * comparator is dist[a] < dist[b] alone, which leaves ties to the (unstable) sort; here ties are broken by ascending
+ * index so the result is the spec's order and the frame built from it is the oracle's frame. */
 void orc_sort_reference_style(const float* pos, int64_t n, const float cam[3], int32_t* order)
 {
     std::vector<float> dist((size_t)n);
@@ -203,7 +205,7 @@ void orc_sort_reference_style(const float* pos, int64_t n, const float cam[3], i
         dist[(size_t)i] = dx * dx + dy * dy + dz * dz;
     }
     const float* d = dist.data();
-    __gnu_parallel::sort(order, order + n, [d](int32_t a, int32_t b) { return d[a] < d[b]; });
+    __gnu_parallel::sort(order, order + n, [d](int32_t a, int32_t b) { return d[a] < d[b] || (d[a] == d[b] && a < b); });
 }
 
 /* ---------------------------------------------------------------- per-splat projection */
@@ -617,12 +619,15 @@ int orc_render(const orc_frame* F, int64_t n,
     std::vector<int64_t> tile_start((size_t)TX * TY + 1);
     orc_stats s; memset(&s, 0, sizeof s); s.n_submitted = n;
     double t0 = now_ms();
+    /* time_reference_sort: the depth order comes from the reference's own CPU stage (distance of every splat + comparison
+     * argsort, R.C:176-216) and is used for the frame — one sort, as in the reference.  Otherwise: the oracle's stable
+     * sort of the keys (culled splats last).  Both give the same sequence of visible splats (NaN distances aside). */
     if (time_reference_sort) { orc_sort_reference_style(pos, n, F->cam, order.data()); s.ms_sort_reference = now_ms() - t0; }
     double t1 = now_ms();
     s.n_visible = orc_project(F, n, pos, cd_h, alpha, scale_h, orient_h, shx, shy, shz,
                               keys.data(), recs.data(), rects.data(), vis.data());
     double t2 = now_ms(); s.ms_project = t2 - t1;
-    orc_sort(keys.data(), n, order.data());
+    if (!time_reference_sort) orc_sort(keys.data(), n, order.data());
     double t3 = now_ms(); s.ms_sort = t3 - t2;
     int64_t D = orc_bin(F, n, order.data(), vis.data(), rects.data(), tile_start.data(), nullptr);
     std::vector<int32_t> inst((size_t)D);
@@ -636,6 +641,8 @@ int orc_render(const orc_frame* F, int64_t n,
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count explicitly */
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int orc_sizeof_frame(void) { return (int)sizeof(orc_frame); }
 int orc_sizeof_record(void) { return (int)sizeof(orc_record); }
 

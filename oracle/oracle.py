@@ -222,3 +222,14 @@ def build_prim(pos: np.ndarray):
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int | None = None) -> int:
+    """Use n host threads (default: every core this process may run on), whatever OMP_NUM_THREADS says."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()

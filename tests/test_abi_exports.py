@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(R.EXPORTS) == syms
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.gsb_abi_version() == 2
+    assert lib.gsb_abi_version() == 3
     assert lib.gsb_last_error() is not None
 
 
@@ -75,4 +75,4 @@ def test_python_constants_match_the_header_enums():
                 assert hasattr(R, py), f"renderer.py lacks {py}"
                 assert getattr(R, py) == val, (name, val, getattr(R, py))
     assert enums["GSB_OPT_LAZY_PROJECT"] == 9 and enums["GSB_DBG_TRECTS"] == 9 and enums["GSB_DEPTH_LEQUAL"] == 2
-    assert int(re.search(r"#define GSB_ABI_VERSION (\d+)", txt).group(1)) == 2
+    assert int(re.search(r"#define GSB_ABI_VERSION (\d+)", txt).group(1)) == 3
