@@ -4,12 +4,16 @@
  * import or execute this file.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, and only as the checker / reported baseline.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests — the reference
- * (rubendhz/houdini-gsplat-renderer @ 833a2124) ships no tests, fixtures or golden vectors
- *  and cannot be built here (needs Houdini HDK + OpenGL).  This oracle is
- * pinned instead by (1) analytic known-answer tests (tests/test_oracle_kat.py),
- * (2) an independent literal emulation of the GLSL text (oracle/glsl_literal.py), and
- * (3) golden vectors it generated itself (tests/golden/, regression pin only).
+ * PARITY STATUS: pinned to the reference's own shader text.  The reference (rubendhz/houdini-gsplat-renderer @ 833a2124)
+ * ships no tests, fixtures or golden vectors and its plugin cannot be built here (Houdini HDK +
+ * OpenGL), but its arithmetic lives in GLSL strings that CAN be compiled: oracle/_ref/libgsplat_ref.so is that text,
+ * unmodified, built as C++ (oracle/build_ref.py, glsl_cxx.h, ref_harness.cpp).  Pins:
+ *   (1) tests/test_ref_pin.py — per-splat vertex-shader outputs, whole frames, depth-tested frames and fragment-shader
+ *       known answers of the compiled reference text vs this oracle; tests/test_ref_golden.py — frames rendered by the
+ *       reference text, committed as fixtures (tests/golden/ref_*.npz + the script that made them);
+ *   (2) analytic known-answer tests (tests/test_oracle_kat.py);
+ *   (3) an independent literal emulation of the GLSL text in numpy (oracle/glsl_literal.py);
+ *   (4) golden vectors this oracle generated itself (tests/golden/g*.npz, regression pin only).
  *
  * What it restates (paths relative to /root/reference/gsplat_plugin):
  *   keys + order         src/GSplatRenderer.C:176-216   (argsortByDistance)
