@@ -245,8 +245,10 @@ emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ o
 // ranges[t] = [first, last + 1) of tile t's run in the tile-sorted instance list; four ids per thread (one 16-byte
 // load plus the two neighbours)
 __global__ void __launch_bounds__(256)
-tile_range_kernel(const uint32_t* __restrict__ ids, uint64_t d, uint2* __restrict__ ranges)
+tile_range_kernel(const uint32_t* __restrict__ ids, const uint64_t d_max, const unsigned long long* __restrict__ d_dev,
+                  uint2* __restrict__ ranges)
 {
+    const uint64_t d = d_dev ? min((unsigned long long)d_max, *d_dev) : d_max;      // the exact count lives on the device
     const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (j0 >= d) return;
     uint32_t v[6];                                           // ids[j0 - 1 .. j0 + 4]; 0xFFFFFFFF outside the list
@@ -267,6 +269,31 @@ tile_range_kernel(const uint32_t* __restrict__ ids, uint64_t d, uint2* __restric
         if (v[k] != t) ranges[t].x = (uint32_t)j;
         if (v[2 + k] != t) ranges[t].y = (uint32_t)(j + 1);
     }
+}
+
+// The spec's depth order is ascending key, ties by ascending splat index.  The live list reaches the depth
+// sort in cell order, not index order, so after the sort every run of equal keys is put in index order: element j of a run
+// [a, b) goes to a + (number of run members with a smaller index).  Runs are short (two or three splats at equal fp32
+// distance); the scan for the run's ends is bounded at TIE_MAX on either side — a run of more than TIE_MAX bit-identical
+// distances keeps the order the sort left it in (the reference's own sort leaves ties unspecified).
+constexpr int TIE_MAX = 1024;
+__global__ void __launch_bounds__(256)
+tie_fix_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t l_max,
+               const unsigned long long* __restrict__ l_dev, uint32_t* __restrict__ vals_out)
+{
+    const uint64_t l = l_dev ? min((unsigned long long)l_max, *l_dev) : l_max;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= l) return;
+    const uint32_t k = __ldg(keys + j), v = __ldg(vals + j);
+    const bool tie_l = j > 0 && __ldg(keys + j - 1) == k, tie_r = j + 1 < l && __ldg(keys + j + 1) == k;
+    if (!tie_l && !tie_r) { vals_out[j] = v; return; }
+    uint64_t a = j, b = j + 1;
+    uint32_t smaller = 0;
+    for (int t = 0; t < TIE_MAX && a > 0 && __ldg(keys + a - 1) == k; ++t) { --a; smaller += (__ldg(vals + a) < v) ? 1u : 0u; }
+    for (int t = 0; t < TIE_MAX && b < l && __ldg(keys + b) == k; ++t) { smaller += (__ldg(vals + b) < v) ? 1u : 0u; ++b; }
+    // b - a <= TIE_MAX: neither scan hit its bound, [a, b) is the whole run and every member sees the same run, so the
+    // destinations are a permutation of it.  Otherwise the run is longer than TIE_MAX for every member: all stay put.
+    vals_out[(b - a <= (uint64_t)TIE_MAX) ? a + smaller : j] = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -325,12 +352,19 @@ void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                                                            fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals);
 }
 
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
-                        cudaStream_t s)
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const unsigned long long* d_dev, uint2* ranges,
+                        int num_tiles, cudaStream_t s)
 {
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s);
-    if (d == 0) return;
-    tile_range_kernel<<<(unsigned)((d + 1023) / 1024), 256, 0, s>>>(sorted_tile_ids, d, ranges);
+    if (d_max == 0) return;
+    tile_range_kernel<<<(unsigned)((d_max + 1023) / 1024), 256, 0, s>>>(sorted_tile_ids, d_max, d_dev, ranges);
+}
+
+void launch_tie_fix(const uint32_t* keys_sorted, const uint32_t* vals_sorted, uint64_t l_max, const unsigned long long* l_dev,
+                    uint32_t* vals_out, cudaStream_t s)
+{
+    if (l_max == 0) return;
+    tie_fix_kernel<<<(unsigned)((l_max + 255) / 256), 256, 0, s>>>(keys_sorted, vals_sorted, l_max, l_dev, vals_out);
 }
 
 void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,

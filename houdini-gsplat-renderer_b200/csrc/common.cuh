@@ -86,24 +86,46 @@ size_t   scan_scratch_bytes(size_t n);
 // exclusive scan of n uint32; out may alias in.  If total_dev != nullptr the 64-bit grand total is stored there.
 void     exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
                             unsigned long long* total_dev, cudaStream_t s, int* launches);
-size_t   sort_scratch_bytes(size_t n);
-// Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit).  Ping-pongs between
-// (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).  n must be < 2^30.
-// *error_flag (device, may be NULL) is set to 1 if a bounded look-back spin ever times out.
-// aux0/aux1 (optional): a second 32-bit payload that rides along, ping-ponging like the values.
-int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                          int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
-                          uint32_t* aux0 = nullptr, uint32_t* aux1 = nullptr,
-                          uint32_t key_min = 0u, uint32_t key_span = 0xFFFFFFFFu);
+// Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit) of the squeezed key (see below).
+// Ping-pongs between (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+//   n_max      host-side upper bound of the element count (< 2^30): sizes the grid cap and the look-back table
+//   n_dev      device pointer to the real count (clamped to n_max), or NULL: n_max is the count
+//   header     sort_header_bytes() of device memory for this invocation: digit histograms + tile tickets.  Must be
+//              zero when the first kernel that touches it runs (header_is_zero = false: this call clears it itself)
+//   hist_ready the histograms in the header were already filled by the kernel that produced the keys (sort_plan gives
+//              the digit layout: pass p counts ((squeeze(key) >> shift[p]) & (2^bits[p] - 1)) at header[p * SORT_RADIX + d])
+//   lookback   sort_lookback_bytes(n_max) bytes, shared by all sorts of a stream; zero it ONCE after allocation, then
+//              never again: entries carry the epoch of the sort that wrote them.  epoch must differ from every epoch
+//              the table has seen (a counter)
+//   error_flag device word (may be NULL), set to 1 if a bounded look-back spin ever times out
+//   aux0/aux1  optional second 32-bit payload that rides along, ping-ponging like the values
 // The sort orders by min(key - key_min, key_span) (order-preserving for keys in [key_min, key_min + key_span),
 // everything above collapses onto key_span); pass end_bit = sort_key_bits(key_span) to sort only the bits that vary.
+constexpr int SORT_MAX_PASSES = 4;
+constexpr int SORT_RADIX      = 512;
+struct SortPlan { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; };
+SortPlan sort_plan(int begin_bit, int end_bit);
+size_t   sort_header_bytes();
+size_t   sort_lookback_bytes(size_t n_max);
+int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n_max,
+                          const unsigned long long* n_dev, int begin_bit, int end_bit,
+                          uint32_t* header, bool header_is_zero, bool hist_ready, unsigned long long* lookback, uint32_t epoch,
+                          uint32_t* error_flag, cudaStream_t s, int* launches,
+                          uint32_t* aux0 = nullptr, uint32_t* aux1 = nullptr,
+                          uint32_t key_min = 0u, uint32_t key_span = 0xFFFFFFFFu);
 int      sort_key_bits(uint32_t key_span);
+__host__ __device__ __forceinline__ uint32_t sort_squeeze(uint32_t key, uint32_t key_min, uint32_t key_span)
+{
+    const uint32_t d = key - key_min;
+    return d < key_span ? d : key_span;
+}
 
 // project.cu
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
                  const uint16_t* orient_h, const uint16_t* shx, const uint16_t* shy, const uint16_t* shz,
                  int64_t count, int64_t dst_offset, float4* geomA, uint4* geomB, uint4* rows, int has_sh, cudaStream_t s);
-// world-space covariance planes from geomB and the object matrix (run when the object matrix or the packed set changes)
+// world-space covariance planes (sigA / sigB, may be NULL: only the exact K1 reads them) and the eigenvalue bound lam from
+// geomB and the object matrix (run when the object matrix or the packed set changes)
 void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4* sigA, float2* sigB, float* lam, cudaStream_t s);
 // K1 (every submitted splat): cull, depth key (culled -> KEY_CULLED), packed tile rectangle (trects, may be NULL), exact
 // pixel rectangle (rects: every splat if rects_all, else only the "wide" ones the packed form cannot hold),
@@ -112,16 +134,38 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
                     uint32_t* keys, uint2* rects, int rects_all, uint32_t* trects,
                     unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
                     cudaStream_t s);
-// owned_rows (every K1/K2 launcher): NULL for a whole frame; for a row-partitioned frame owned_rows[y] = number of tile
+// owned_rows (exact K1 / K2 launchers): NULL for a whole frame; for a row-partitioned frame owned_rows[y] = number of tile
 // rows < y this rank owns (tiles_y + 1 entries), so the ownership cull is two look-ups.
-// Bounded K1 (every submitted splat, GSB_OPT_LAZY_PROJECT): the cheap exact culls (alpha, clip.w, clip.z), the exact
-// depth key, and a CONSERVATIVE packed tile rectangle — a superset of the exact one, from the centre and the bound
-// h <= min(rr, 2 sqrt 2) * sqrt(2 (|J|^2 |W|^2 lambda_max(Sigma) + 0.3)) on the quad's half extent — in ~1/5 of the exact
-// kernel's instructions and half its bytes (20 B read per splat).  Splats the bound keeps but the exact projection (K2)
-// culls get no instances.  *n_visible += splats that pass the cheap culls with a non-empty bound (an upper bound of V).
-void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
-                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
-                          cudaStream_t s);
+
+// ---- bounded K1 over spatial cells (GSB_OPT_LAZY_PROJECT, the production path; see project.cu) ----------------------
+constexpr int CELL = 256;                       // splats per cell = threads of the per-cell selection CTA
+struct CellBox { float lo[3], hi[3]; float rr_max, lam_max; };   // 32 B: box of the positions, largest discard radius
+                                                                 // (-1: nothing visible), largest eigenvalue bound (inf: unbounded)
+// pack time: Morton keys of the packed positions (bbox = min xyz, max xyz of the set); after sorting (mkeys, idx) the
+// values are the original indices in cell order (orig); geomA_p = geomA in that order
+void launch_morton(const float4* geomA, int64_t n, const float bbox[6], uint32_t* mkeys, uint32_t* idx, cudaStream_t s);
+void launch_gather_geom(const uint32_t* orig, const float4* geomA, int64_t n, float4* geomA_p, cudaStream_t s);
+// whenever lam changes (object matrix): lam in cell order + the cell boxes
+void launch_cell_build(const float4* geomA_p, const uint32_t* orig, const float* lam, int64_t n, float* lam_p, CellBox* cells,
+                       cudaStream_t s);
+// per frame: views[c] = (key_lo, key_hi, tx0 | tx1 << 16, ty0 | ty1 << 16), key_lo > key_hi = invisible; the chunk plan's
+// bucket histogram (may be NULL); *n_visible += members of the visible cells (an upper bound of V)
+void launch_cell_project(const FrameConsts& fc, const CellBox* cells, int64_t n, DepthBuckets db, uint32_t* bucket_hist,
+                         uint4* views, unsigned long long* n_visible, cudaStream_t s);
+// per depth chunk: the cells that can hold a live splat of the chunk -> sel_cells[0 .. *n_sel) (*n_sel zero before)
+void launch_cell_select(const uint4* views, int64_t n, const ChunkPlan* plan, int chunk, const FrameConsts& fc,
+                        const uint32_t* sat, uint32_t* sel_cells, uint32_t* n_sel, cudaStream_t s);
+// per depth chunk: the live splats of the selected cells -> (keys_out, vals_out = ORIGINAL index), unordered;
+// *l_total += their number, *d_total += an upper bound of their tile instances; sort_hist (zero before) receives the digit
+// histograms of the depth sort described by sp / key_min / key_span
+void launch_splat_select(const FrameConsts& fc, const float4* geomA_p, const float* lam_p, const uint32_t* orig, int64_t n,
+                         const uint32_t* sel_cells, const uint32_t* n_sel, const ChunkPlan* plan, int chunk,
+                         const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
+                         unsigned long long* l_total, unsigned long long* d_total,
+                         const SortPlan& sp, uint32_t key_min, uint32_t key_span, uint32_t* sort_hist, cudaStream_t s);
+// debug view: the bound of every packed splat, by original index (same bound_one() the selection evaluates)
+void launch_project_bound_debug(const FrameConsts& fc, const float4* geomA_p, const float* lam_p, const uint32_t* orig, int64_t n,
+                                uint32_t* keys, uint32_t* trects, cudaStream_t s);
 // chunk plan from the bucket histogram: chunk c (< nchunks - 1) ends at the first bucket whose exclusive count reaches
 // V * (2^(c+1) - 1) / 2^shift (the first chunk holds V / 2^shift splats, every further one doubles; the last takes the rest)
 // and the bucket boundaries are turned into key boundaries (plan->key_lo: the smallest key whose bucket belongs to the
@@ -160,8 +204,12 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
 void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                  const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
-void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d, uint2* ranges, int num_tiles,
-                        cudaStream_t s);
+// d_max: host-side upper bound (grid size), d_dev: the exact count on the device (NULL: d_max is exact)
+void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const unsigned long long* d_dev, uint2* ranges,
+                        int num_tiles, cudaStream_t s);
+// after the depth sort: runs of equal keys are put in ascending value (= splat index) order; keys stay where they are
+void launch_tie_fix(const uint32_t* keys_sorted, const uint32_t* vals_sorted, uint64_t l_max, const unsigned long long* l_dev,
+                    uint32_t* vals_out, cudaStream_t s);
 // debug views (GSB_OPT_KEEP_INTERMEDIATES): records by splat index, instances as splat indices
 void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,
                         const uint32_t* inst_refs, uint64_t d, uint32_t* inst_splats, cudaStream_t s);

@@ -385,7 +385,7 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
     }
 }
 
-// ---- bounded K1 (GSB_OPT_LAZY_PROJECT): persistent CTAs like project_kernel, 20 B streamed per splat.
+// ---- bounded K1 (GSB_OPT_LAZY_PROJECT): 20 B per evaluated splat.
 // Exact (the spec's operations): the alpha / clip.w / clip.z culls and the depth key.  Bounded: the pixel rectangle.
 // With T = J W (LIB.h:38-76), lambda_1 = lambda_max(T Sigma T^T) + 0.3 <= |J|_2^2 |W|_2^2 lambda_max(Sigma) + 0.3 and
 // |J|_2^2 = j0^2 (1 + rx^2 + ry^2) (J J^T = j0^2 I + j2 j2^T, j2 = -j0 (rx, ry) with the clamped ratios rx, ry), so
@@ -395,94 +395,368 @@ project_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__
 // chain is covered by the explicit margins (relative 2e-3 on the extent, 0.06 px + 2e-6 |c| on the position).
 // A splat the bound keeps and the exact projection culls (degenerate axes, empty exact rectangle) gets a zero live-tile
 // count in K2 and no instances.  NaN positions behave like the exact kernel's fmaxf/fminf: the rectangle opens up.
-__global__ void __launch_bounds__(K1_THREADS, 6)
-project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA, const float* __restrict__ lam,
-                     int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ trects,
-                     unsigned long long* __restrict__ n_visible, const DepthBuckets db, uint32_t* __restrict__ bucket_hist,
-                     const uint32_t* __restrict__ owned_rows)
+struct Bound { bool vis; uint32_t key; int tx0, tx1, ty0, ty1; };
+__device__ __forceinline__ Bound bound_one(const FrameConsts& F, const float4 ga, const float lm)
+{
+    Bound o; o.key = KEY_CULLED; o.tx0 = 1; o.tx1 = 0; o.ty0 = 1; o.ty1 = 0;
+    const float p[3] = { ga.x, ga.y, ga.z };
+    const float rr = ga.w;
+    bool vis = rr >= 0.0f;
+    float psx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; psx[k] = t + F.origin[k]; }
+    float vc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
+    const float fy = -vc[1];
+    float clip[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
+    const float cw = clip[3];
+    vis = vis && (cw > 0.0f) && (clip[2] >= -cw && clip[2] <= cw);
+    if (vis) {
+        // (from here on nothing has to match the exact chain bit for bit: fused multiply-adds, MUFU approximations)
+        const float iw = __fdividef(1.0f, cw);
+        const float hw = 0.5f * F.W, hh = 0.5f * F.H;
+        const float cx = fmaf(clip[0] * iw, hw, hw);
+        const float cy = fmaf((-clip[1]) * iw, hh, hh);
+        float t[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            t[r] = fmaf(MAT(F.view, r, 0), psx[0], fmaf(MAT(F.view, r, 1), psx[1], fmaf(MAT(F.view, r, 2), psx[2], MAT(F.view, r, 3))));
+        const float itz = __fdividef(1.0f, t[2]);
+        const float rx = fminf(fmaxf(t[0] * itz, -F.lim_x), F.lim_x) * 1.0001f;
+        const float ry = fminf(fmaxf(t[1] * itz, -F.lim_y), F.lim_y) * 1.0001f;
+        const float j0 = F.focal * itz;
+        const float nj2 = (j0 * j0) * fmaf(ry, ry, fmaf(rx, rx, 1.0f));
+        const float l1 = fmaf((nj2 * F.wnorm2) * 1.002f, lm, 0.3006f);       // >= lambda_1 of the exact chain
+        float s1; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(2.0f * l1));
+        s1 = fminf(s1 * 1.0005f, 4096.0f);
+        float hb = (fminf(rr, 2.8284272f) * s1) * 1.001f + 0.06f;
+        if (!(hb <= 1.0e9f)) hb = 1.0e9f;                                   // inf / NaN bound: the whole screen
+        const float hbx = fmaf(2.0e-6f, fabsf(cx), hb), hby = fmaf(2.0e-6f, fabsf(cy), hb);
+        const float x0f = fmaxf(ceilf((cx - hbx) - 0.5f), 0.0f);
+        const float x1f = fminf(floorf((cx + hbx) - 0.5f), F.W - 1.0f);
+        const float y0f = fmaxf(ceilf((cy - hby) - 0.5f), 0.0f);
+        const float y1f = fminf(floorf((cy + hby) - 0.5f), F.H - 1.0f);
+        vis = (x0f <= x1f) && (y0f <= y1f);
+        if (vis) {
+            static_assert(TILE == 16, "tile shift");
+            o.tx0 = (int)((unsigned)x0f >> 4); o.tx1 = (int)((unsigned)x1f >> 4);       // 0 <= x <= 65535
+            o.ty0 = (int)((unsigned)y0f >> 4); o.ty1 = (int)((unsigned)y1f >> 4);
+            const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
+            o.key = __float_as_uint(dx * dx + dy * dy + dz * dz);
+        }
+    }
+    o.vis = vis;
+    return o;
+}
+
+// Debug view of the bound (gsb_debug_fetch GSB_DBG_TRECTS / GSB_DBG_KEYS_UNSORTED with the bounded K1): the bound of EVERY
+// packed splat, written at its original index.  The frame path never runs this; splat_select_kernel evaluates the same
+// bound_one() only for the splats of the cells a depth chunk selects.
+__global__ void __launch_bounds__(K1_THREADS)
+project_bound_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA_p, const float* __restrict__ lam_p,
+                     const uint32_t* __restrict__ orig, int64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ trects)
+{
+    const int64_t p = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const Bound b = bound_one(F, __ldg(geomA_p + p), __ldg(lam_p + p));
+    const uint32_t i = __ldg(orig + p);
+    keys[i] = b.key;
+    trects[i] = b.vis ? pack_trect(b.tx0, b.tx1, b.ty0, b.ty1) : TRECT_CULLED;
+}
+
+// ------------------------------------------------------------------------------------ spatial cells (r02)
+// At pack time the active set is ordered along a Morton curve and cut into cells of CELL consecutive splats; only the
+// 20-byte K1 stream (position + discard radius, eigenvalue bound) and the original index are stored in that order, the
+// 128-byte lines K2 gathers stay where they were.  A cell keeps the bounding box of its positions, its largest discard
+// radius and its largest eigenvalue bound.  Per frame ONE thread per cell projects the box: a conservative tile
+// rectangle (the corner projections grown by the largest extent any member can have: bound_one's formula with the cell's
+// worst-case operands) and a conservative depth-key interval.  A depth chunk then evaluates bound_one() only for the
+// members of cells whose interval meets the chunk's and whose rectangle still holds a live tile — the two 8-byte-per-
+// splat streams per chunk and the 28-byte-per-splat K1 stream of r01 shrink to the cells that can matter (and, for a
+// row-partitioned frame, to the cells that touch the rank's rows: the N-proportional work no longer repeats on every GPU).
+// Selection order no longer follows the splat index, so ties of the depth sort are put in index order afterwards
+// (tie_fix_kernel): the spec's order (ascending key, ties ascending index) is unchanged.
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v)      // 10 bits -> every third bit
+{
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+struct MortonBox { float lo[3]; float inv[3]; };             // quantisation: q = (p - lo) * inv, 10 bits per axis
+
+__global__ void __launch_bounds__(256)
+morton_kernel(const float4* __restrict__ geomA, int64_t n, const MortonBox mb, uint32_t* __restrict__ mkeys, uint32_t* __restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 g = __ldg(geomA + i);
+    const float q[3] = { (g.x - mb.lo[0]) * mb.inv[0], (g.y - mb.lo[1]) * mb.inv[1], (g.z - mb.lo[2]) * mb.inv[2] };
+    uint32_t key = 0x3FFFFFFFu;                               // non-finite positions go last (their cells are flagged)
+    if (q[0] == q[0] && q[1] == q[1] && q[2] == q[2]) {
+        const uint32_t a = (uint32_t)fminf(fmaxf(q[0], 0.0f), 1023.0f), b = (uint32_t)fminf(fmaxf(q[1], 0.0f), 1023.0f),
+                       c = (uint32_t)fminf(fmaxf(q[2], 0.0f), 1023.0f);
+        key = spread10(a) | (spread10(b) << 1) | (spread10(c) << 2);
+    }
+    mkeys[i] = key; idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+gather_geom_kernel(const uint32_t* __restrict__ orig, const float4* __restrict__ geomA, int64_t n, float4* __restrict__ geomA_p)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) geomA_p[p] = __ldg(geomA + __ldg(orig + p));
+}
+
+// one CTA per cell: lam in cell order, and the cell's box / largest discard radius / largest eigenvalue bound
+__global__ void __launch_bounds__(CELL)
+cell_build_kernel(const float4* __restrict__ geomA_p, const uint32_t* __restrict__ orig, const float* __restrict__ lam,
+                  int64_t n, float* __restrict__ lam_p, CellBox* __restrict__ cells)
+{
+    __shared__ float red[CELL / 32][8];
+    __shared__ uint32_t bad[CELL / 32];
+    const int64_t p = (int64_t)blockIdx.x * CELL + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }, rr = -1.0f, lm = 0.0f;
+    uint32_t nonfinite = 0u;
+    if (p < n) {
+        const float4 g = __ldg(geomA_p + p);
+        lm = __ldg(lam + __ldg(orig + p));
+        lam_p[p] = lm;
+        const float q[3] = { g.x, g.y, g.z };
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (fabsf(q[k]) <= 3.0e38f) { lo[k] = q[k]; hi[k] = q[k]; } else nonfinite = 1u;
+        }
+        rr = g.w;
+        if (!(lm >= 0.0f && lm <= 3.0e38f)) { lm = __int_as_float(0x7f800000); }      // inf / NaN eigenvalue bound: whole screen
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+        lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+        nonfinite |= __shfl_xor_sync(0xffffffffu, nonfinite, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; }
+        red[warp][6] = rr; red[warp][7] = lm; bad[warp] = nonfinite;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CellBox c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { c.lo[k] = red[0][k]; c.hi[k] = red[0][3 + k]; }
+        c.rr_max = red[0][6]; c.lam_max = red[0][7]; uint32_t nf = bad[0];
+        for (int w = 1; w < CELL / 32; ++w) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c.lo[k] = fminf(c.lo[k], red[w][k]); c.hi[k] = fmaxf(c.hi[k], red[w][3 + k]); }
+            c.rr_max = fmaxf(c.rr_max, red[w][6]); c.lam_max = fmaxf(c.lam_max, red[w][7]); nf |= bad[w];
+        }
+        if (c.lo[0] > c.hi[0] || c.lo[1] > c.hi[1] || c.lo[2] > c.hi[2]) nf = 1u;       // no finite position at all
+        if (nf) c.lam_max = __int_as_float(0x7f800000);                                   // flagged: whole screen, every key
+        cells[blockIdx.x] = c;
+    }
+}
+
+// per frame, one thread per cell: conservative tile rectangle + depth-key interval (CellView), the chunk plan's histogram
+// (cell population at the bucket of the interval's middle) and the visible-splat estimate
+__global__ void __launch_bounds__(256)
+cell_project_kernel(const __grid_constant__ FrameConsts F, const CellBox* __restrict__ cells, const int64_t ncells, const int64_t n,
+                    const DepthBuckets db, uint32_t* __restrict__ bucket_hist, uint4* __restrict__ views,
+                    unsigned long long* __restrict__ n_visible)
 {
     __shared__ uint32_t sh_hist[DEPTH_BUCKETS];
     if (bucket_hist) {
-        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) sh_hist[b] = 0u;
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += 256) sh_hist[b] = 0u;
         __syncthreads();
     }
-    uint32_t nvis = 0;
-    const int64_t stride = (int64_t)gridDim.x * K1_THREADS;
-    int64_t i = (int64_t)blockIdx.x * K1_THREADS + threadIdx.x;
-    float4 ga_next = make_float4(0.f, 0.f, 0.f, -1.f); float lm_next = 0.f;
-    if (i < n) { ga_next = __ldg(geomA + i); lm_next = __ldg(lam + i); }
-    for (; i < n; i += stride) {
-        const float4 ga = ga_next; const float lm = lm_next;
-        if (i + stride < n) { ga_next = __ldg(geomA + i + stride); lm_next = __ldg(lam + i + stride); }
-        const float p[3] = { ga.x, ga.y, ga.z };
-        const float rr = ga.w;
-        uint32_t key = KEY_CULLED, tr = TRECT_CULLED;
-        bool vis = rr >= 0.0f;
-        float psx[3];
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t pop = 0;
+    if (c < ncells) {
+        const CellBox cb = cells[c];
+        uint4 view = make_uint4(1u, 0u, 1u, 1u);                 // klo > khi: never selected; rectangle empty
+        const int64_t left = n - c * CELL;
+        const uint32_t members = (uint32_t)(left < CELL ? left : CELL);
+        if (cb.rr_max >= 0.0f) {
+            const bool flagged = !(cb.lam_max <= 3.0e38f) && !(cb.lo[0] <= cb.hi[0]);      // non-finite positions inside
+            bool whole = !(cb.lam_max <= 3.0e38f);                                         // unbounded extent: the whole screen
+            float lo[3], hi[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { float t = p[k] - F.origin[k]; psx[k] = t + F.origin[k]; }
-        float vc[3];
+            for (int k = 0; k < 3; ++k) {                            // room for the (P - origin) + origin round trip and fp32 slop
+                const float m = 4.0e-7f * (fabsf(cb.lo[k]) + fabsf(cb.hi[k]) + fabsf(F.origin[k])) + 1.0e-30f;
+                lo[k] = cb.lo[k] - m; hi[k] = cb.hi[k] + m;
+            }
+            // depth-key interval: squared distance from the camera to the box, nearest and farthest point
+            float dmin2 = 0.0f, dmax2 = 0.0f;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-            vc[r] = ((MAT(F.obj_view, r, 0) * psx[0] + MAT(F.obj_view, r, 1) * psx[1]) + MAT(F.obj_view, r, 2) * psx[2]) + MAT(F.obj_view, r, 3);
-        const float fy = -vc[1];
-        float clip[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            clip[r] = ((MAT(F.proj, r, 0) * vc[0] + MAT(F.proj, r, 1) * fy) + MAT(F.proj, r, 2) * vc[2]) + MAT(F.proj, r, 3);
-        const float cw = clip[3];
-        vis = vis && (cw > 0.0f) && (clip[2] >= -cw && clip[2] <= cw);
-        if (vis) {
-            // (from here on nothing has to match the exact chain bit for bit: fused multiply-adds, MUFU approximations)
-            const float iw = __fdividef(1.0f, cw);
+            for (int k = 0; k < 3; ++k) {
+                const float a = lo[k] - F.cam[k], b = F.cam[k] - hi[k];
+                const float nr = fmaxf(fmaxf(a, b), 0.0f), fr = fmaxf(fabsf(F.cam[k] - lo[k]), fabsf(F.cam[k] - hi[k]));
+                dmin2 = fmaf(nr, nr, dmin2); dmax2 = fmaf(fr, fr, dmax2);
+            }
+            uint32_t klo = __float_as_uint(fmaxf(dmin2 * (1.0f - 2.0e-5f), 0.0f));
+            uint32_t khi = (dmax2 <= 3.0e38f) ? __float_as_uint(dmax2 * (1.0f + 2.0e-5f)) : 0x7F800000u;
+            if (!(dmin2 == dmin2) || !(dmax2 == dmax2) || flagged || !(cb.lo[0] <= cb.hi[0])) { klo = 0u; khi = KEY_CULLED - 1u; whole = true; }
+            // the eight corners: centre range on screen, nearest view-space depth
+            float cxmin = 3.0e38f, cxmax = -3.0e38f, cymin = 3.0e38f, cymax = -3.0e38f, tzmin = 3.0e38f, tzmax = -3.0e38f;
             const float hw = 0.5f * F.W, hh = 0.5f * F.H;
-            const float cx = fmaf(clip[0] * iw, hw, hw);
-            const float cy = fmaf((-clip[1]) * iw, hh, hh);
-            float t[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-                t[r] = fmaf(MAT(F.view, r, 0), psx[0], fmaf(MAT(F.view, r, 1), psx[1], fmaf(MAT(F.view, r, 2), psx[2], MAT(F.view, r, 3))));
-            const float itz = __fdividef(1.0f, t[2]);
-            const float rx = fminf(fmaxf(t[0] * itz, -F.lim_x), F.lim_x) * 1.0001f;
-            const float ry = fminf(fmaxf(t[1] * itz, -F.lim_y), F.lim_y) * 1.0001f;
-            const float j0 = F.focal * itz;
-            const float nj2 = (j0 * j0) * fmaf(ry, ry, fmaf(rx, rx, 1.0f));
-            const float l1 = fmaf((nj2 * F.wnorm2) * 1.002f, lm, 0.3006f);       // >= lambda_1 of the exact chain
-            float s1; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(2.0f * l1));
-            s1 = fminf(s1 * 1.0005f, 4096.0f);
-            float hb = (fminf(rr, 2.8284272f) * s1) * 1.001f + 0.06f;
-            if (!(hb <= 1.0e9f)) hb = 1.0e9f;                                   // inf / NaN bound: the whole screen
-            const float hbx = fmaf(2.0e-6f, fabsf(cx), hb), hby = fmaf(2.0e-6f, fabsf(cy), hb);
-            const float x0f = fmaxf(ceilf((cx - hbx) - 0.5f), 0.0f);
-            const float x1f = fminf(floorf((cx + hbx) - 0.5f), F.W - 1.0f);
-            const float y0f = fmaxf(ceilf((cy - hby) - 0.5f), 0.0f);
-            const float y1f = fminf(floorf((cy + hby) - 0.5f), F.H - 1.0f);
-            vis = (x0f <= x1f) && (y0f <= y1f);
-            if (vis) {
-                static_assert(TILE == 16, "tile shift");
-                const int tx0 = (int)((unsigned)x0f >> 4), tx1 = (int)((unsigned)x1f >> 4);       // 0 <= x <= 65535
-                const int ty0 = (int)((unsigned)y0f >> 4), ty1 = (int)((unsigned)y1f >> 4);
-                if (owned_rows) vis = __ldg(owned_rows + ty1 + 1) != __ldg(owned_rows + ty0);
-                if (vis) {
-                    const float dx = p[0] - F.cam[0], dy = p[1] - F.cam[1], dz = p[2] - F.cam[2];
-                    key = __float_as_uint(dx * dx + dy * dy + dz * dz);
-                    tr = pack_trect(tx0, tx1, ty0, ty1);
-                    ++nvis;
+            for (int q = 0; q < 8; ++q) {
+                const float px = (q & 1) ? hi[0] : lo[0], py = (q & 2) ? hi[1] : lo[1], pz = (q & 4) ? hi[2] : lo[2];
+                float vc[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    vc[r] = fmaf(MAT(F.obj_view, r, 0), px, fmaf(MAT(F.obj_view, r, 1), py, fmaf(MAT(F.obj_view, r, 2), pz, MAT(F.obj_view, r, 3))));
+                const float fy = -vc[1];
+                const float c0 = fmaf(MAT(F.proj, 0, 0), vc[0], fmaf(MAT(F.proj, 0, 1), fy, fmaf(MAT(F.proj, 0, 2), vc[2], MAT(F.proj, 0, 3))));
+                const float c1 = fmaf(MAT(F.proj, 1, 0), vc[0], fmaf(MAT(F.proj, 1, 1), fy, fmaf(MAT(F.proj, 1, 2), vc[2], MAT(F.proj, 1, 3))));
+                const float c3 = fmaf(MAT(F.proj, 3, 0), vc[0], fmaf(MAT(F.proj, 3, 1), fy, fmaf(MAT(F.proj, 3, 2), vc[2], MAT(F.proj, 3, 3))));
+                const float tz = fmaf(MAT(F.view, 2, 0), px, fmaf(MAT(F.view, 2, 1), py, fmaf(MAT(F.view, 2, 2), pz, MAT(F.view, 2, 3))));
+                if (!(c3 > 1.0e-20f)) whole = true;                 // the box reaches the camera plane (or NaN)
+                const float iw = 1.0f / c3;
+                const float cx = fmaf(c0 * iw, hw, hw), cy = fmaf((-c1) * iw, hh, hh);
+                cxmin = fminf(cxmin, cx); cxmax = fmaxf(cxmax, cx); cymin = fminf(cymin, cy); cymax = fmaxf(cymax, cy);
+                tzmin = fminf(tzmin, tz); tzmax = fmaxf(tzmax, tz);
+                if (!(cx == cx) || !(cy == cy) || !(tz == tz)) whole = true;
+            }
+            if (!(tzmin > 0.0f) && !(tzmax < 0.0f)) whole = true;   // view-space depth changes sign inside the box: |J| unbounded
+            int tx0 = 0, tx1 = F.tiles_x - 1, ty0 = 0, ty1 = F.tiles_y - 1;
+            bool empty = false;
+            if (!whole) {
+                const float az = fminf(fabsf(tzmin), fabsf(tzmax));
+                const float itz = (1.0f / az) * 1.00001f;
+                const float j0 = F.focal * itz;
+                const float nj2 = (j0 * j0) * (1.0f + 1.0003f * (F.lim_x * F.lim_x + F.lim_y * F.lim_y));
+                const float l1 = (nj2 * F.wnorm2) * 1.003f * cb.lam_max + 0.3006f;
+                const float s1 = fminf(sqrtf(2.0f * l1) * 1.001f, 4096.0f);
+                float hb = (fminf(cb.rr_max, 2.8284272f) * s1) * 1.002f + 0.1f;
+                if (!(hb <= 1.0e9f)) hb = 1.0e9f;
+                const float hbx = hb + 4.0e-6f * fmaxf(fabsf(cxmin), fabsf(cxmax)) + 0.1f;
+                const float hby = hb + 4.0e-6f * fmaxf(fabsf(cymin), fabsf(cymax)) + 0.1f;
+                const float x0f = fmaxf(ceilf((cxmin - hbx) - 0.5f), 0.0f), x1f = fminf(floorf((cxmax + hbx) - 0.5f), F.W - 1.0f);
+                const float y0f = fmaxf(ceilf((cymin - hby) - 0.5f), 0.0f), y1f = fminf(floorf((cymax + hby) - 0.5f), F.H - 1.0f);
+                if (!(x0f <= x1f) || !(y0f <= y1f)) empty = true;
+                else {
+                    tx0 = (int)((unsigned)x0f >> 4); tx1 = (int)((unsigned)x1f >> 4);
+                    ty0 = (int)((unsigned)y0f >> 4); ty1 = (int)((unsigned)y1f >> 4);
                 }
             }
+            if (!empty) {
+                view = make_uint4(klo, khi, (uint32_t)tx0 | ((uint32_t)tx1 << 16), (uint32_t)ty0 | ((uint32_t)ty1 << 16));
+                pop = members;
+                if (bucket_hist) atomicAdd(&sh_hist[depth_bucket((klo >> 1) + (khi >> 1), db)], members);
+            }
         }
-        keys[i] = key;
-        trects[i] = tr;
-        if (bucket_hist) atomicAdd(&sh_hist[depth_bucket(key, db)], 1u);
+        views[c] = view;
     }
-    nvis = __reduce_add_sync(0xffffffffu, nvis);
-    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(n_visible, (unsigned long long)nvis);
+    pop = __reduce_add_sync(0xffffffffu, pop);
+    if ((threadIdx.x & 31) == 0 && pop) atomicAdd(n_visible, (unsigned long long)pop);
     if (bucket_hist) {
         __syncthreads();
-        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += K1_THREADS) {
-            const uint32_t c = sh_hist[b];
-            if (c) atomicAdd(bucket_hist + b, c);
+        for (int b = threadIdx.x; b < DEPTH_BUCKETS; b += 256) {
+            const uint32_t v = sh_hist[b];
+            if (v) atomicAdd(bucket_hist + b, v);
         }
+    }
+}
+
+// per depth chunk, one thread per cell: cells whose key interval meets the chunk's and whose rectangle holds a live tile
+__global__ void __launch_bounds__(256)
+cell_select_kernel(const uint4* __restrict__ views, const int64_t ncells, const ChunkPlan* __restrict__ plan, const int chunk,
+                   const int tiles_x, const uint32_t* __restrict__ sat, uint32_t* __restrict__ sel_cells, uint32_t* __restrict__ n_sel)
+{
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t key_lo = plan ? __ldg(&plan->key_lo[chunk]) : 0u;
+    const uint32_t key_hi = plan ? __ldg(&plan->key_lo[chunk + 1]) : KEY_CULLED;
+    bool sel = false;
+    if (c < ncells) {
+        const uint4 v = __ldg(views + c);
+        if (v.x <= v.y && v.y >= key_lo && v.x < key_hi)
+            sel = live_tiles((int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu), (int)(v.w >> 16), tiles_x, sat) != 0u;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(n_sel, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (sel) sel_cells[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)c;
+    }
+}
+
+// per depth chunk: bound_one() for the members of the selected cells; the splats whose key lies in the chunk's interval
+// and whose bound holds a live tile are appended (key, ORIGINAL index) to the live list, their number and instance bound
+// are accumulated, and the digit histograms of the depth sort that follows are built on the way (no pass over the keys).
+// Persistent CTAs; one CTA handles one cell at a time (thread t = member t).
+struct SelectSort { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; uint32_t key_min, key_span; };
+__global__ void __launch_bounds__(CELL)
+splat_select_kernel(const __grid_constant__ FrameConsts F, const float4* __restrict__ geomA_p, const float* __restrict__ lam_p,
+                    const uint32_t* __restrict__ orig, const int64_t n, const uint32_t* __restrict__ sel_cells,
+                    const uint32_t* __restrict__ n_sel, const ChunkPlan* __restrict__ plan, const int chunk,
+                    const uint32_t* __restrict__ sat, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                    unsigned long long* __restrict__ l_total, unsigned long long* __restrict__ d_total,
+                    const SelectSort ss, uint32_t* __restrict__ sort_hist)
+{
+    __shared__ uint32_t sh_hist[SORT_MAX_PASSES][SORT_RADIX];
+    __shared__ uint32_t s_wl[CELL / 32], s_wd[CELL / 32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_MAX_PASSES * SORT_RADIX; i += CELL) (&sh_hist[0][0])[i] = 0u;
+    const uint32_t key_lo = plan ? __ldg(&plan->key_lo[chunk]) : 0u;
+    const uint32_t key_hi = plan ? __ldg(&plan->key_lo[chunk + 1]) : KEY_CULLED;
+    const uint32_t nsel = *n_sel;
+    __syncthreads();
+    for (uint32_t s = blockIdx.x; s < nsel; s += gridDim.x) {
+        const int64_t p = (int64_t)__ldg(sel_cells + s) * CELL + threadIdx.x;
+        uint32_t cnt = 0, key = KEY_CULLED;
+        if (p < n) {
+            const Bound b = bound_one(F, __ldg(geomA_p + p), __ldg(lam_p + p));
+            key = b.key;
+            if (b.vis && key >= key_lo && key < key_hi) cnt = live_tiles(b.tx0, b.tx1, b.ty0, b.ty1, F.tiles_x, sat);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cnt != 0u);
+        const uint32_t dsum = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) { s_wl[warp] = (uint32_t)__popc(m); s_wd[warp] = dsum; }
+        __syncthreads();
+        uint32_t wbase = 0, l = 0, d = 0;
+#pragma unroll
+        for (int w = 0; w < CELL / 32; ++w) { wbase += (w < warp) ? s_wl[w] : 0u; l += s_wl[w]; d += s_wd[w]; }
+        if (threadIdx.x == 0 && l) {
+            s_base = atomicAdd(l_total, (unsigned long long)l);
+            atomicAdd(d_total, (unsigned long long)d);
+        }
+        __syncthreads();
+        if (cnt != 0u) {
+            const size_t o = (size_t)s_base + wbase + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            keys_out[o] = key; vals_out[o] = __ldg(orig + p);
+            const uint32_t q = sort_squeeze(key, ss.key_min, ss.key_span);
+#pragma unroll
+            for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
+                if (ps < ss.passes) atomicAdd(&sh_hist[ps][(q >> ss.shift[ps]) & ((1u << ss.bits[ps]) - 1u)], 1u);
+        }
+        // (s_wl / s_wd / s_base are rewritten only after the next iteration's first barrier... no: s_wl is written before
+        // it; this barrier keeps a fast warp of the next iteration from overwriting what a slow warp still reads)
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ss.passes * SORT_RADIX; i += CELL) {
+        const uint32_t v = (&sh_hist[0][0])[i];
+        if (v) atomicAdd(sort_hist + i, v);
     }
 }
 
@@ -522,8 +796,10 @@ sigma_kernel(const __grid_constant__ ObjMat O, const uint4* __restrict__ geomB, 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Sigma sg = sigma_of(O.m, __ldg(geomB + i));
-    sigA[i] = make_float4(sg.s[0], sg.s[1], sg.s[2], sg.s[3]);
-    sigB[i] = make_float2(sg.s[4], sg.s[5]);
+    if (sigA) {                                             // the covariance planes are only read by the exact K1
+        sigA[i] = make_float4(sg.s[0], sg.s[1], sg.s[2], sg.s[3]);
+        sigB[i] = make_float2(sg.s[4], sg.s[5]);
+    }
     lam[i] = lambda_max_upper(sg);
 }
 
@@ -661,19 +937,72 @@ void launch_sigma(const float object[16], const uint4* geomB, int64_t n, float4*
     sigma_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, geomB, n, sigA, sigB, lam);
 }
 
-void launch_project_bound(const FrameConsts& fc, const PackedSplats& ps, int64_t n, uint32_t* keys, uint32_t* trects,
-                          unsigned long long* n_visible, DepthBuckets db, uint32_t* bucket_hist, const uint32_t* owned_rows,
-                          cudaStream_t s)
+void launch_project_bound_debug(const FrameConsts& fc, const float4* geomA_p, const float* lam_p, const uint32_t* orig, int64_t n,
+                                uint32_t* keys, uint32_t* trects, cudaStream_t s)
+{
+    if (n <= 0) return;
+    project_bound_kernel<<<(unsigned)((n + K1_THREADS - 1) / K1_THREADS), K1_THREADS, 0, s>>>(fc, geomA_p, lam_p, orig, n, keys, trects);
+}
+
+void launch_morton(const float4* geomA, int64_t n, const float bbox[6], uint32_t* mkeys, uint32_t* idx, cudaStream_t s)
+{
+    if (n <= 0) return;
+    MortonBox mb;
+    for (int k = 0; k < 3; ++k) {
+        const float ext = bbox[3 + k] - bbox[k];
+        mb.lo[k] = bbox[k];
+        mb.inv[k] = (ext > 0.0f && ext <= 3.0e38f) ? 1024.0f / ext : 0.0f;
+    }
+    morton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(geomA, n, mb, mkeys, idx);
+}
+
+void launch_gather_geom(const uint32_t* orig, const float4* geomA, int64_t n, float4* geomA_p, cudaStream_t s)
+{
+    if (n <= 0) return;
+    gather_geom_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(orig, geomA, n, geomA_p);
+}
+
+void launch_cell_build(const float4* geomA_p, const uint32_t* orig, const float* lam, int64_t n, float* lam_p, CellBox* cells,
+                       cudaStream_t s)
+{
+    if (n <= 0) return;
+    cell_build_kernel<<<(unsigned)((n + CELL - 1) / CELL), CELL, 0, s>>>(geomA_p, orig, lam, n, lam_p, cells);
+}
+
+void launch_cell_project(const FrameConsts& fc, const CellBox* cells, int64_t n, DepthBuckets db, uint32_t* bucket_hist,
+                         uint4* views, unsigned long long* n_visible, cudaStream_t s)
+{
+    if (n <= 0) return;
+    const int64_t ncells = (n + CELL - 1) / CELL;
+    cell_project_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, s>>>(fc, cells, ncells, n, db, bucket_hist, views, n_visible);
+}
+
+void launch_cell_select(const uint4* views, int64_t n, const ChunkPlan* plan, int chunk, const FrameConsts& fc,
+                        const uint32_t* sat, uint32_t* sel_cells, uint32_t* n_sel, cudaStream_t s)
+{
+    if (n <= 0) return;
+    const int64_t ncells = (n + CELL - 1) / CELL;
+    cell_select_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, s>>>(views, ncells, plan, chunk, fc.tiles_x, sat, sel_cells, n_sel);
+}
+
+void launch_splat_select(const FrameConsts& fc, const float4* geomA_p, const float* lam_p, const uint32_t* orig, int64_t n,
+                         const uint32_t* sel_cells, const uint32_t* n_sel, const ChunkPlan* plan, int chunk,
+                         const uint32_t* sat, uint32_t* keys_out, uint32_t* vals_out,
+                         unsigned long long* l_total, unsigned long long* d_total,
+                         const SortPlan& sp, uint32_t key_min, uint32_t key_span, uint32_t* sort_hist, cudaStream_t s)
 {
     if (n <= 0) return;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_bound_kernel, K1_THREADS, 0);
-        if (rc != cudaSuccess || per_sm < 1) per_sm = 6;
+        cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_select_kernel, CELL, 0);
+        if (rc != cudaSuccess || per_sm < 1) per_sm = 4;
     }
-    const int64_t want = (n + K1_THREADS - 1) / K1_THREADS, cap = (int64_t)NUM_SMS * per_sm;
-    project_bound_kernel<<<(unsigned)(want < cap ? want : cap), K1_THREADS, 0, s>>>(fc, ps.geomA, ps.lam, n, keys, trects,
-                                                                                   n_visible, db, bucket_hist, owned_rows);
+    const int64_t ncells = (n + CELL - 1) / CELL, cap = (int64_t)NUM_SMS * per_sm;
+    SelectSort ss{};
+    ss.passes = sp.passes; ss.key_min = key_min; ss.key_span = key_span;
+    for (int p = 0; p < sp.passes; ++p) { ss.shift[p] = sp.shift[p]; ss.bits[p] = sp.bits[p]; }
+    splat_select_kernel<<<(unsigned)(ncells < cap ? ncells : cap), CELL, 0, s>>>(fc, geomA_p, lam_p, orig, n, sel_cells, n_sel, plan, chunk,
+                                                                               sat, keys_out, vals_out, l_total, d_total, ss, sort_hist);
 }
 
 void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,

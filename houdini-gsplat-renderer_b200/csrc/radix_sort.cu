@@ -15,6 +15,14 @@
 // Safety: tiles take their index from an atomic ticket, so a tile only ever waits on tiles that already
 // started; every spin is bounded and raises an error flag instead of hanging the GPU.
 //
+// r02: the frame pipeline never learns element counts on the host in time, so (i) every kernel reads n from DEVICE memory
+// (n_dev; the host only supplies an upper bound for the scratch size), (ii) the pass kernel is PERSISTENT: <= 2 CTAs per SM
+// loop over ticketed tiles, so a loose upper bound costs no empty CTAs, (iii) look-back entries are 64-bit, tagged with a
+// per-sort EPOCH in the high word: entries of earlier sorts read as "not published" and the table is never cleared,
+// (iv) the exclusive scan of the digit histogram happens at the start of every pass CTA (one block scan of <= 512 bins)
+// instead of in a kernel of its own, and (v) the histogram itself may be supplied by the kernel that produced the keys
+// (hist_ready), which removes the upfront pass over them.
+//
 // Ranking inside a warp needs, per key, the mask of lanes holding the same digit.  match.any does that in one
 // instruction but runs on the ADU pipe at ~2 cycles per DISTINCT value (ncu r01: ADU 97 % busy, 62 cycles per
 // warp for random digits), so the mask is built from one vote.ballot per digit bit instead (<= 8 ballots + LOP3).
@@ -48,6 +56,7 @@ constexpr uint32_t LB_MASK = 0x3FFFFFFFu;   // counts < 2^30
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 struct PassPlan { int shift[RS_MAX_PASSES]; int bits[RS_MAX_PASSES]; int passes; uint32_t key_min, key_span; };
+static_assert(RS_MAX_PASSES == SORT_MAX_PASSES && RS_RADIX == SORT_RADIX, "common.cuh mirrors the sort's table shape");
 
 // dynamic shared memory of os_pass_kernel
 struct PassSmem {
@@ -56,6 +65,7 @@ struct PassSmem {
     uint32_t global_delta[RS_RADIX];    // global offset of digit d for this tile - local_base[d]
     uint32_t tot[RS_RADIX];             // tile total per digit
     uint32_t excl[RS_RADIX];            // look-back result per digit
+    uint32_t digit_base[RS_RADIX];      // exclusive scan of the pass's global digit histogram (once per CTA)
     uint32_t wtot[RS_WARPS];
     uint32_t tile;
     uint32_t sk[RS_TILE];
@@ -67,13 +77,13 @@ __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
 }
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p)
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p)
 {
-    uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+    unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v)
+__device__ __forceinline__ void st_volatile(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Order-preserving key compression: keys below key_min + key_span keep their order after subtracting key_min,
@@ -113,9 +123,11 @@ __device__ __forceinline__ size_t item_index(size_t base, int warp, int lane, in
 // ---- upfront: global digit histograms of all passes, one read of the keys --------------------------------
 // hist layout: [pass][RS_RADIX].  Persistent CTAs, shared-memory REDs, one global RED per non-zero bin per CTA.
 __global__ void __launch_bounds__(RS_THREADS)
-os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint32_t* __restrict__ hist)
+os_hist_kernel(const uint32_t* __restrict__ keys, size_t n_max, const unsigned long long* __restrict__ n_dev, PassPlan plan,
+               uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t h[RS_MAX_PASSES][RS_RADIX];
+    const size_t n = n_dev ? (size_t)min((unsigned long long)n_max, *n_dev) : n_max;
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&h[0][0])[i] = 0u;
     __syncthreads();
     const size_t stride = (size_t)gridDim.x * RS_THREADS;
@@ -132,33 +144,17 @@ os_hist_kernel(const uint32_t* __restrict__ keys, size_t n, PassPlan plan, uint3
     }
 }
 
-// exclusive scan of each pass's RS_RADIX bins, in place (one CTA of RS_RADIX threads per pass)
-__global__ void __launch_bounds__(RS_RADIX) os_scan_hist_kernel(uint32_t* __restrict__ hist)
-{
-    __shared__ uint32_t wtot[RS_RADIX / 32];
-    uint32_t* h = hist + (size_t)blockIdx.x * RS_RADIX;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t v = h[threadIdx.x];
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < RS_RADIX / 32; ++w) woff += (w < warp) ? wtot[w] : 0u;
-    h[threadIdx.x] = woff + inc - v;
-}
-
 // ---- one pass ------------------------------------------------------------------------------------------------
-// lookback layout: [tile][nbins]: a tile publishes one coalesced row; a look-back step reads LB_WIN rows.
+// lookback layout: [tile][nbins] 64-bit entries (epoch << 32 | flags | count): a tile publishes one coalesced row; a
+// look-back step reads LB_WIN rows.  Persistent: every CTA loops over ticketed tiles until the tickets run out.
 template <int NBITS, class DigitFn>
 __global__ void __launch_bounds__(RS_THREADS, GSB_RS_MINB)
 os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-               const DigitFn dig, const uint32_t* __restrict__ digit_base,
-               uint32_t* __restrict__ lookback, unsigned num_tiles, uint32_t* __restrict__ ticket,
-               uint32_t* __restrict__ error_flag,
+               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const size_t n_max,
+               const unsigned long long* __restrict__ n_dev,
+               const DigitFn dig, const uint32_t* __restrict__ hist,
+               unsigned long long* __restrict__ lookback, uint32_t* __restrict__ ticket,
+               uint32_t* __restrict__ error_flag, const uint32_t epoch,
                const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ aux_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,132 +163,158 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nbins = 1 << NBITS;
     const unsigned lt = lanemask_lt();
-    if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-
-    const size_t base = (size_t)tile * RS_TILE;
-    const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
-    uint32_t k[RS_ITEMS], v[RS_ITEMS];
-    uint16_t rank[RS_ITEMS];
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        size_t idx = item_index(base, warp, lane, j);
-        bool valid = idx < n;
-        k[j] = valid ? __ldg(keys_in + idx) : 0u;
-        v[j] = valid ? __ldg(vals_in + idx) : 0u;
-    }
+    const size_t n = n_dev ? (size_t)min((unsigned long long)n_max, *n_dev) : n_max;
+    const unsigned num_tiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
+    const unsigned long long etag = (unsigned long long)epoch << 32;
     const bool has_aux = aux_in != nullptr;
 
-    // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
+    // global digit offsets of this pass: exclusive scan of the histogram, once per CTA
+    {
+        const uint32_t hv = ((int)threadIdx.x < nbins) ? __ldg(hist + threadIdx.x) : 0u;
+        uint32_t inc = hv;
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        size_t idx = item_index(base, warp, lane, j);
-        bool valid = idx < n;
-        uint32_t d = dig(k[j]);
-        unsigned peers = match_digit<NBITS>(d, valid);
-        uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
-        __syncwarp();
-        if (valid && lane == (__ffs(peers) - 1)) sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers));
-        __syncwarp();
-        rank[j] = (uint16_t)(pre + __popc(peers & lt));
+        for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
+        if (lane == 31) sm.wtot[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
+        if ((int)threadIdx.x < nbins) sm.digit_base[threadIdx.x] = woff + inc - hv;
+        __syncthreads();
     }
-    __syncthreads();
 
-    // thread d: exclusive prefix over warps for digit d, tile total for d; publish the aggregate
-    uint32_t total = 0;
-    if ((int)threadIdx.x < nbins) {
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = sm.cnt[w][threadIdx.x]; sm.cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
-        sm.tot[threadIdx.x] = total;
-        st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, total | (tile == 0 ? LB_INCL : LB_AGG));
-        if (tile == 0) sm.excl[threadIdx.x] = 0u;
-    }
-    // exclusive scan of the digit totals across the block
-    uint32_t inc = total;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
-    if (lane == 31) sm.wtot[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
-    if ((int)threadIdx.x < nbins) sm.local_base[threadIdx.x] = woff + inc - total;
-    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
+        for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        if (tile >= num_tiles) break;                                   // CTA-uniform
 
-    // reorder through shared memory so each digit's run is contiguous (needs no global information, and lets the
-    // key/value/rank registers die before the look-back)
+        const size_t base = (size_t)tile * RS_TILE;
+        const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
+        uint32_t k[RS_ITEMS], v[RS_ITEMS];
+        uint16_t rank[RS_ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        size_t idx = item_index(base, warp, lane, j);
-        if (idx < n) {
-            uint32_t d = dig(k[j]);
-            uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
-            sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
-            if (has_aux) sm.sa[lp] = __ldg(aux_in + idx);       // the payload rides along (loaded late: short live range)
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            size_t idx = item_index(base, warp, lane, j);
+            bool valid = idx < n;
+            k[j] = valid ? __ldg(keys_in + idx) : 0u;
+            v[j] = valid ? __ldg(vals_in + idx) : 0u;
         }
-    }
 
-    // Decoupled look-back, one thread per digit, LB_WIN predecessors per step: the LB_WIN volatile loads of a step are
-    // independent (one L2 round trip), rows of the [tile][digit] table are read coalesced across the warp.  With a window
-    // this wide the chain of not-yet-inclusive predecessors stays shorter than one window (equilibrium: resident tiles x
-    // round trip / (window x tile time) < 1); a narrow or serial walk lets it grow to the number of resident tiles.
-    if (tile > 0 && (int)threadIdx.x < nbins) {
-        const uint32_t* col = lookback + threadIdx.x;
-        uint32_t excl = 0, spins = 0;
-        int t = (int)tile - 1;
-        bool done = false;
-        while (!done) {
-            uint32_t val[LB_WIN];
+        // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
 #pragma unroll
-            for (int j = 0; j < LB_WIN; ++j)
-                val[j] = (t - j >= 0) ? ld_volatile(col + (size_t)(t - j) * nbins) : LB_INCL;
-            int used = 0;
-            bool blocked = false;
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            size_t idx = item_index(base, warp, lane, j);
+            bool valid = idx < n;
+            uint32_t d = dig(k[j]);
+            unsigned peers = match_digit<NBITS>(d, valid);
+            uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
+            __syncwarp();
+            if (valid && lane == (__ffs(peers) - 1)) sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers));
+            __syncwarp();
+            rank[j] = (uint16_t)(pre + __popc(peers & lt));
+        }
+        __syncthreads();
+
+        // thread d: exclusive prefix over warps for digit d, tile total for d; publish the aggregate
+        uint32_t total = 0;
+        if ((int)threadIdx.x < nbins) {
 #pragma unroll
-            for (int j = 0; j < LB_WIN; ++j) {
-                if (!done && !blocked) {
-                    if ((val[j] & (LB_AGG | LB_INCL)) == 0u) blocked = true;          // not published yet: retry from here
-                    else { excl += val[j] & LB_MASK; ++used; done = (val[j] & LB_INCL) != 0u; }
+            for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = sm.cnt[w][threadIdx.x]; sm.cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
+            sm.tot[threadIdx.x] = total;
+            st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, etag | total | (tile == 0 ? LB_INCL : LB_AGG));
+            if (tile == 0) sm.excl[threadIdx.x] = 0u;
+        }
+        // exclusive scan of the digit totals across the block
+        uint32_t inc = total;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
+        if (lane == 31) sm.wtot[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
+        if ((int)threadIdx.x < nbins) sm.local_base[threadIdx.x] = woff + inc - total;
+        __syncthreads();
+
+        // reorder through shared memory so each digit's run is contiguous (needs no global information, and lets the
+        // key/value/rank registers die before the look-back)
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            size_t idx = item_index(base, warp, lane, j);
+            if (idx < n) {
+                uint32_t d = dig(k[j]);
+                uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
+                sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
+                if (has_aux) sm.sa[lp] = __ldg(aux_in + idx);       // the payload rides along (loaded late: short live range)
+            }
+        }
+
+        // Decoupled look-back, one thread per digit, LB_WIN predecessors per step: the LB_WIN volatile loads of a step are
+        // independent (one L2 round trip), rows of the [tile][digit] table are read coalesced across the warp.  With a window
+        // this wide the chain of not-yet-inclusive predecessors stays shorter than one window (equilibrium: resident tiles x
+        // round trip / (window x tile time) < 1); a narrow or serial walk lets it grow to the number of resident tiles.
+        // An entry whose epoch word is not this sort's is a leftover of an earlier sort: not published yet.
+        if (tile > 0 && (int)threadIdx.x < nbins) {
+            const unsigned long long* col = lookback + threadIdx.x;
+            uint32_t excl = 0, spins = 0;
+            int t = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long val[LB_WIN];
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j)
+                    val[j] = (t - j >= 0) ? ld_volatile(col + (size_t)(t - j) * nbins) : (etag | LB_INCL);
+                int used = 0;
+                bool blocked = false;
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j) {
+                    if (!done && !blocked) {
+                        const uint32_t lo = (uint32_t)val[j];
+                        if ((uint32_t)(val[j] >> 32) != epoch || (lo & (LB_AGG | LB_INCL)) == 0u) blocked = true;   // not published yet: retry from here
+                        else { excl += lo & LB_MASK; ++used; done = (lo & LB_INCL) != 0u; }
+                    }
+                }
+                t -= used;
+                if (blocked) {
+                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); break; }
+                    __nanosleep(20);
                 }
             }
-            t -= used;
-            if (blocked) {
-                if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); break; }
-                __nanosleep(20);
-            }
+            sm.excl[threadIdx.x] = excl;
+            st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, etag | ((excl + total) & LB_MASK) | LB_INCL);
         }
-        sm.excl[threadIdx.x] = excl;
-        st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, ((excl + total) & LB_MASK) | LB_INCL);
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < nbins)
-        sm.global_delta[threadIdx.x] = digit_base[threadIdx.x] + sm.excl[threadIdx.x] - sm.local_base[threadIdx.x];
-    __syncthreads();
+        __syncthreads();
+        if ((int)threadIdx.x < nbins)
+            sm.global_delta[threadIdx.x] = sm.digit_base[threadIdx.x] + sm.excl[threadIdx.x] - sm.local_base[threadIdx.x];
+        __syncthreads();
 
 #pragma unroll
-    for (int t = 0; t < RS_ITEMS; ++t) {
-        uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
-        if (i < tile_count) {
-            uint32_t key = sm.sk[i];
-            uint32_t d = dig(key);
-            size_t o = (size_t)(sm.global_delta[d] + i);
-            keys_out[o] = key; vals_out[o] = sm.sv[i];
-            if (has_aux) aux_out[o] = sm.sa[i];
+        for (int t = 0; t < RS_ITEMS; ++t) {
+            uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
+            if (i < tile_count) {
+                uint32_t key = sm.sk[i];
+                uint32_t d = dig(key);
+                size_t o = (size_t)(sm.global_delta[d] + i);
+                keys_out[o] = key; vals_out[o] = sm.sv[i];
+                if (has_aux) aux_out[o] = sm.sa[i];
+            }
         }
+        __syncthreads();                                                // smem is reused by the next ticket
     }
 }
 }  // namespace
 
 static inline size_t rs_blocks(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 
-// scratch layout: [hist 4*512 u32][tickets 4 u32][error flag ...][pad to 256 B][lookback passes * 512 * blocks u32]
-static inline size_t os_header_bytes() { return ((RS_MAX_PASSES * RS_RADIX + 8) * sizeof(uint32_t) + 255) & ~size_t(255); }
+// header of one sort invocation: [hist passes x 512 u32][tickets 4 u32][spare 4 u32], zero before its first use
+size_t sort_header_bytes() { return ((RS_MAX_PASSES * RS_RADIX + 8) * sizeof(uint32_t) + 255) & ~size_t(255); }
 
-size_t sort_scratch_bytes(size_t n)
+// look-back table for sorts of up to n_max elements: passes x tiles x 512 bins x 8 bytes (never cleared: epoch tagged)
+size_t sort_lookback_bytes(size_t n_max)
 {
-    return os_header_bytes() + (size_t)RS_MAX_PASSES * rs_blocks(n) * (RS_RADIX / 2) * sizeof(uint32_t) * 2 + 256;
+    return (size_t)RS_MAX_PASSES * (rs_blocks(n_max) + 1) * RS_RADIX * sizeof(unsigned long long) + 256;
 }
 
 int sort_key_bits(uint32_t key_span)
@@ -300,47 +322,65 @@ int sort_key_bits(uint32_t key_span)
     int b = 0; while (b < 32 && (key_span >> b) != 0u) ++b; return b < 1 ? 1 : b;
 }
 
-int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n,
-                     int begin_bit, int end_bit, void* scratch, uint32_t* error_flag, cudaStream_t s, int* launches,
+SortPlan sort_plan(int begin_bit, int end_bit)
+{
+    SortPlan p{};
+    int bits_left = end_bit - begin_bit;
+    if (bits_left <= 0) return p;
+    const int p8 = (bits_left + 7) / 8, p9 = (bits_left + 8) / 9;
+    p.passes = p9 < p8 ? p9 : p8;          // 9-bit digits only when they save a whole pass
+    int shift = begin_bit;
+    for (int i = 0; i < p.passes; ++i) {
+        int b = (bits_left + (p.passes - i) - 1) / (p.passes - i);
+        p.shift[i] = shift; p.bits[i] = b; shift += b; bits_left -= b;
+    }
+    return p;
+}
+
+int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n_max,
+                     const unsigned long long* n_dev, int begin_bit, int end_bit,
+                     uint32_t* header, bool header_is_zero, bool hist_ready, unsigned long long* lookback, uint32_t epoch,
+                     uint32_t* error_flag, cudaStream_t s, int* launches,
                      uint32_t* aux0, uint32_t* aux1, uint32_t key_min, uint32_t key_span)
 {
-    if (n == 0 || end_bit <= begin_bit) return 0;
+    if (n_max == 0 || end_bit <= begin_bit) return 0;
     static bool attr_set = false;
+    static int pass_ctas_per_sm = GSB_RS_MINB;
     if (!attr_set) {
 #define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
         GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
         GSB_SET_ATTR(8); GSB_SET_ATTR(9);
 #undef GSB_SET_ATTR
+        int per = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, BitsDigit>, RS_THREADS, sizeof(PassSmem)) == cudaSuccess && per >= 1)
+            pass_ctas_per_sm = per;
         attr_set = true;
     }
-    const unsigned nb = (unsigned)rs_blocks(n);
+    const unsigned nb = (unsigned)rs_blocks(n_max);
+    const SortPlan sp = sort_plan(begin_bit, end_bit);
     PassPlan plan{};
-    plan.key_min = key_min; plan.key_span = key_span;
-    int bits_left = end_bit - begin_bit;
-    const int p8 = (bits_left + 7) / 8, p9 = (bits_left + 8) / 9;
-    plan.passes = p9 < p8 ? p9 : p8;          // 9-bit digits only when they save a whole pass
-    int shift = begin_bit;
-    for (int p = 0; p < plan.passes; ++p) {
-        int b = (bits_left + (plan.passes - p) - 1) / (plan.passes - p);
-        plan.shift[p] = shift; plan.bits[p] = b; shift += b; bits_left -= b;
-    }
-    uint32_t* hist = static_cast<uint32_t*>(scratch);
+    plan.key_min = key_min; plan.key_span = key_span; plan.passes = sp.passes;
+    for (int p = 0; p < sp.passes; ++p) { plan.shift[p] = sp.shift[p]; plan.bits[p] = sp.bits[p]; }
+    uint32_t* hist = header;
     uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
     if (!error_flag) error_flag = tickets + RS_MAX_PASSES;      // nobody looks: still a valid sink
-    uint32_t* lookback = reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + os_header_bytes());
     size_t lb_off[RS_MAX_PASSES + 1]; lb_off[0] = 0;
     for (int p = 0; p < plan.passes; ++p) lb_off[p + 1] = lb_off[p] + ((size_t)nb << plan.bits[p]);
-    cudaMemsetAsync(scratch, 0, os_header_bytes() + lb_off[plan.passes] * sizeof(uint32_t), s);
-    const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
-    os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n, plan, hist);
-    os_scan_hist_kernel<<<plan.passes, RS_RADIX, 0, s>>>(hist);
+    if (!header_is_zero) { cudaMemsetAsync(header, 0, sort_header_bytes(), s); if (launches) *launches += 0; }
+    if (!hist_ready) {
+        const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
+        os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n_max, n_dev, plan, hist);
+        if (launches) *launches += 1;
+    }
+    const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
+    const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     uint32_t* ain = aux0; uint32_t* aout = aux1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
-#define GSB_PASS(B) case B: os_pass_kernel<B, BitsDigit><<<nb, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n, \
-                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], nb, \
-                        tickets + p, error_flag, ain, aout); break
+#define GSB_PASS(B) case B: os_pass_kernel<B, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n_max, n_dev, \
+                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], \
+                        tickets + p, error_flag, epoch, ain, aout); break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
         }
@@ -351,7 +391,7 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
         t = ain; ain = aout; aout = t;
         cur ^= 1;
     }
-    if (launches) *launches += 2 + plan.passes;
+    if (launches) *launches += plan.passes;
     return cur;
 }
 

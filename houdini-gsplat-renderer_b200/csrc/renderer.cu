@@ -180,13 +180,23 @@ struct gsb_context {
 
     // packed render-layout attributes
     DevBuf geomA, geomB, rows, sigA, sigB, lam;
-    bool   sigma_valid = false;                      // sigA/sigB match the packed set and sigma_object
+    bool   sigma_valid = false;                      // lam (and the cell boxes) match the packed set and sigma_object
+    bool   sigma_planes_valid = false;               // ... and so do sigA / sigB (only the exact K1 reads them)
     float  sigma_object[16] = {};
+    // spatial cells of the bounded K1 (built by gsb_generate_render_geometry): the K1 stream in Morton order
+    DevBuf geomA_p, lam_p, orig, cells, cell_views, sel_cells;
+    DevBuf arena;                                    // per-frame counters, histograms, sort headers, tile flags: ONE memset per frame
+    DevBuf lookback;                                 // radix-sort look-back table (epoch tagged, cleared on allocation only)
+    uint32_t sort_epoch = 0;
+    cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
+    std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
+    FrameConsts last_fc{}; bool last_lazy = false;   // for the on-demand debug view of the bound
+    uint32_t* last_tile_consumed = nullptr;
 
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
     // lkeys/lvals: the live splats of the current chunk (ping-pong of their depth sort); ltiles: their tile rectangles (K2).
     DevBuf keys, trects, lkeys[2], lvals[2], ltiles, recs, rects, counts, ikeys[2], ivals[2],
-           ranges, tile_consumed, tile_done, live_sat, owned_rows, fb, plan, bucket_hist;
+           ranges, live_sat, owned_rows, fb, plan;
     DevBuf zdepth, scene_depth_buf;                  // scene-depth occlusion: window depth per live rank; GL depth copy
     struct cudaGraphicsResource* gl_depth_res = nullptr; uint32_t gl_depth_tex = 0; int gl_depth_w = 0, gl_depth_h = 0;
     DevBuf dbg_recs, dbg_inst;                       // GSB_OPT_KEEP_INTERMEDIATES views (by splat index)
@@ -194,9 +204,10 @@ struct gsb_context {
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
     Stager stager;                                   // pinned double-buffered staging of the cold-path uploads
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
-    DevBuf sort_scratch, scan_scratch, counters;     // counters: [0]=V, [1]=D, [2]=D_c  (u64 each)
-    unsigned long long* counters_h = nullptr;        // pinned mirror
-    int order_buf = 0, inst_buf = 0;
+    DevBuf scan_scratch;
+    unsigned long long* counters_h = nullptr;        // pinned mirror: [0..8) frame counters, [8..16) the current chunk's, [16..) every chunk's at frame end
+    int order_buf = 0, order_vals_buf = 0, inst_buf = 0;
+    int chunks_last = 0;
     int64_t last_live = 0;                           // live splats of the last depth chunk
     int64_t last_n = 0, last_sorted = 0; uint64_t last_d = 0; int last_tiles = 0; int last_w = 0, last_h = 0;
     float4* last_fb = nullptr;
@@ -316,6 +327,8 @@ double sym3_lambda_max(const double g[3][3])
 
 int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
 
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
 }  // namespace
 
 // Nothing may throw across the C ABI (std::bad_alloc from the registry's containers, std::length_error, ...): every
@@ -324,6 +337,27 @@ int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
     catch (const std::bad_alloc&) { return fail(GSB_ERR_NOMEM, "out of host memory"); }                   \
     catch (const std::exception& e_) { return fail(GSB_ERR_INVALID, std::string("internal error: ") + e_.what()); } \
     catch (...) { return fail(GSB_ERR_INVALID, "internal error: unknown exception"); }
+
+// look-back table of the radix sorts: entries carry the epoch of the sort that wrote them, so the table is cleared only
+// when it is (re)allocated or when the 32-bit epoch counter wraps
+static int ensure_lookback(gsb_context* ctx, size_t n_max)
+{
+    const size_t need = sort_lookback_bytes(n_max);
+    if (need > ctx->lookback.cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(ctx->lookback.ensure(need));
+        CU(cudaMemsetAsync(ctx->lookback.p, 0, ctx->lookback.cap, ctx->stream));
+    }
+    return GSB_OK;
+}
+static uint32_t next_epoch(gsb_context* ctx)
+{
+    if (ctx->sort_epoch >= 0xFFFFFFF0u) {
+        if (ctx->lookback.p) cudaMemsetAsync(ctx->lookback.p, 0, ctx->lookback.cap, ctx->stream);
+        ctx->sort_epoch = 0;
+    }
+    return ++ctx->sort_epoch;
+}
 
 // ============================================================================== C ABI
 extern "C" {
@@ -352,10 +386,10 @@ try {
     c->stream = c->own_stream;
     for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) CU(cudaEventCreate(&c->evc[i][j]));
-    CU(c->counters.ensure(64));
-    CU(cudaMallocHost(&c->counters_h, 64));
-    memset(c->counters_h, 0, 64);
-    CU(c->plan.ensure(sizeof(ChunkPlan))); CU(c->bucket_hist.ensure(DEPTH_BUCKETS * 4));
+    CU(cudaEventCreateWithFlags(&c->ev_sel, cudaEventDisableTiming));
+    CU(cudaMallocHost(&c->counters_h, (16 + MAX_CHUNKS * 8) * 8));
+    memset(c->counters_h, 0, (16 + MAX_CHUNKS * 8) * 8);
+    CU(c->plan.ensure(sizeof(ChunkPlan)));
     *out = c.release();
     return GSB_OK;
 } GSB_CATCH_ALL
@@ -370,6 +404,7 @@ try {
     for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 16; ++i) for (int j = 0; j < 5; ++j) if (ctx->evc[i][j]) cudaEventDestroy(ctx->evc[i][j]);
     if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+    if (ctx->ev_sel) cudaEventDestroy(ctx->ev_sel);
     cudaStream_t s = ctx->own_stream;
     delete ctx;
     if (s) cudaStreamDestroy(s);
@@ -722,7 +757,31 @@ try {
         offset += cnt;
     }
     CU(cudaGetLastError());
-    ctx->sigma_valid = false;
+    // spatial cells of the bounded K1: order the set along a Morton curve (30-bit keys over the set's bounding box), keep
+    // the original index of every position of that order, and lay the K1 stream (position + discard radius) out in it.
+    // The cell boxes depend on the eigenvalue bounds, i.e. on the object matrix: gsb_render builds them with lam.
+    {
+        const int64_t ncells = ((int64_t)n + CELL - 1) / CELL;
+        CU(ctx->geomA_p.ensure(n * 16)); CU(ctx->lam_p.ensure(n * 4)); CU(ctx->orig.ensure(n * 4 + 16));
+        CU(ctx->cells.ensure((size_t)ncells * sizeof(CellBox))); CU(ctx->cell_views.ensure((size_t)ncells * 16));
+        CU(ctx->sel_cells.ensure((size_t)ncells * 4 + 16));
+        DevBuf mk[2], mi[2], hdr;
+        for (int b = 0; b < 2; ++b) { CU(mk[b].ensure(n * 4 + 16)); CU(mi[b].ensure(n * 4 + 16)); }
+        CU(hdr.ensure(sort_header_bytes()));
+        int rc2 = ensure_lookback(ctx, n);
+        if (rc2) return rc2;
+        float bb[6] = { 0, 0, 0, 0, 0, 0 };
+        if (ctx->bbox_valid) memcpy(bb, ctx->bbox, sizeof bb);          // invalid box: every key 0, the order stays the index order
+        launch_morton(ctx->geomA.as<float4>(), (int64_t)n, bb, mk[0].as<uint32_t>(), mi[0].as<uint32_t>(), ctx->stream);
+        const int cur = radix_sort_pairs(mk[0].as<uint32_t>(), mi[0].as<uint32_t>(), mk[1].as<uint32_t>(), mi[1].as<uint32_t>(), n, nullptr,
+                                         0, 30, hdr.as<uint32_t>(), false, false, ctx->lookback.as<unsigned long long>(),
+                                         next_epoch(ctx), nullptr, ctx->stream, nullptr);
+        CU(cudaMemcpyAsync(ctx->orig.p, mi[cur].p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        launch_gather_geom(ctx->orig.as<uint32_t>(), ctx->geomA.as<float4>(), (int64_t)n, ctx->geomA_p.as<float4>(), ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));                          // the temporaries die here
+    }
+    ctx->sigma_valid = false; ctx->sigma_planes_valid = false;
     ctx->can_render = true;
     ctx->stats.repacked = 1;
     return GSB_OK;
@@ -825,21 +884,21 @@ try {
     const int key_bits = sort_key_bits(key_span);
 
     // buffers
-    // packed tile rectangles ride along as a payload (screens up to 512 x 512 tiles); otherwise exact rectangles by index
+    // exact K1 only: packed tile rectangles ride along as a payload (screens up to 512 x 512 tiles); otherwise exact rectangles by index
     const bool use_trects = fc.tiles_x <= 512 && fc.tiles_y <= 512;
-    // bounded K1: conservative tile rectangles for every splat, the exact projection only in K2 for the splats a chunk
-    // selects.  The debug views (exact rectangles by splat index) and huge screens keep the exact K1.
-    const bool lazy = ctx->lazy_project && !ctx->keep_intermediates && use_trects &&
+    // bounded K1 over spatial cells (production): conservative tile rectangles, evaluated only for the members of the cells
+    // a depth chunk selects; the exact projection runs in K2 for the splats that were selected.  The debug views (exact
+    // rectangles by splat index) keep the exact K1 for every splat.
+    const bool lazy = ctx->lazy_project && !ctx->keep_intermediates &&
                       std::isfinite(fc.lim_x) && std::isfinite(fc.lim_y) && std::isfinite(fc.focal) && std::isfinite(fc.wnorm2);
-    CU(ctx->keys.ensure(N * 4));
-    if (use_trects) CU(ctx->trects.ensure(N * 4));
-    if (!lazy) CU(ctx->rects.ensure(N * 8));
-    CU(ctx->counts.ensure(N * 4 + 16));
-    CU(ctx->sort_scratch.ensure(sort_scratch_bytes(N)));
+    if (!lazy) {
+        CU(ctx->keys.ensure(N * 4));
+        if (use_trects) CU(ctx->trects.ensure(N * 4));
+        CU(ctx->rects.ensure(N * 8));
+    }
     CU(ctx->scan_scratch.ensure(std::max(scan_scratch_bytes(N), select_scratch_bytes(n))));
-    CU(ctx->ranges.ensure((size_t)num_tiles * 8)); CU(ctx->tile_consumed.ensure((size_t)num_tiles * 4));
+    CU(ctx->ranges.ensure((size_t)num_tiles * 8));
     const size_t done_bytes = (size_t)done_words_per_row(fc.tiles_x) * (size_t)fc.tiles_y * 4;      // one bit per tile
-    CU(ctx->tile_done.ensure(done_bytes));
     CU(ctx->live_sat.ensure((size_t)(fc.tiles_x + 1) * (size_t)(fc.tiles_y + 1) * 4));
     float4* fb = nullptr;
     const size_t fb_bytes = (size_t)fr->width * fr->height * 16;
@@ -881,42 +940,70 @@ try {
         }
     }
 
-    unsigned long long* cnt = ctx->counters.as<unsigned long long>();     // [0] V [1] D_c [2] sort/scan error [3] done tiles [4] D [5] L [6] scan total
+    // ---- the frame arena: every counter, histogram, sort header and tile flag of the frame, cleared by ONE memset.
+    //   [0, 64)                    frame counters (u64): [0] V  [1] D_c  [2] sort error flag  [3] finished tiles
+    //   [64, 64 + 64 MAX_CHUNKS)   per depth chunk (u64): [0] L  [1] bound of D (selection)  [2] selected cells (u32)  [3] D (exact)
+    //   bucket histogram of the chunk plan, 2 sort headers per chunk, tile_done bit map, tile_consumed
+    const size_t hdr_bytes = sort_header_bytes();
+    const size_t off_chunk = 64, off_hist = off_chunk + (size_t)MAX_CHUNKS * 64, off_sort = align256(off_hist + DEPTH_BUCKETS * 4),
+                 off_done = off_sort + (size_t)MAX_CHUNKS * 2 * hdr_bytes, off_cons = align256(off_done + done_bytes),
+                 arena_bytes = off_cons + (size_t)num_tiles * 4;
+    CU(ctx->arena.ensure(arena_bytes));
+    char* const arena = ctx->arena.as<char>();
     const bool tm = ctx->stage_timing;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_START], s));
-    CU(cudaMemsetAsync(cnt, 0, 64, s));
+    CU(cudaMemsetAsync(arena, 0, arena_bytes, s));
+    unsigned long long* const cnt = reinterpret_cast<unsigned long long*>(arena);
+    uint32_t* const tile_done = reinterpret_cast<uint32_t*>(arena + off_done);
+    uint32_t* const tile_consumed = reinterpret_cast<uint32_t*>(arena + off_cons);
+    ctx->last_tile_consumed = tile_consumed;
+    {
+        int rc2 = ensure_lookback(ctx, N);
+        if (rc2) return rc2;
+    }
 
-    // K1: cull + depth key + tile rectangle for every submitted splat (+ the depth-bucket histogram)
-    if (!ctx->sigma_valid || memcmp(ctx->sigma_object, fr->object, 64) != 0) {      // the covariance cache follows the object matrix
-        CU(ctx->sigA.ensure(N * 16)); CU(ctx->sigB.ensure(N * 8)); CU(ctx->lam.ensure(N * 4));
-        launch_sigma(fr->object, ctx->geomB.as<uint4>(), n, ctx->sigA.as<float4>(), ctx->sigB.as<float2>(), ctx->lam.as<float>(), s);
+    // eigenvalue bounds (and, for the exact K1, the covariance planes) follow the object matrix; so do the cell boxes
+    const bool object_changed = memcmp(ctx->sigma_object, fr->object, 64) != 0;
+    if (!ctx->sigma_valid || object_changed || (!lazy && !ctx->sigma_planes_valid)) {
+        CU(ctx->lam.ensure(N * 4));
+        if (!lazy) { CU(ctx->sigA.ensure(N * 16)); CU(ctx->sigB.ensure(N * 8)); }
+        launch_sigma(fr->object, ctx->geomB.as<uint4>(), n, lazy ? nullptr : ctx->sigA.as<float4>(),
+                     lazy ? nullptr : ctx->sigB.as<float2>(), ctx->lam.as<float>(), s);
+        launch_cell_build(ctx->geomA_p.as<float4>(), ctx->orig.as<uint32_t>(), ctx->lam.as<float>(), n, ctx->lam_p.as<float>(),
+                          ctx->cells.as<CellBox>(), s);
         memcpy(ctx->sigma_object, fr->object, 64);
         ctx->sigma_valid = true;
-        st.launches += 1;
+        ctx->sigma_planes_valid = !lazy;
+        st.launches += 2;
     }
-    // row-partitioned frame: prefix count of the tile rows this rank owns (the ownership cull of K1 / K2)
+    // row-partitioned frame, exact K1 / K2: prefix count of the tile rows this rank owns (cached per partition)
     const uint32_t* owned_rows = nullptr;
     if (fr->row_world > 1) {
-        std::vector<uint32_t> pre((size_t)fc.tiles_y + 1, 0u);
-        for (int ty = 0; ty < fc.tiles_y; ++ty) pre[ty + 1] = pre[ty] + (owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1u : 0u);
-        CU(ctx->owned_rows.ensure(pre.size() * 4));
-        CU(cudaMemcpyAsync(ctx->owned_rows.p, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));                   // pre is a local: the copy must have left it
+        const int key4[4] = { fc.tiles_y, fc.row_rank, fc.row_world, fc.row_group };
+        if (memcmp(key4, ctx->owned_key, sizeof key4) != 0) {
+            CU(cudaStreamSynchronize(s));                   // nothing in flight reads the old table
+            ctx->owned_rows_h.assign((size_t)fc.tiles_y + 1, 0u);
+            for (int ty = 0; ty < fc.tiles_y; ++ty)
+                ctx->owned_rows_h[ty + 1] = ctx->owned_rows_h[ty] + (owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1u : 0u);
+            CU(ctx->owned_rows.ensure(ctx->owned_rows_h.size() * 4));
+            CU(cudaMemcpyAsync(ctx->owned_rows.p, ctx->owned_rows_h.data(), ctx->owned_rows_h.size() * 4, cudaMemcpyHostToDevice, s));
+            memcpy(ctx->owned_key, key4, sizeof key4);
+        }
         owned_rows = ctx->owned_rows.as<uint32_t>();
     }
     PackedSplats ps{ ctx->geomA.as<float4>(), ctx->geomB.as<uint4>(), ctx->rows.as<uint4>(), ctx->sigA.as<float4>(),
                      ctx->sigB.as<float2>(), ctx->lam.as<float>() };
-    uint32_t* bucket_hist = nchunks > 1 ? ctx->bucket_hist.as<uint32_t>() : nullptr;
-    if (bucket_hist) CU(cudaMemsetAsync(bucket_hist, 0, DEPTH_BUCKETS * 4, s));
-    if (lazy) launch_project_bound(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->trects.as<uint32_t>(), cnt + 0, db, bucket_hist,
-                                   owned_rows, s);
+    uint32_t* bucket_hist = nchunks > 1 ? reinterpret_cast<uint32_t*>(arena + off_hist) : nullptr;
+    // K1.  Bounded: one thread per CELL projects the cell's box (tile rectangle + key interval + the chunk plan's histogram);
+    // the per-splat bound runs later, inside the chunks, for the selected cells only.  Exact: every submitted splat.
+    if (lazy) launch_cell_project(fc, ctx->cells.as<CellBox>(), n, db, bucket_hist, ctx->cell_views.as<uint4>(), cnt + 0, s);
     else launch_project(fc, ps, n, ctx->keys.as<uint32_t>(), ctx->rects.as<uint2>(),
                         (ctx->keep_intermediates || !use_trects) ? 1 : 0, use_trects ? ctx->trects.as<uint32_t>() : nullptr,
                         cnt + 0, db, bucket_hist, owned_rows, s);
     const uint2* exact_rects = lazy ? nullptr : ctx->rects.as<uint2>();
     st.launches += 1;
     // The depth order is cut into chunks WITHOUT sorting or moving the cloud: the chunk plan maps every depth bucket to
-    // a chunk; each chunk then selects its own live splats with one 4-byte-per-splat scan of the keys.
+    // a chunk and turns the bucket boundaries into key boundaries; each chunk then selects its own live splats.
     const ChunkPlan* chunk_plan = nullptr;
     if (nchunks > 1) {
         ChunkPlan* plan = ctx->plan.as<ChunkPlan>();
@@ -931,32 +1018,34 @@ try {
     if (tm) CU(cudaEventRecord(ctx->ev[EV_PROJECT], s));
     if (tm) CU(cudaEventRecord(ctx->ev[EV_SORT], s));
 
-    // K3b + K4 + K2 + K5 per depth chunk.  The splats of the chunk that still touch a live tile (owned by this rank, not
-    // saturated by nearer chunks) are compacted, depth-sorted, binned, given their records and blended; tiles whose
-    // pixels all saturated are flagged.  The per-pixel sequence of blended instances is the one a single global sort
-    // would give, so the frame is bit-identical to the single-chunk result.
-    uint32_t* tile_done = ctx->tile_done.as<uint32_t>();
-    CU(cudaMemsetAsync(tile_done, 0, done_bytes, s));
-    CU(cudaMemsetAsync(ctx->tile_consumed.p, 0, (size_t)num_tiles * 4, s));     // accumulates over chunks
+    // Per depth chunk: live selection -> depth sort -> K2 records -> binning -> blend.  The splats of the chunk that still
+    // touch a live tile (owned by this rank, not saturated by nearer chunks) are compacted, depth-sorted, binned, given their
+    // records and blended; tiles whose pixels all saturated are flagged.  The per-pixel sequence of blended instances is the
+    // one a single global sort would give, so the frame is bit-identical to the single-chunk result.
+    // Every kernel reads its element count from the device; the host needs L and a bound of D only to size buffers, and
+    // learns them from ONE event wait per chunk that it reaches after it has queued the chunk's depth sort.
     if (fr->row_world > 1 && fb_final == fb) CU(cudaMemsetAsync(fb, 0, fb_bytes, s));   // rows this rank does not own stay zero
     const int tile_bits = std::max(1, ceil_log2((uint32_t)num_tiles));
+    const SortPlan depth_plan = sort_plan(0, key_bits);
     // tiles this rank owns: when all of them are saturated no deeper splat can change a pixel and the frame is done
     int n_owned_rows = 0;
     for (int ty = 0; ty < fc.tiles_y; ++ty) n_owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
     const uint64_t owned_tiles = (uint64_t)n_owned_rows * (uint64_t)fc.tiles_x;
-    uint64_t D_total = 0, L_total = 0, V = 0, D = 0, L = 0;
+    uint64_t L_total = 0, V = 0, D = 0, L = 0;
     int chunks_run = 0;
-    // upper bound of a chunk's live splats: the visible splats of the chunk (all of them for the first chunk); the
-    // live buffers are sized once for the cloud so no size has to come back from the device before the selection
-    // (the second halves double as the selection's staging area: CTA-local runs, dead before the sort ping-pongs)
+    // the live buffers are sized once for the cloud, so no size has to come back from the device before the selection
+    // (exact K1: the second halves double as the selection's staging area: CTA-local runs, dead before the sort ping-pongs)
     const size_t live_bytes = select_stage_elems(n) * 4 + 16;
     for (int b = 0; b < 2; ++b) {
         CU(ctx->lkeys[b].ensure(live_bytes)); CU(ctx->lvals[b].ensure(live_bytes));
     }
+    uint32_t* const err_flag = reinterpret_cast<uint32_t*>(cnt + 2);
     for (int c = 0; c < nchunks; ++c) {
         const bool first = (c == 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][0], s));
-        uint32_t* counts = ctx->counts.as<uint32_t>();
+        unsigned long long* const cc = cnt + 8 + (size_t)c * 8;              // this chunk's counters
+        uint32_t* const hdr_depth = reinterpret_cast<uint32_t*>(arena + off_sort + (size_t)(2 * c) * hdr_bytes);
+        uint32_t* const hdr_tile = reinterpret_cast<uint32_t*>(arena + off_sort + (size_t)(2 * c + 1) * hdr_bytes);
         // live map of this chunk as a summed-area table (first chunk of a single rank: every tile is live, no table)
         const uint32_t* sat = nullptr;
         if (!first || fr->row_world > 1) {
@@ -964,17 +1053,35 @@ try {
             st.launches += 1;
             sat = ctx->live_sat.as<uint32_t>();
         }
-        // live selection, one pass over the keys: the splats of the chunk that still touch a live tile, compacted in
-        // submission order (so the stable sort below breaks ties by ascending index), their number L and the instances D
-        launch_select_live(pkeys, ptrects, exact_rects, n, chunk_plan, c, fc,
-                           sat, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
-                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), ctx->scan_scratch.p, cnt + 5, cnt + 4, s);
-        st.launches += 3;
-        // one host sync per chunk: V, this chunk's D and L, and the number of tiles saturated by the previous chunks
-        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 48, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        V = ctx->counters_h[0]; D = ctx->counters_h[4]; L = ctx->counters_h[5];
-        const bool all_done = ctx->counters_h[3] >= owned_tiles;        // implies D == 0
+        // live selection: the splats of the chunk that still touch a live tile -> (key, index) pairs, their number L and a
+        // bound of the instances D they will emit
+        if (lazy) {
+            launch_cell_select(ctx->cell_views.as<uint4>(), n, chunk_plan, c, fc, sat, ctx->sel_cells.as<uint32_t>(),
+                               reinterpret_cast<uint32_t*>(cc + 2), s);
+            launch_splat_select(fc, ctx->geomA_p.as<float4>(), ctx->lam_p.as<float>(), ctx->orig.as<uint32_t>(), n,
+                                ctx->sel_cells.as<uint32_t>(), reinterpret_cast<const uint32_t*>(cc + 2), chunk_plan, c, sat,
+                                ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(), cc + 0, cc + 1,
+                                depth_plan, key_min, key_span, hdr_depth, s);
+            st.launches += 2;
+        } else {
+            launch_select_live(pkeys, ptrects, exact_rects, n, chunk_plan, c, fc,
+                               sat, ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                               ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), ctx->scan_scratch.p, cc + 0, cc + 1, s);
+            st.launches += 3;
+        }
+        CU(cudaMemcpyAsync(ctx->counters_h, cnt, 64, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(ctx->counters_h + 8, cc, 64, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(ctx->ev_sel, s));
+        // depth sort of the live splats, queued BEFORE the host waits: the count is read on the device, the persistent pass
+        // kernels do not depend on it, and the GPU has work while the host sizes the chunk's buffers
+        ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
+                                          ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), N, cc + 0, 0, key_bits,
+                                          hdr_depth, true, lazy, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s, &st.launches,
+                                          nullptr, nullptr, key_min, key_span);
+        // the one host wait of the chunk: V, this chunk's L and bound of D, the tiles finished by the previous chunks
+        CU(cudaEventSynchronize(ctx->ev_sel));
+        V = ctx->counters_h[0]; L = ctx->counters_h[8]; D = ctx->counters_h[9];
+        const bool all_done = ctx->counters_h[3] >= owned_tiles;        // implies L == 0
         // the last chunk that has work, or the last chunk at all, finalises the un-saturated tiles
         const bool last = (c == nchunks - 1) || all_done;
         if (D > 0x3fffffffull) return fail(GSB_ERR_LIMIT, "more than 2^30-1 tile instances in one depth chunk");
@@ -984,54 +1091,53 @@ try {
             if (tm) for (int e = 1; e < 5; ++e) CU(cudaEventRecord(ctx->evc[c][e], s));
             break;
         }
-        // depth sort of the live splats: stable LSD, ties keep ascending index
         for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
         CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16)); CU(ctx->ltiles.ensure((size_t)L * 8 + 16));
+        CU(ctx->counts.ensure((size_t)L * 4 + 16));
         if (scene_depth) CU(ctx->zdepth.ensure((size_t)L * 4 + 16));
         float* zdepth = scene_depth ? ctx->zdepth.as<float>() : nullptr;
-        CU(ctx->sort_scratch.ensure(sort_scratch_bytes((size_t)std::max<uint64_t>(D, L))));
-        ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
-                                          ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), (size_t)L, 0, key_bits,
-                                          ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches,
-                                          nullptr, nullptr, key_min, key_span);
-        const uint32_t* order = ctx->lvals[ctx->order_buf].as<uint32_t>();
+        {
+            int rc2 = ensure_lookback(ctx, (size_t)std::max<uint64_t>(D, N));
+            if (rc2) return rc2;
+        }
+        uint32_t* counts = ctx->counts.as<uint32_t>();
+        // ties of the depth sort in index order (the live list arrives in cell order): the final order
+        ctx->order_vals_buf = ctx->order_buf ^ 1;
+        launch_tie_fix(ctx->lkeys[ctx->order_buf].as<uint32_t>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), L, nullptr,
+                       ctx->lvals[ctx->order_vals_buf].as<uint32_t>(), s);
+        st.launches += (L ? 1 : 0);
+        const uint32_t* order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
         launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        // K4: live-tile counts (K2) -> offsets -> instances -> stable partition by tile -> tile ranges
-        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cnt + 6, s, &st.launches);
-        if (lazy && L) {
-            // the selection counted instances with the bound's rectangles (an upper bound that sized the buffers);
-            // the exact number comes from K2's counts
-            CU(cudaMemcpyAsync(ctx->counters_h + 6, cnt + 6, 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            D = ctx->counters_h[6];
-        }
-        D_total += D;
-        launch_emit(ctx->ltiles.as<uint2>(), counts, cnt + 6, (int64_t)L, fc,
+        // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device) -> instances -> stable partition
+        // by tile -> tile ranges
+        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
         st.launches += (L ? 1 : 0);
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
-                                         ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, 0, tile_bits,
-                                         ctx->sort_scratch.p, reinterpret_cast<uint32_t*>(cnt + 2), s, &st.launches);
-        launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, ctx->ranges.as<uint2>(), num_tiles, s);
+                                         ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, cc + 3, 0, tile_bits,
+                                         hdr_tile, true, false, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s,
+                                         &st.launches);
+        launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, cc + 3, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][3], s));
         launch_blend(ctx->recs.as<Record>(), ctx->ivals[ctx->inst_buf].as<uint32_t>(), ctx->ranges.as<uint2>(), fb, fb_final, fc,
-                     first ? 1 : 0, last ? 1 : 0, tile_done, ctx->tile_consumed.as<uint32_t>(), cnt + 1, cnt + 3,
+                     first ? 1 : 0, last ? 1 : 0, tile_done, tile_consumed, cnt + 1, cnt + 3,
                      zdepth, scene_depth, s);
         st.launches += 1;
         if (tm) CU(cudaEventRecord(ctx->evc[c][4], s));
     }
     nchunks = chunks_run;
     CU(cudaGetLastError());
-    ctx->evc_chunks = nchunks;
-    const uint64_t D_last = D;      // the instance buffers hold the last chunk only
-    D = D_total;
+    ctx->evc_chunks = nchunks; ctx->chunks_last = nchunks;
     if (tm) CU(cudaEventRecord(ctx->ev[EV_BLEND], s));
-    CU(cudaMemcpyAsync(ctx->counters_h + 1, cnt + 1, 16, cudaMemcpyDeviceToHost, s));   // D_c and the sort error flag
+    // D_c, the sort error flag and every chunk's exact D: to pinned memory, read after the next synchronisation
+    CU(cudaMemcpyAsync(ctx->counters_h, cnt, 64, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->counters_h + 16, cnt + 8, (size_t)MAX_CHUNKS * 64, cudaMemcpyDeviceToHost, s));
 
     if (target && target->host_rgba) {
         if (!host_is_final) CU(cudaMemcpyAsync(target->host_rgba, fb_final, fb_bytes, cudaMemcpyDeviceToHost, s));
@@ -1060,18 +1166,22 @@ try {
     }
     ctx->ev_valid = tm;
 
+    uint64_t D_last = 0;                  // exact instance count of the last chunk (its buffers are the ones still around)
     if (ctx->keep_intermediates) {        // debug views of the last chunk: records by splat index, instances as splat indices
+        CU(cudaStreamSynchronize(s));
+        D_last = nchunks > 0 ? ctx->counters_h[16 + (size_t)(nchunks - 1) * 8 + 3] : 0;
         CU(ctx->dbg_recs.ensure(N * sizeof(Record) + 16)); CU(ctx->dbg_inst.ensure((size_t)D_last * 4 + 16));
         CU(cudaMemsetAsync(ctx->dbg_recs.p, 0, N * sizeof(Record), s));
-        launch_debug_views(ctx->recs.as<Record>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), (int64_t)L, ctx->dbg_recs.as<Record>(),
+        launch_debug_views(ctx->recs.as<Record>(), ctx->lvals[ctx->order_vals_buf].as<uint32_t>(), (int64_t)L, ctx->dbg_recs.as<Record>(),
                            ctx->ivals[ctx->inst_buf].as<uint32_t>(), D_last, ctx->dbg_inst.as<uint32_t>(), s);
         CU(cudaGetLastError());
     }
     ctx->last_live = (int64_t)L;
     ctx->last_n = n; ctx->last_sorted = (int64_t)L; ctx->last_d = D_last; ctx->last_tiles = num_tiles; ctx->last_w = fr->width; ctx->last_h = fr->height;
     ctx->last_fb = fb_final;
+    ctx->last_fc = fc; ctx->last_lazy = lazy;
     st.depth_chunks = nchunks;
-    st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = (int64_t)D; st.n_live = (int64_t)L_total;
+    st.rendered = 1; st.n_submitted = n; st.n_visible = (int64_t)V; st.n_instances = 0 /* gsb_get_stats */; st.n_live = (int64_t)L_total;
     st.sh_order_used = fc.sh_order; st.width = fr->width; st.height = fr->height;
     st.tiles_x = fc.tiles_x; st.tiles_y = fc.tiles_y;
     memcpy(st.camera, fc.cam, 12); memcpy(st.origin, fc.origin, 12);
@@ -1099,7 +1209,12 @@ try {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     gsb_stats& st = ctx->stats;
-    if (st.rendered) st.n_consumed = (int64_t)ctx->counters_h[1];
+    if (st.rendered) {
+        st.n_consumed = (int64_t)ctx->counters_h[1];
+        unsigned long long d = 0;                                      // exact instance counts of the chunks, summed
+        for (int c = 0; c < ctx->chunks_last; ++c) d += ctx->counters_h[16 + (size_t)c * 8 + 3];
+        st.n_instances = (int64_t)d;
+    }
     if (st.rendered && ctx->counters_h[2] != 0ull)
         return fail(GSB_ERR_CUDA, "radix sort look-back timed out (internal error); the last frame is invalid");
     st.ms_project = st.ms_sort = st.ms_bin = st.ms_blend = st.ms_copy = st.ms_total = st.ms_records = 0.0f;
@@ -1189,18 +1304,28 @@ try {
     const uint64_t n = (uint64_t)ctx->last_n, d = ctx->last_d, t = (uint64_t)ctx->last_tiles;
     switch (which) {
     case GSB_DBG_KEYS_UNSORTED: src = ctx->keys.p; need = n * 4; break;
-    case GSB_DBG_ORDER:         src = ctx->lvals[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
+    case GSB_DBG_ORDER:         src = ctx->lvals[ctx->order_vals_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
     case GSB_DBG_KEYS_SORTED:   src = ctx->lkeys[ctx->order_buf].p; need = (uint64_t)ctx->last_sorted * 4; break;
     case GSB_DBG_RECORDS:       src = ctx->dbg_recs.p; need = ctx->keep_intermediates ? n * sizeof(Record) : 0; break;
     case GSB_DBG_RECTS:         src = ctx->rects.p; need = ctx->keep_intermediates ? n * 8 : 0; break;
     case GSB_DBG_TILE_RANGES:   src = ctx->ranges.p; need = t * 8; break;
     case GSB_DBG_INSTANCES:     src = ctx->dbg_inst.p; need = ctx->keep_intermediates ? d * 4 : 0; break;
     case GSB_DBG_FRAMEBUFFER:   src = ctx->last_fb; need = (uint64_t)ctx->last_w * ctx->last_h * 16; break;
-    case GSB_DBG_TILE_CONSUMED: src = ctx->tile_consumed.p; need = t * 4; break;
-    case GSB_DBG_TRECTS:        src = ctx->trects.p; need = (ctx->trects.p && ctx->last_w <= 8192 && ctx->last_h <= 8192) ? n * 4 : 0; break;
+    case GSB_DBG_TILE_CONSUMED: src = ctx->last_tile_consumed; need = t * 4; break;
+    case GSB_DBG_TRECTS:        src = ctx->trects.p; need = (ctx->last_w <= 8192 && ctx->last_h <= 8192) ? n * 4 : 0; break;
     default: return fail(GSB_ERR_INVALID, "gsb_debug_fetch: unknown buffer");
     }
     if (bytes_needed) *bytes_needed = need;
+    if (dst && need && ctx->last_lazy && (which == GSB_DBG_KEYS_UNSORTED || which == GSB_DBG_TRECTS) && n) {
+        // the bounded K1 evaluates its bound only inside the cells a chunk selects; the debug view computes it for EVERY
+        // splat with the same device function (bound_one) and the last frame's constants, by original index
+        CU(ctx->keys.ensure(n * 4)); CU(ctx->trects.ensure(n * 4));
+        launch_project_bound_debug(ctx->last_fc, ctx->geomA_p.as<float4>(), ctx->lam_p.as<float>(), ctx->orig.as<uint32_t>(), (int64_t)n,
+                                   ctx->keys.as<uint32_t>(), ctx->trects.as<uint32_t>(), ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        src = which == GSB_DBG_KEYS_UNSORTED ? ctx->keys.p : ctx->trects.p;
+    }
     if (dst && need) {
         if (dst_bytes < need) return fail(GSB_ERR_INVALID, "gsb_debug_fetch: destination too small");
         if (!src) return fail(GSB_ERR_INVALID, "gsb_debug_fetch: buffer not available");
@@ -1215,15 +1340,20 @@ try {
     if (!ctx || (n && (!keys || !vals || !keys_out || !vals_out))) return fail(GSB_ERR_INVALID, "NULL argument");
     if (begin_bit < 0 || end_bit > 32 || end_bit < begin_bit) return fail(GSB_ERR_INVALID, "bad bit range");
     CU(cudaSetDevice(ctx->device));
-    DevBuf k[2], v[2], scr;
+    DevBuf k[2], v[2], hdr;
     for (int b = 0; b < 2; ++b) { CU(k[b].ensure(n * 4 + 16)); CU(v[b].ensure(n * 4 + 16)); }
-    CU(scr.ensure(sort_scratch_bytes(n)));
+    CU(hdr.ensure(sort_header_bytes()));
+    {
+        int rc2 = ensure_lookback(ctx, (size_t)n);
+        if (rc2) return rc2;
+    }
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(k[0].p, keys, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(v[0].p, vals, n * 4, cudaMemcpyHostToDevice, s));
     int launches = 0;
-    int r = radix_sort_pairs(k[0].as<uint32_t>(), v[0].as<uint32_t>(), k[1].as<uint32_t>(), v[1].as<uint32_t>(), n,
-                             begin_bit, end_bit, scr.p, nullptr, s, &launches);
+    int r = radix_sort_pairs(k[0].as<uint32_t>(), v[0].as<uint32_t>(), k[1].as<uint32_t>(), v[1].as<uint32_t>(), n, nullptr,
+                             begin_bit, end_bit, hdr.as<uint32_t>(), false, false, ctx->lookback.as<unsigned long long>(),
+                             next_epoch(ctx), nullptr, s, &launches);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(keys_out, k[r].p, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(vals_out, v[r].p, n * 4, cudaMemcpyDeviceToHost, s));
