@@ -191,6 +191,7 @@ struct gsb_context {
     cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
     std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
     FrameConsts last_fc{}; bool last_lazy = false;   // for the on-demand debug view of the bound
+    bool obj_level_warned = false;                   // _justPrintedOBJLevelRenderingWarning (R.h:127)
     uint32_t* last_tile_consumed = nullptr;
 
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
@@ -792,11 +793,15 @@ int gsb_render(gsb_context* ctx, const gsb_frame* fr, const gsb_target* target)
 try {
     if (!ctx || !fr) return fail(GSB_ERR_INVALID, "gsb_render: NULL argument");
     gsb_stats& st = ctx->stats;
-    st.rendered = 0; st.launches = 0;
+    st.rendered = 0; st.launches = 0; st.warnings = 0;
     if (!ctx->render_enabled || !ctx->can_render) return GSB_OK;          // R.C:536-539
     bool any = false;
     for (auto& kv : ctx->registry) any |= kv.second->active;
     if (!any) return GSB_OK;                                             // R.C:541-549
+    // OBJ-level rendering: the reference warns once per switch to OBJ level and renders anyway (R.C:565-581)
+    if (fr->is_object_level) {
+        if (!ctx->obj_level_warned) { st.warnings |= GSB_WARN_OBJECT_LEVEL; ctx->obj_level_warned = true; }
+    } else ctx->obj_level_warned = false;
     if (fr->width < 1 || fr->height < 1 || fr->width > 65535 || fr->height > 65535)
         return fail(GSB_ERR_LIMIT, "gsb_render: screen size must be 1..65535");
     if (fr->row_world < 1 || fr->row_rank < 0 || fr->row_rank >= fr->row_world)

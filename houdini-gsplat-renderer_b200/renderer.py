@@ -57,6 +57,7 @@ class FrameC(C.Structure):
 
 
 DEPTH_NONE, DEPTH_LESS, DEPTH_LEQUAL = 0, 1, 2
+WARN_OBJECT_LEVEL = 1
 
 
 class TargetC(C.Structure):
@@ -84,7 +85,7 @@ class StatsC(C.Structure):
                 ("n_consumed", C.c_int64), ("rendered", C.c_int32), ("repacked", C.c_int32),
                 ("sh_order_used", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("launches", C.c_int32),
-                ("depth_chunks", C.c_int32), ("reserved0", C.c_int32),
+                ("depth_chunks", C.c_int32), ("warnings", C.c_int32),
                 ("camera", C.c_float * 3), ("origin", C.c_float * 3),
                 ("ms_project", C.c_float), ("ms_sort", C.c_float), ("ms_bin", C.c_float),
                 ("ms_blend", C.c_float), ("ms_copy", C.c_float), ("ms_total", C.c_float),

@@ -115,7 +115,7 @@ typedef struct gsb_stats {
     int32_t tiles_x, tiles_y;
     int32_t launches;        /* kernels launched by the last gsb_render */
     int32_t depth_chunks;    /* depth chunks the last frame was binned/blended in */
-    int32_t reserved0;
+    int32_t warnings;        /* enum gsb_warning bits raised by the last gsb_render (the reference logs these, R.C:565-581) */
     float   camera[3];       /* WorldSpaceCameraPos used for keys and SH */
     float   origin[3];       /* GSplatOrigin (mean of barycentres, R.C:403-418) */
     /* device time per stage of the last gsb_render, CUDA events on the library stream;
@@ -126,6 +126,12 @@ typedef struct gsb_stats {
     int64_t n_live;          /* L: splats that reached a live (owned, un-saturated) tile, summed over depth chunks: only these
                                 are depth-sorted, given a 2-D record (SH evaluated) and binned */
 } gsb_stats;
+
+enum gsb_warning {
+    GSB_WARN_OBJECT_LEVEL = 1    /* gsb_frame.is_object_level: OBJ-level transforms other than identity are not supported by the
+                                    reference's formulas (R.C:565-577), which this library reproduces; raised on the
+                                    first OBJ-level frame after a SOP-level one, like the reference's one-time log line */
+};
 
 enum gsb_option {
     GSB_OPT_SPLAT_CAP = 1,       /* max splats packed; default GSB_REFERENCE_SPLAT_CAP; 0 = unlimited */
