@@ -40,17 +40,6 @@ __device__ __forceinline__ TileRect tile_rect_packed(const bool has_packed, cons
     return t;
 }
 
-// Saturation flags (tile_done): one BIT per tile, rows padded to whole 32-bit words (done_words_per_row), set by the
-// blend of an earlier depth chunk.  The live tiles of a splat's row segment [tx0, tx1] are then a mask and a popcount
-// per word (one word for almost every splat) instead of a load per tile.
-__device__ __forceinline__ uint32_t live_word(const uint32_t* __restrict__ done, int wpr, int ty, int w, int tx0, int tx1)
-{
-    uint32_t m = 0xffffffffu;
-    if (w == (tx0 >> 5)) m &= 0xffffffffu << (tx0 & 31);
-    if (w == (tx1 >> 5)) m &= 0xffffffffu >> (31 - (tx1 & 31));
-    return m & ~__ldg(done + ty * wpr + w);
-}
-
 // summed-area table of the live map, one CTA: row prefixes (a warp per row), then column sums (a thread per column;
 // the loads do not depend on the running sum, so they pipeline)
 __global__ void __launch_bounds__(1024)

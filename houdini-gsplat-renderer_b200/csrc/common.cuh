@@ -178,6 +178,17 @@ void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_
                     const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
                     const uint32_t* owned_rows, cudaStream_t s);
 // zdepth (may be NULL): window depth of live rank j (scene-depth occlusion)
+// K2 fused with the first half of the binning (r02): the same records, and in the same kernel the exclusive scan of the
+// live-tile counts (one decoupled look-back per CTA over `status`: records_status_bytes(n_live) bytes, epoch tagged like the
+// sort's table, never cleared after allocation), the instance emit (tile id, live rank) at the scanned offsets, rows
+// ascending then columns ascending, live tiles only, the exact instance total (*d_total) and the digit histograms of the
+// tile partition that follows (tile_plan over [0, tile_bits); tile_hist zero before).  *ticket zero before.
+size_t records_status_bytes(int64_t n_live);
+void launch_records_emit(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
+                         const uint32_t* sat, Record* recs, float* zdepth, const uint32_t* owned_rows,
+                         unsigned long long* status, uint32_t epoch, uint32_t* ticket, const uint32_t* tile_done,
+                         uint32_t* inst_keys, uint32_t* inst_vals, unsigned long long* d_total,
+                         const SortPlan& tile_plan, uint32_t* tile_hist, uint32_t* error_flag, cudaStream_t s);
 
 // binning.cu
 // tile_done: saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) +
@@ -259,6 +270,17 @@ __device__ __forceinline__ uint32_t live_tiles(int tx0, int tx1, int ty0, int ty
 
 // words per tile row of the saturation bit map (tile_done)
 __host__ __device__ __forceinline__ int done_words_per_row(int tiles_x) { return (tiles_x + 31) >> 5; }
+
+// Saturation flags (tile_done): one BIT per tile, rows padded to whole 32-bit words (done_words_per_row), set by the
+// blend of an earlier depth chunk.  The live tiles of a splat's row segment [tx0, tx1] are then a mask and a popcount
+// per word (one word for almost every splat) instead of a load per tile.
+__device__ __forceinline__ uint32_t live_word(const uint32_t* __restrict__ done, int wpr, int ty, int w, int tx0, int tx1)
+{
+    uint32_t m = 0xffffffffu;
+    if (w == (tx0 >> 5)) m &= 0xffffffffu << (tx0 & 31);
+    if (w == (tx1 >> 5)) m &= 0xffffffffu >> (31 - (tx1 & 31));
+    return m & ~__ldg(done + ty * wpr + w);
+}
 
 // tile-row ownership rule shared by every kernel
 __host__ __device__ __forceinline__ bool owns_row(int ty, int rank, int world, int group)

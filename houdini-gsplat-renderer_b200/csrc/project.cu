@@ -865,19 +865,16 @@ choose_chunks_kernel(const uint32_t* __restrict__ hist, const int nchunks, const
 // and the splat's tile rectangle and live-tile count (the binning inputs) to tile_rects[j] / counts[j].
 constexpr int K2_THREADS = 256;
 constexpr int K2_PITCH   = ROW_U4 + 1;             // uint4 per staged line
+
+// the K2 work of one thread: gather (cooperatively, per warp) the lines of 32 consecutive live ranks, redo the projection
+// with K1's code, write the record of rank j, return its tile rectangle and live-tile count (0: the exact projection culls it)
 template <int ORDER>
-__global__ void __launch_bounds__(K2_THREADS)
-records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
-               const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
-               Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts,
-               float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows)
+__device__ __forceinline__ uint32_t record_one(const FrameConsts& F, const uint4* __restrict__ rows, uint4* sw, const int lane,
+                                               const uint32_t my, const bool valid, const int64_t j, const uint32_t* __restrict__ sat,
+                                               Record* __restrict__ recs, float* __restrict__ zdepth,
+                                               const uint32_t* __restrict__ owned_rows, uint2& trect)
 {
-    __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
     constexpr int NCH = 2 + (ORDER == 0 ? 1 : (ORDER == 1 ? 2 : (ORDER == 2 ? 4 : 6)));     // chunks of the line this order reads
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t j = (int64_t)blockIdx.x * K2_THREADS + threadIdx.x;
-    const uint32_t my = (j < n_live) ? __ldg(live_splats + j) : 0u;
-    uint4* sw = srow[warp];
     const int c = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -886,7 +883,8 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
         if (c < NCH) sw[r * K2_PITCH + c] = __ldg(rows + (size_t)idx * ROW_U4 + c);
     }
     __syncwarp();
-    if (j >= n_live) return;
+    trect = make_uint2(1u, 1u);
+    if (!valid) return 0u;
     const uint4* row = sw + lane * K2_PITCH;
     const uint4 ra = row[0];
     const uint4 gb = row[1];
@@ -895,20 +893,17 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     Geom g;
     float4* out = reinterpret_cast<float4*>(recs + j);
     const float pmax = pmax_of_alpha(alpha);
-    if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g, owned_rows)) {  // cannot happen (K1 kept it)
+    if (!project_geom(F, p, (pmax >= 0.0f) ? sqrtf(pmax) : -1.0f, sigma_of(F.object, gb), g, owned_rows)) {
+        // the bound kept it, the exact projection culls it (degenerate axes, empty exact rectangle, no owned row): no instances
         out[0] = make_float4(-1.0e9f, -1.0e9f, 0.f, 0.f); out[1] = make_float4(0.f, 0.f, 0.f, -1.0f);
         out[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        tile_rects[j] = make_uint2(1u, 1u); counts[j] = 0u;
         if (zdepth) zdepth[j] = 0.0f;
-        return;
+        return 0u;
     }
     if (zdepth) zdepth[j] = ((g.clipz / g.clipw) * F.depth_hr) + F.depth_hm;     // window depth of the whole quad
-    // binning inputs of this live splat: its tile rectangle and the number of live tiles in it
-    {
-        const int tx0 = g.x0 / TILE, tx1 = g.x1 / TILE, ty0 = g.y0 / TILE, ty1 = g.y1 / TILE;
-        tile_rects[j] = make_uint2((uint32_t)tx0 | ((uint32_t)tx1 << 16), (uint32_t)ty0 | ((uint32_t)ty1 << 16));
-        counts[j] = live_tiles(tx0, tx1, ty0, ty1, F.tiles_x, sat);
-    }
+    const int tx0 = g.x0 / TILE, tx1 = g.x1 / TILE, ty0 = g.y0 / TILE, ty1 = g.y1 / TILE;
+    trect = make_uint2((uint32_t)tx0 | ((uint32_t)tx1 << 16), (uint32_t)ty0 | ((uint32_t)ty1 << 16));
+    const uint32_t count = live_tiles(tx0, tx1, ty0, ty1, F.tiles_x, sat);
     float rgb[3];
     shade_colour<ORDER>(F, row + 2, g.psx, rgb);
     const uint32_t hpack = (uint32_t)__half_as_ushort(__float2half_ru(g.hx)) |
@@ -916,6 +911,139 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     out[0] = make_float4(g.cx, g.cy, g.m00, g.m01);
     out[1] = make_float4(g.m10, g.m11, alpha, pmax);
     out[2] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(hpack));
+    return count;
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(K2_THREADS)
+records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
+               const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
+               Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts,
+               float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows)
+{
+    __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * K2_THREADS + threadIdx.x;
+    const bool valid = j < n_live;
+    const uint32_t my = valid ? __ldg(live_splats + j) : 0u;
+    uint2 tr;
+    const uint32_t cnt = record_one<ORDER>(F, rows, srow[warp], lane, my, valid, j, sat, recs, zdepth, owned_rows, tr);
+    if (valid) { tile_rects[j] = tr; counts[j] = cnt; }
+}
+
+// ---- K2 + count scan + instance emit + tile-sort histograms in ONE kernel (r02).  CTAs take their slice of the live list
+// from a ticket, so a CTA only ever waits for slices that already started: the single-value decoupled look-back below
+// cannot deadlock; its spin is bounded like the sort's.  status[t] = epoch << 32 | flag << 30 | count (30 bits).
+constexpr uint32_t ST_AGG = 0x40000000u, ST_INCL = 0x80000000u, ST_MASK = 0x3FFFFFFFu;
+struct TileSort { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; };
+template <int ORDER>
+__global__ void __launch_bounds__(K2_THREADS)
+records_emit_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
+                    const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
+                    Record* __restrict__ recs, float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows,
+                    unsigned long long* __restrict__ status, const uint32_t epoch, uint32_t* __restrict__ ticket,
+                    const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals,
+                    unsigned long long* __restrict__ d_total, const TileSort ts, uint32_t* __restrict__ tile_hist,
+                    uint32_t* __restrict__ error_flag)
+{
+    __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
+    __shared__ uint32_t sh_hist[SORT_MAX_PASSES][SORT_RADIX];
+    __shared__ uint32_t s_wsum[K2_THREADS / 32];
+    __shared__ uint32_t s_tile, s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < SORT_MAX_PASSES * SORT_RADIX; i += K2_THREADS) (&sh_hist[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t j = (int64_t)tile * K2_THREADS + threadIdx.x;
+    const bool valid = j < n_live;
+    const uint32_t my = valid ? __ldg(live_splats + j) : 0u;
+    uint2 tr;
+    const uint32_t cnt = record_one<ORDER>(F, rows, srow[warp], lane, my, valid, j, sat, recs, zdepth, owned_rows, tr);
+
+    // exclusive scan of the CTA's counts
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < K2_THREADS / 32; ++w) { woff += (w < warp) ? s_wsum[w] : 0u; total += s_wsum[w]; }
+    // decoupled look-back over the preceding slices (warp 0: 32 predecessors per step, independent loads)
+    if (warp == 0) {
+        const unsigned long long etag = (unsigned long long)epoch << 32;
+        if (lane == 0) {
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | (tile == 0 ? ST_INCL : ST_AGG) | (total & ST_MASK)) : "memory");
+        }
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            uint32_t spins = 0;
+            bool done = false;
+            while (!done) {
+                unsigned long long v = etag | ST_INCL;                   // before the first slice: an inclusive zero
+                if (t - lane >= 0) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(status + (t - lane)) : "memory");
+                const uint32_t lo = (uint32_t)v;
+                const bool pub = (uint32_t)(v >> 32) == epoch && (lo & (ST_AGG | ST_INCL)) != 0u;
+                const unsigned not_pub = __ballot_sync(0xffffffffu, !pub);
+                const unsigned incl = __ballot_sync(0xffffffffu, pub && (lo & ST_INCL) != 0u);
+                // usable prefix of the window: lanes before the first unpublished entry, up to and including the first inclusive one
+                const int first_bad = not_pub ? (__ffs(not_pub) - 1) : 32;
+                const unsigned incl_ok = incl & ((first_bad >= 32) ? 0xffffffffu : ((1u << first_bad) - 1u));
+                const int first_incl = incl_ok ? (__ffs(incl_ok) - 1) : -1;
+                const int use = first_incl >= 0 ? first_incl + 1 : first_bad;         // entries consumed this step
+                uint32_t part = (lane < use) ? (lo & ST_MASK) : 0u;
+                part = __reduce_add_sync(0xffffffffu, part);
+                excl += part;
+                t -= use;
+                if (first_incl >= 0) done = true;
+                else if (use == 0) {
+                    if (++spins > (1u << 22)) { if (lane == 0) atomicExch(error_flag, 1u); done = true; }
+                    __nanosleep(20);
+                }
+            }
+            if (lane == 0)
+                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | ST_INCL | ((excl + total) & ST_MASK)) : "memory");
+        }
+        if (lane == 0) {
+            s_base = excl;
+            if ((int64_t)(tile + 1) * K2_THREADS >= n_live) *d_total = (unsigned long long)excl + total;     // the last slice knows D
+        }
+    }
+    __syncthreads();
+    // emit this splat's instances at its scanned offset: rows ascending, columns ascending, live tiles only
+    if (cnt != 0u) {
+        size_t o = (size_t)s_base + woff + (inc - cnt);
+        const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
+        const int wpr = done_words_per_row(F.tiles_x);
+        for (int ty = ty0; ty <= ty1; ++ty) {
+            if (!owns_row(ty, F.row_rank, F.row_world, F.row_group)) continue;
+            for (int w = tx0 >> 5; w <= (tx1 >> 5); ++w) {
+                uint32_t live;
+                if (tile_done) live = live_word(tile_done, wpr, ty, w, tx0, tx1);
+                else {
+                    live = 0xffffffffu;
+                    if (w == (tx0 >> 5)) live &= 0xffffffffu << (tx0 & 31);
+                    if (w == (tx1 >> 5)) live &= 0xffffffffu >> (31 - (tx1 & 31));
+                }
+                while (live) {                                   // ascending columns
+                    const int b = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint32_t id = (uint32_t)(ty * F.tiles_x + w * 32 + b);
+                    inst_keys[o] = id; inst_vals[o] = (uint32_t)j; ++o;
+#pragma unroll
+                    for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
+                        if (ps < ts.passes) atomicAdd(&sh_hist[ps][(id >> ts.shift[ps]) & ((1u << ts.bits[ps]) - 1u)], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ts.passes * SORT_RADIX; i += K2_THREADS) {
+        const uint32_t v = (&sh_hist[0][0])[i];
+        if (v) atomicAdd(tile_hist + i, v);
+    }
 }
 
 }  // namespace
@@ -1034,6 +1162,30 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
 void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s)
 {
     choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, db, plan);
+}
+
+size_t records_status_bytes(int64_t n_live) { return (size_t)((n_live + K2_THREADS - 1) / K2_THREADS + 1) * sizeof(unsigned long long); }
+
+void launch_records_emit(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
+                         const uint32_t* sat, Record* recs, float* zdepth, const uint32_t* owned_rows,
+                         unsigned long long* status, uint32_t epoch, uint32_t* ticket, const uint32_t* tile_done,
+                         uint32_t* inst_keys, uint32_t* inst_vals, unsigned long long* d_total,
+                         const SortPlan& tile_plan, uint32_t* tile_hist, uint32_t* error_flag, cudaStream_t s)
+{
+    if (n_live <= 0) return;
+    const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
+    TileSort ts{};
+    ts.passes = tile_plan.passes;
+    for (int p = 0; p < tile_plan.passes; ++p) { ts.shift[p] = tile_plan.shift[p]; ts.bits[p] = tile_plan.bits[p]; }
+#define GSB_RE(O) records_emit_kernel<O><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, zdepth, owned_rows, status, \
+                      epoch, ticket, tile_done, inst_keys, inst_vals, d_total, ts, tile_hist, error_flag)
+    switch (fc.sh_order) {
+    case 0:  GSB_RE(0); break;
+    case 1:  GSB_RE(1); break;
+    case 2:  GSB_RE(2); break;
+    default: GSB_RE(3); break;
+    }
+#undef GSB_RE
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,

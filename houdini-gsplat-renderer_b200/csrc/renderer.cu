@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -52,11 +53,14 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    cudaError_t ensure(size_t bytes)
+    // per-frame buffers whose size follows the camera (instances, records): half as much again, so a camera that orbits
+    // towards a denser view re-allocates (a device-wide sync) a handful of times in total instead of every few frames
+    cudaError_t ensure_grow(size_t bytes) { return ensure(bytes, 1); }
+    cudaError_t ensure(size_t bytes, int slack_shift = 3)
     {
         if (bytes <= cap) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;       // a little headroom so D jitter does not realloc every frame
+        size_t want = bytes + (bytes >> slack_shift) + 256;       // headroom so D jitter does not realloc every frame
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
         if (e == cudaSuccess) cap = want;
@@ -187,6 +191,7 @@ struct gsb_context {
     DevBuf geomA_p, lam_p, orig, cells, cell_views, sel_cells;
     DevBuf arena;                                    // per-frame counters, histograms, sort headers, tile flags: ONE memset per frame
     DevBuf lookback;                                 // radix-sort look-back table (epoch tagged, cleared on allocation only)
+    DevBuf k2_status;                                // look-back status of the fused K2 count scan (same tagging)
     uint32_t sort_epoch = 0;
     cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
     std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
@@ -1096,10 +1101,10 @@ try {
             if (tm) for (int e = 1; e < 5; ++e) CU(cudaEventRecord(ctx->evc[c][e], s));
             break;
         }
-        for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure((size_t)D * 4 + 16)); }
-        CU(ctx->recs.ensure((size_t)L * sizeof(Record) + 16)); CU(ctx->ltiles.ensure((size_t)L * 8 + 16));
-        CU(ctx->counts.ensure((size_t)L * 4 + 16));
-        if (scene_depth) CU(ctx->zdepth.ensure((size_t)L * 4 + 16));
+        for (int b = 0; b < 2; ++b) { CU(ctx->ikeys[b].ensure_grow((size_t)D * 4 + 16)); CU(ctx->ivals[b].ensure_grow((size_t)D * 4 + 16)); }
+        CU(ctx->recs.ensure_grow((size_t)L * sizeof(Record) + 16)); CU(ctx->ltiles.ensure_grow((size_t)L * 8 + 16));
+        CU(ctx->counts.ensure_grow((size_t)L * 4 + 16));
+        if (scene_depth) CU(ctx->zdepth.ensure_grow((size_t)L * 4 + 16));
         float* zdepth = scene_depth ? ctx->zdepth.as<float>() : nullptr;
         {
             int rc2 = ensure_lookback(ctx, (size_t)std::max<uint64_t>(D, N));
@@ -1113,19 +1118,36 @@ try {
         st.launches += (L ? 1 : 0);
         const uint32_t* order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
-        // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
-        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
-        st.launches += (L ? 1 : 0);
-        if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device) -> instances -> stable partition
-        // by tile -> tile ranges
-        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
-        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
-                    first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
-        st.launches += (L ? 1 : 0);
+        // K2 + the first half of K4 in one kernel: records of the live splats in depth order, their live-tile counts scanned
+        // on the fly (decoupled look-back), instances emitted at the scanned offsets, the exact total D left on the device
+        // (cc + 3) and the digit histograms of the tile partition built on the way.  GSB_FUSED_K2=0: the separate kernels.
+        static const bool fused_k2 = [] { const char* e = getenv("GSB_FUSED_K2"); return !(e && atoi(e) == 0); }();
+        const SortPlan tile_plan = sort_plan(0, tile_bits);
+        if (fused_k2) {
+            const size_t need = records_status_bytes((int64_t)L);
+            if (need > ctx->k2_status.cap) {
+                CU(ctx->k2_status.ensure(need + need / 2));
+                CU(cudaMemsetAsync(ctx->k2_status.p, 0, ctx->k2_status.cap, s));
+            }
+            launch_records_emit(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), zdepth, owned_rows,
+                                ctx->k2_status.as<unsigned long long>(), next_epoch(ctx), reinterpret_cast<uint32_t*>(cc + 4),
+                                first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), cc + 3,
+                                tile_plan, hdr_tile, err_flag, s);
+            st.launches += (L ? 1 : 0);
+            if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+        } else {
+            launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
+            st.launches += (L ? 1 : 0);
+            if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+            exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+            launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
+                        first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
+            st.launches += (L ? 1 : 0);
+        }
+        // stable partition of the instances by tile -> tile ranges
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, cc + 3, 0, tile_bits,
-                                         hdr_tile, true, false, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s,
+                                         hdr_tile, true, fused_k2, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s,
                                          &st.launches);
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, cc + 3, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
