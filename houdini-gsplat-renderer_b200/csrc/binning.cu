@@ -198,35 +198,62 @@ select_gather_kernel(const uint32_t* __restrict__ stage_k, const uint32_t* __res
     }
 }
 
-// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only
+// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only; the digit
+// histograms of the tile partition that follows are built on the way (shared-memory bins, one flush per CTA), so the
+// partition needs no pass of its own over the instance keys
+struct EmitSort { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; };
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ offsets,
             const unsigned long long* __restrict__ total,
             int64_t n, int tiles_x, int row_rank, int row_world, int row_group,
-            const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals)
+            const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals,
+            const EmitSort es, uint32_t* __restrict__ tile_hist)
 {
+    __shared__ uint32_t sh_hist[SORT_MAX_PASSES][SORT_RADIX];
+    if (tile_hist) {
+        for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) (&sh_hist[0][0])[i] = 0u;
+        __syncthreads();
+    }
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t o0 = offsets[k];
-    const uint32_t o1 = (k + 1 < n) ? offsets[k + 1] : (uint32_t)(*total);
-    if (o1 == o0) return;                                    // every tile it touches is saturated
-    const uint2 tr = __ldg(tile_rects + k);
-    const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
-    size_t o = o0;
-    const int wpr = done_words_per_row(tiles_x);
-    for (int ty = ty0; ty <= ty1; ++ty) {
-        if (!owns_row(ty, row_rank, row_world, row_group)) continue;
-        if (!tile_done) {
-            for (int tx = tx0; tx <= tx1; ++tx) { inst_keys[o] = (uint32_t)(ty * tiles_x + tx); inst_vals[o] = (uint32_t)k; ++o; }
-        } else {
+    uint32_t o0 = 0, o1 = 0;
+    if (k < n) {
+        o0 = offsets[k];
+        o1 = (k + 1 < n) ? offsets[k + 1] : (uint32_t)(*total);
+    }
+    if (o1 != o0) {                                              // else: every tile it touches is saturated
+        const uint2 tr = __ldg(tile_rects + k);
+        const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
+        size_t o = o0;
+        const int wpr = done_words_per_row(tiles_x);
+        for (int ty = ty0; ty <= ty1; ++ty) {
+            if (!owns_row(ty, row_rank, row_world, row_group)) continue;
             for (int w = tx0 >> 5; w <= (tx1 >> 5); ++w) {
-                uint32_t live = live_word(tile_done, wpr, ty, w, tx0, tx1);
+                uint32_t live;
+                if (tile_done) live = live_word(tile_done, wpr, ty, w, tx0, tx1);
+                else {
+                    live = 0xffffffffu;
+                    if (w == (tx0 >> 5)) live &= 0xffffffffu << (tx0 & 31);
+                    if (w == (tx1 >> 5)) live &= 0xffffffffu >> (31 - (tx1 & 31));
+                }
                 while (live) {                                   // ascending columns
                     const int b = __ffs(live) - 1;
                     live &= live - 1;
-                    inst_keys[o] = (uint32_t)(ty * tiles_x + w * 32 + b); inst_vals[o] = (uint32_t)k; ++o;
+                    const uint32_t id = (uint32_t)(ty * tiles_x + w * 32 + b);
+                    inst_keys[o] = id; inst_vals[o] = (uint32_t)k; ++o;
+                    if (tile_hist) {
+#pragma unroll
+                        for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
+                            if (ps < es.passes) atomicAdd(&sh_hist[ps][(id >> es.shift[ps]) & ((1u << es.bits[ps]) - 1u)], 1u);
+                    }
                 }
             }
+        }
+    }
+    if (tile_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) {
+            const uint32_t v = (&sh_hist[0][0])[i];
+            if (v) atomicAdd(tile_hist + i, v);
         }
     }
 }
@@ -334,11 +361,15 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
 
 void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                  const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
-                 uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s)
+                 uint32_t* inst_keys, uint32_t* inst_vals, const SortPlan& tile_plan, uint32_t* tile_hist, cudaStream_t s)
 {
     if (n <= 0) return;
+    EmitSort es{};
+    es.passes = tile_plan.passes;
+    for (int p = 0; p < tile_plan.passes; ++p) { es.shift[p] = tile_plan.shift[p]; es.bits[p] = tile_plan.bits[p]; }
     emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tile_rects, offsets, total, n, fc.tiles_x,
-                                                           fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals);
+                                                           fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals,
+                                                           es, tile_hist);
 }
 
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const unsigned long long* d_dev, uint2* ranges,

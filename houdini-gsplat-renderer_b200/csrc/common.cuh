@@ -212,9 +212,10 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
                         cudaStream_t s);
 // instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only;
 // tile_rects = K2's rectangles by live rank; offsets = exclusive scan of K2's counts, *total = its grand total (device)
+// tile_hist (may be NULL; zero before): receives the digit histograms of the tile partition described by tile_plan
 void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
                  const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
-                 uint32_t* inst_keys, uint32_t* inst_vals, cudaStream_t s);
+                 uint32_t* inst_keys, uint32_t* inst_vals, const SortPlan& tile_plan, uint32_t* tile_hist, cudaStream_t s);
 // d_max: host-side upper bound (grid size), d_dev: the exact count on the device (NULL: d_max is exact)
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const unsigned long long* d_dev, uint2* ranges,
                         int num_tiles, cudaStream_t s);

@@ -1120,8 +1120,11 @@ try {
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2 + the first half of K4 in one kernel: records of the live splats in depth order, their live-tile counts scanned
         // on the fly (decoupled look-back), instances emitted at the scanned offsets, the exact total D left on the device
-        // (cc + 3) and the digit histograms of the tile partition built on the way.  GSB_FUSED_K2=0: the separate kernels.
-        static const bool fused_k2 = [] { const char* e = getenv("GSB_FUSED_K2"); return !(e && atoi(e) == 0); }();
+        // (cc + 3) and the digit histograms of the tile partition built on the way.
+        // r02 measured the fused kernel SLOWER than the separate ones (records + scan + emit: 144-163 us vs ~115 us per chunk at
+        // 20 M / 1080p: the serial per-thread emit and the look-back wait sit inside a 64-register, gather-latency-bound
+        // kernel), so it is off unless GSB_FUSED_K2=1; the separate emit kernel builds the tile histograms instead.
+        static const bool fused_k2 = [] { const char* e = getenv("GSB_FUSED_K2"); return e && atoi(e) != 0; }();
         const SortPlan tile_plan = sort_plan(0, tile_bits);
         if (fused_k2) {
             const size_t need = records_status_bytes((int64_t)L);
@@ -1141,13 +1144,13 @@ try {
             if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
             exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
             launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
-                        first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), s);
+                        first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
             st.launches += (L ? 1 : 0);
         }
         // stable partition of the instances by tile -> tile ranges
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, cc + 3, 0, tile_bits,
-                                         hdr_tile, true, fused_k2, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s,
+                                         hdr_tile, true, true, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s,
                                          &st.launches);
         launch_tile_ranges(ctx->ikeys[ctx->inst_buf].as<uint32_t>(), D, cc + 3, ctx->ranges.as<uint2>(), num_tiles, s);
         st.launches += (D ? 1 : 0);
