@@ -178,17 +178,6 @@ void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_
                     const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
                     const uint32_t* owned_rows, cudaStream_t s);
 // zdepth (may be NULL): window depth of live rank j (scene-depth occlusion)
-// K2 fused with the first half of the binning (r02): the same records, and in the same kernel the exclusive scan of the
-// live-tile counts (one decoupled look-back per CTA over `status`: records_status_bytes(n_live) bytes, epoch tagged like the
-// sort's table, never cleared after allocation), the instance emit (tile id, live rank) at the scanned offsets, rows
-// ascending then columns ascending, live tiles only, the exact instance total (*d_total) and the digit histograms of the
-// tile partition that follows (tile_plan over [0, tile_bits); tile_hist zero before).  *ticket zero before.
-size_t records_status_bytes(int64_t n_live);
-void launch_records_emit(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                         const uint32_t* sat, Record* recs, float* zdepth, const uint32_t* owned_rows,
-                         unsigned long long* status, uint32_t epoch, uint32_t* ticket, const uint32_t* tile_done,
-                         uint32_t* inst_keys, uint32_t* inst_vals, unsigned long long* d_total,
-                         const SortPlan& tile_plan, uint32_t* tile_hist, uint32_t* error_flag, cudaStream_t s);
 
 // binning.cu
 // tile_done: saturation flags, one bit per tile, tile (tx, ty) at bit tx & 31 of word ty * done_words_per_row(tiles_x) +
@@ -227,8 +216,9 @@ void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t
                         const uint32_t* inst_refs, uint64_t d, uint32_t* inst_splats, cudaStream_t s);
 
 // ingest.cu: raw fp32 point attributes -> the arrays registerUpdate receives (NULL source = default)
+// activation: 0 = the attributes are Houdini's (the reference's contract), 1 = raw INRIA PLY columns, activated here (8f-2)
 void launch_ingest_core(const float* P, const float* Cd, const float* alpha, const float* scale, const float* orient,
-                        int64_t n, float* pos_out, uint16_t* cd_out, float* alpha_out, uint16_t* scale_out,
+                        int64_t n, int activation, float* pos_out, uint16_t* cd_out, float* alpha_out, uint16_t* scale_out,
                         uint16_t* orient_out, cudaStream_t s);
 // src = [n][len][3] (planar = 0, `sh_coefficients`) or [15][n][3] (planar = 1, `sh1`..`sh15`)
 void launch_ingest_sh_vec3(const float* src, int64_t n, int len, int planar, uint16_t* shx, uint16_t* shy, uint16_t* shz,

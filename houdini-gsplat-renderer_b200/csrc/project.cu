@@ -931,121 +931,6 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     if (valid) { tile_rects[j] = tr; counts[j] = cnt; }
 }
 
-// ---- K2 + count scan + instance emit + tile-sort histograms in ONE kernel (r02).  CTAs take their slice of the live list
-// from a ticket, so a CTA only ever waits for slices that already started: the single-value decoupled look-back below
-// cannot deadlock; its spin is bounded like the sort's.  status[t] = epoch << 32 | flag << 30 | count (30 bits).
-constexpr uint32_t ST_AGG = 0x40000000u, ST_INCL = 0x80000000u, ST_MASK = 0x3FFFFFFFu;
-struct TileSort { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; };
-template <int ORDER>
-__global__ void __launch_bounds__(K2_THREADS)
-records_emit_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
-                    const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
-                    Record* __restrict__ recs, float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows,
-                    unsigned long long* __restrict__ status, const uint32_t epoch, uint32_t* __restrict__ ticket,
-                    const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals,
-                    unsigned long long* __restrict__ d_total, const TileSort ts, uint32_t* __restrict__ tile_hist,
-                    uint32_t* __restrict__ error_flag)
-{
-    __shared__ uint4 srow[K2_THREADS / 32][32 * K2_PITCH];
-    __shared__ uint32_t sh_hist[SORT_MAX_PASSES][SORT_RADIX];
-    __shared__ uint32_t s_wsum[K2_THREADS / 32];
-    __shared__ uint32_t s_tile, s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < SORT_MAX_PASSES * SORT_RADIX; i += K2_THREADS) (&sh_hist[0][0])[i] = 0u;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t j = (int64_t)tile * K2_THREADS + threadIdx.x;
-    const bool valid = j < n_live;
-    const uint32_t my = valid ? __ldg(live_splats + j) : 0u;
-    uint2 tr;
-    const uint32_t cnt = record_one<ORDER>(F, rows, srow[warp], lane, my, valid, j, sat, recs, zdepth, owned_rows, tr);
-
-    // exclusive scan of the CTA's counts
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) s_wsum[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < K2_THREADS / 32; ++w) { woff += (w < warp) ? s_wsum[w] : 0u; total += s_wsum[w]; }
-    // decoupled look-back over the preceding slices (warp 0: 32 predecessors per step, independent loads)
-    if (warp == 0) {
-        const unsigned long long etag = (unsigned long long)epoch << 32;
-        if (lane == 0) {
-            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | (tile == 0 ? ST_INCL : ST_AGG) | (total & ST_MASK)) : "memory");
-        }
-        uint32_t excl = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            uint32_t spins = 0;
-            bool done = false;
-            while (!done) {
-                unsigned long long v = etag | ST_INCL;                   // before the first slice: an inclusive zero
-                if (t - lane >= 0) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(status + (t - lane)) : "memory");
-                const uint32_t lo = (uint32_t)v;
-                const bool pub = (uint32_t)(v >> 32) == epoch && (lo & (ST_AGG | ST_INCL)) != 0u;
-                const unsigned not_pub = __ballot_sync(0xffffffffu, !pub);
-                const unsigned incl = __ballot_sync(0xffffffffu, pub && (lo & ST_INCL) != 0u);
-                // usable prefix of the window: lanes before the first unpublished entry, up to and including the first inclusive one
-                const int first_bad = not_pub ? (__ffs(not_pub) - 1) : 32;
-                const unsigned incl_ok = incl & ((first_bad >= 32) ? 0xffffffffu : ((1u << first_bad) - 1u));
-                const int first_incl = incl_ok ? (__ffs(incl_ok) - 1) : -1;
-                const int use = first_incl >= 0 ? first_incl + 1 : first_bad;         // entries consumed this step
-                uint32_t part = (lane < use) ? (lo & ST_MASK) : 0u;
-                part = __reduce_add_sync(0xffffffffu, part);
-                excl += part;
-                t -= use;
-                if (first_incl >= 0) done = true;
-                else if (use == 0) {
-                    if (++spins > (1u << 22)) { if (lane == 0) atomicExch(error_flag, 1u); done = true; }
-                    __nanosleep(20);
-                }
-            }
-            if (lane == 0)
-                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | ST_INCL | ((excl + total) & ST_MASK)) : "memory");
-        }
-        if (lane == 0) {
-            s_base = excl;
-            if ((int64_t)(tile + 1) * K2_THREADS >= n_live) *d_total = (unsigned long long)excl + total;     // the last slice knows D
-        }
-    }
-    __syncthreads();
-    // emit this splat's instances at its scanned offset: rows ascending, columns ascending, live tiles only
-    if (cnt != 0u) {
-        size_t o = (size_t)s_base + woff + (inc - cnt);
-        const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
-        const int wpr = done_words_per_row(F.tiles_x);
-        for (int ty = ty0; ty <= ty1; ++ty) {
-            if (!owns_row(ty, F.row_rank, F.row_world, F.row_group)) continue;
-            for (int w = tx0 >> 5; w <= (tx1 >> 5); ++w) {
-                uint32_t live;
-                if (tile_done) live = live_word(tile_done, wpr, ty, w, tx0, tx1);
-                else {
-                    live = 0xffffffffu;
-                    if (w == (tx0 >> 5)) live &= 0xffffffffu << (tx0 & 31);
-                    if (w == (tx1 >> 5)) live &= 0xffffffffu >> (31 - (tx1 & 31));
-                }
-                while (live) {                                   // ascending columns
-                    const int b = __ffs(live) - 1;
-                    live &= live - 1;
-                    const uint32_t id = (uint32_t)(ty * F.tiles_x + w * 32 + b);
-                    inst_keys[o] = id; inst_vals[o] = (uint32_t)j; ++o;
-#pragma unroll
-                    for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
-                        if (ps < ts.passes) atomicAdd(&sh_hist[ps][(id >> ts.shift[ps]) & ((1u << ts.bits[ps]) - 1u)], 1u);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ts.passes * SORT_RADIX; i += K2_THREADS) {
-        const uint32_t v = (&sh_hist[0][0])[i];
-        if (v) atomicAdd(tile_hist + i, v);
-    }
-}
-
 }  // namespace
 
 void launch_pack(const float* pos, const uint16_t* cd_h, const float* alpha, const uint16_t* scale_h,
@@ -1162,30 +1047,6 @@ void launch_project(const FrameConsts& fc, const PackedSplats& ps, int64_t n,
 void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s)
 {
     choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, db, plan);
-}
-
-size_t records_status_bytes(int64_t n_live) { return (size_t)((n_live + K2_THREADS - 1) / K2_THREADS + 1) * sizeof(unsigned long long); }
-
-void launch_records_emit(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
-                         const uint32_t* sat, Record* recs, float* zdepth, const uint32_t* owned_rows,
-                         unsigned long long* status, uint32_t epoch, uint32_t* ticket, const uint32_t* tile_done,
-                         uint32_t* inst_keys, uint32_t* inst_vals, unsigned long long* d_total,
-                         const SortPlan& tile_plan, uint32_t* tile_hist, uint32_t* error_flag, cudaStream_t s)
-{
-    if (n_live <= 0) return;
-    const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
-    TileSort ts{};
-    ts.passes = tile_plan.passes;
-    for (int p = 0; p < tile_plan.passes; ++p) { ts.shift[p] = tile_plan.shift[p]; ts.bits[p] = tile_plan.bits[p]; }
-#define GSB_RE(O) records_emit_kernel<O><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, zdepth, owned_rows, status, \
-                      epoch, ticket, tile_done, inst_keys, inst_vals, d_total, ts, tile_hist, error_flag)
-    switch (fc.sh_order) {
-    case 0:  GSB_RE(0); break;
-    case 1:  GSB_RE(1); break;
-    case 2:  GSB_RE(2); break;
-    default: GSB_RE(3); break;
-    }
-#undef GSB_RE
 }
 
 void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,

@@ -44,10 +44,8 @@ namespace {
 constexpr int RS_THREADS = GSB_RS_THREADS;          // the wide shape: 512 threads x 8 keys (9-bit digits need 512 threads)
 constexpr int RS_ITEMS   = GSB_RS_ITEMS;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096: the granularity the scratch sizes are computed for
-// the narrow shape (r02): 256 threads x 8 keys for passes of <= 8 bits.  Same registers per thread, half the CTA: four
-// independent CTAs per SM instead of two, so the barrier / look-back phases of one tile overlap the ranking of three others
-// (ncu r02: the 512-thread tile partition passes stall mostly on barriers, 2 CTAs per SM, 48 % of the issue slots used)
-constexpr int RS_THREADS_NARROW = 256;
+// (r02 measured a 256-thread x 8-key shape for the <= 8-bit passes, four CTAs per SM instead of two: 3 % slower frames — the
+// per-tile fixed costs (counter clearing, barriers, look-back rows) double with the tile count; the template parameter stays)
 constexpr int RS_MAXBITS = 9;
 constexpr int RS_RADIX   = 1 << RS_MAXBITS;         // up to 512 bins per pass
 constexpr int RS_MAX_PASSES = 4;
@@ -356,26 +354,18 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
 {
     if (n_max == 0 || end_bit <= begin_bit) return 0;
     static bool attr_set = false;
-    static int wide_per_sm = GSB_RS_MINB, narrow_per_sm = 4;
-    static bool use_narrow = true;
+    static int pass_ctas_per_sm = GSB_RS_MINB;
     if (!attr_set) {
-#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmemT<RS_THREADS>))
+#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
         GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
         GSB_SET_ATTR(8); GSB_SET_ATTR(9);
 #undef GSB_SET_ATTR
-#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS_NARROW, 4, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmemT<RS_THREADS_NARROW>))
-        GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
-        GSB_SET_ATTR(8);
-#undef GSB_SET_ATTR
         int per = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, RS_THREADS, GSB_RS_MINB, BitsDigit>, RS_THREADS, sizeof(PassSmemT<RS_THREADS>)) == cudaSuccess && per >= 1)
-            wide_per_sm = per;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, RS_THREADS_NARROW, 4, BitsDigit>, RS_THREADS_NARROW, sizeof(PassSmemT<RS_THREADS_NARROW>)) == cudaSuccess && per >= 1)
-            narrow_per_sm = per;
-        const char* e = getenv("GSB_RS_NARROW");                 // GSB_RS_NARROW=0: every pass on the 512-thread shape
-        use_narrow = !(e && atoi(e) == 0);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, RS_THREADS, GSB_RS_MINB, BitsDigit>, RS_THREADS, sizeof(PassSmem)) == cudaSuccess && per >= 1)
+            pass_ctas_per_sm = per;
         attr_set = true;
     }
+    const unsigned nb = (unsigned)rs_blocks(n_max);
     const SortPlan sp = sort_plan(begin_bit, end_bit);
     PassPlan plan{};
     plan.key_min = key_min; plan.key_span = key_span; plan.passes = sp.passes;
@@ -383,37 +373,27 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     uint32_t* hist = header;
     uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
     if (!error_flag) error_flag = tickets + RS_MAX_PASSES;      // nobody looks: still a valid sink
-    // look-back rows per pass: one per tile of the shape the pass runs on
-    bool narrow[RS_MAX_PASSES]; unsigned tiles[RS_MAX_PASSES];
     size_t lb_off[RS_MAX_PASSES + 1]; lb_off[0] = 0;
-    for (int p = 0; p < plan.passes; ++p) {
-        narrow[p] = use_narrow && plan.bits[p] <= 8;
-        const size_t tile = (size_t)(narrow[p] ? RS_THREADS_NARROW : RS_THREADS) * RS_ITEMS;
-        tiles[p] = (unsigned)((n_max + tile - 1) / tile);
-        lb_off[p + 1] = lb_off[p] + ((size_t)tiles[p] << plan.bits[p]);
-    }
+    for (int p = 0; p < plan.passes; ++p) lb_off[p + 1] = lb_off[p] + ((size_t)nb << plan.bits[p]);
     if (!header_is_zero) cudaMemsetAsync(header, 0, sort_header_bytes(), s);
     if (!hist_ready) {
-        const unsigned nb = (unsigned)rs_blocks(n_max);
         const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
         os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n_max, n_dev, plan, hist);
         if (launches) *launches += 1;
     }
+    const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
+    const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     uint32_t* ain = aux0; uint32_t* aout = aux1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
-        const unsigned cap = (unsigned)(NUM_SMS * (narrow[p] ? narrow_per_sm : wide_per_sm));
-        const unsigned grid = tiles[p] < cap ? tiles[p] : cap;
-#define GSB_PASS_ARGS(B) (kin, vin, kout, vout, n_max, n_dev, BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, \
-                          hist + p * RS_RADIX, lookback + lb_off[p], tickets + p, error_flag, epoch, ain, aout)
-#define GSB_PASS(B) case B: if (narrow[p]) os_pass_kernel<(B > 8 ? 8 : B), RS_THREADS_NARROW, 4, BitsDigit><<<grid, RS_THREADS_NARROW, sizeof(PassSmemT<RS_THREADS_NARROW>), s>>> GSB_PASS_ARGS((B > 8 ? 8 : B)); \
-                            else os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmemT<RS_THREADS>), s>>> GSB_PASS_ARGS(B); break
+#define GSB_PASS(B) case B: os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n_max, n_dev, \
+                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], \
+                        tickets + p, error_flag, epoch, ain, aout); break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
         }
 #undef GSB_PASS
-#undef GSB_PASS_ARGS
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

@@ -191,7 +191,6 @@ struct gsb_context {
     DevBuf geomA_p, lam_p, orig, cells, cell_views, sel_cells;
     DevBuf arena;                                    // per-frame counters, histograms, sort headers, tile flags: ONE memset per frame
     DevBuf lookback;                                 // radix-sort look-back table (epoch tagged, cleared on allocation only)
-    DevBuf k2_status;                                // look-back status of the fused K2 count scan (same tagging)
     uint32_t sort_epoch = 0;
     cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
     std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
@@ -530,6 +529,8 @@ try {
     if (!ctx || !key || !a || !out) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: NULL argument");
     if (a->count < 0 || a->count > 0x3fffffffLL) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: bad count");
     if (a->count > 0 && !a->P) return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: P is required");
+    if (a->activation != GSB_ACT_NONE && a->activation != GSB_ACT_INRIA)
+        return fail(GSB_ERR_INVALID, "gsb_update_from_attributes: activation must be GSB_ACT_NONE or GSB_ACT_INRIA");
     CU(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof *out);
     const size_t n = (size_t)a->count;
@@ -576,7 +577,7 @@ try {
     CU(e.pos.ensure(n * 12 + 16)); CU(e.cd.ensure(n * 6 + 16)); CU(e.alpha.ensure(n * 4 + 16));
     CU(e.scale.ensure(n * 6 + 16)); CU(e.orient.ensure(n * 8 + 16));
     launch_ingest_core(dP.as<float>(), a->Cd ? dCd.as<float>() : nullptr, alpha_src ? dA.as<float>() : nullptr,
-                       a->scale ? dS.as<float>() : nullptr, a->orient ? dO.as<float>() : nullptr, a->count,
+                       a->scale ? dS.as<float>() : nullptr, a->orient ? dO.as<float>() : nullptr, a->count, a->activation,
                        e.pos.as<float>(), e.cd.as<uint16_t>(), e.alpha.as<float>(), e.scale.as<uint16_t>(), e.orient.as<uint16_t>(), s);
     if (sh_found) {
         CU(e.shx.ensure(n * 32)); CU(e.shy.ensure(n * 32)); CU(e.shz.ensure(n * 32));
@@ -1118,35 +1119,17 @@ try {
         st.launches += (L ? 1 : 0);
         const uint32_t* order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
-        // K2 + the first half of K4 in one kernel: records of the live splats in depth order, their live-tile counts scanned
-        // on the fly (decoupled look-back), instances emitted at the scanned offsets, the exact total D left on the device
-        // (cc + 3) and the digit histograms of the tile partition built on the way.
-        // r02 measured the fused kernel SLOWER than the separate ones (records + scan + emit: 144-163 us vs ~115 us per chunk at
-        // 20 M / 1080p: the serial per-thread emit and the look-back wait sit inside a 64-register, gather-latency-bound
-        // kernel), so it is off unless GSB_FUSED_K2=1; the separate emit kernel builds the tile histograms instead.
-        static const bool fused_k2 = [] { const char* e = getenv("GSB_FUSED_K2"); return e && atoi(e) != 0; }();
+        // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
+        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
+        st.launches += (L ? 1 : 0);
+        if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
+        // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device, cc + 3) -> instances (the emit also
+        // builds the digit histograms of the tile partition) -> stable partition by tile -> tile ranges
         const SortPlan tile_plan = sort_plan(0, tile_bits);
-        if (fused_k2) {
-            const size_t need = records_status_bytes((int64_t)L);
-            if (need > ctx->k2_status.cap) {
-                CU(ctx->k2_status.ensure(need + need / 2));
-                CU(cudaMemsetAsync(ctx->k2_status.p, 0, ctx->k2_status.cap, s));
-            }
-            launch_records_emit(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), zdepth, owned_rows,
-                                ctx->k2_status.as<unsigned long long>(), next_epoch(ctx), reinterpret_cast<uint32_t*>(cc + 4),
-                                first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), cc + 3,
-                                tile_plan, hdr_tile, err_flag, s);
-            st.launches += (L ? 1 : 0);
-            if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        } else {
-            launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
-            st.launches += (L ? 1 : 0);
-            if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-            exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
-            launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
-                        first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
-            st.launches += (L ? 1 : 0);
-        }
+        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
+                    first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
+        st.launches += (L ? 1 : 0);
         // stable partition of the instances by tile -> tile ranges
         ctx->inst_buf = radix_sort_pairs(ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(),
                                          ctx->ikeys[1].as<uint32_t>(), ctx->ivals[1].as<uint32_t>(), (size_t)D, cc + 3, 0, tile_bits,

@@ -1,14 +1,15 @@
-"""INRIA 3D-Gaussian-splatting ``.ply`` -> the point attributes the plugin consumes.
+"""INRIA 3D-Gaussian-splatting ``.ply`` -> the raw attribute arrays of ``gsb_update_from_attributes``.
 
 The reference has no PLY code: its example scene (/root/reference/hip/GSplatPlugin_simpleScene_v001.hip) loads the
 file with a File SOP and converts the INRIA columns with point wrangles, then casts to fp16 (SURVEY.md §2 row 12,
-§8a note N1).  ``activate_inria`` restates those wrangles:
+§8a note N1):
     Cd      = 0.28209479177387814 * f_dc + 0.5          (SH band 0 folded into the colour)
     opacity = 1 / (1 + exp(-opacity_raw))
     scale   = exp(scale_raw)
     orient  = normalize(rot_1, rot_2, rot_3, rot_0)     (Houdini quaternions are (x, y, z, w); INRIA stores w first)
     f_rest_j pass through (the renderer's f_rest encoding, GR_GSplat.C:173-184,357-366)
-all in fp32; the fp16 cast happens on the GPU in gsb_update_from_attributes (csrc/ingest.cu).  Host-side I/O, not hot path.
+That conversion runs ON THE GPU, inside the ingestion kernel (csrc/ingest.cu, ``activation = GSB_ACT_INRIA``), together
+with the fp16 cast; this module only reads the file and lines the raw columns up.  Host-side I/O, not hot path.
 """
 from __future__ import annotations
 
@@ -75,22 +76,21 @@ def write_ply(path, cols: dict):
         rec.tofile(f)
 
 
-def activate_inria(cols: dict) -> dict:
-    """INRIA columns -> attribute dict for GSplatRenderer.update (fp32)."""
+def inria_raw_attributes(cols: dict) -> dict:
+    """INRIA columns -> the RAW attribute dict for ``GSplatRenderer.update(..., activation=ACT_INRIA)``: nothing is
+    converted here (Cd = f_dc, opacity = logit, scale = log scale, orient = (rot_0, rot_1, rot_2, rot_3))."""
     f32 = lambda k: np.ascontiguousarray(cols[k], np.float32)
-    attrs = {"P": np.stack([f32("x"), f32("y"), f32("z")], axis=1)}
-    attrs["Cd"] = (SH_C0 * np.stack([f32("f_dc_0"), f32("f_dc_1"), f32("f_dc_2")], axis=1) + np.float32(0.5)).astype(np.float32)
-    attrs["opacity"] = (np.float32(1) / (np.float32(1) + np.exp(-f32("opacity")))).astype(np.float32)
-    attrs["scale"] = np.exp(np.stack([f32("scale_0"), f32("scale_1"), f32("scale_2")], axis=1)).astype(np.float32)
-    q = np.stack([f32("rot_1"), f32("rot_2"), f32("rot_3"), f32("rot_0")], axis=1)
-    norm = np.sqrt((q * q).sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
-    attrs["orient"] = (q / np.where(norm > 0, norm, np.float32(1))).astype(np.float32)
-    nrest = sum(1 for k in cols if k.startswith("f_rest_"))
-    if nrest >= 45:
+    attrs = {"P": np.stack([f32("x"), f32("y"), f32("z")], axis=1),
+             "Cd": np.stack([f32("f_dc_0"), f32("f_dc_1"), f32("f_dc_2")], axis=1),
+             "opacity": f32("opacity"),
+             "scale": np.stack([f32("scale_0"), f32("scale_1"), f32("scale_2")], axis=1),
+             "orient": np.stack([f32("rot_0"), f32("rot_1"), f32("rot_2"), f32("rot_3")], axis=1)}
+    if sum(1 for k in cols if k.startswith("f_rest_")) >= 45:
         for j in range(45):
             attrs[f"f_rest_{j}"] = f32(f"f_rest_{j}")
     return attrs
 
 
 def load_inria(path) -> dict:
-    return activate_inria(read_ply(path))
+    """Raw attributes of an INRIA .ply; pass them to ``GSplatRenderer.update(..., activation=ACT_INRIA)``."""
+    return inria_raw_attributes(read_ply(path))

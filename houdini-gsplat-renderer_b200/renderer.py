@@ -58,6 +58,7 @@ class FrameC(C.Structure):
 
 DEPTH_NONE, DEPTH_LESS, DEPTH_LEQUAL = 0, 1, 2
 WARN_OBJECT_LEVEL = 1
+ACT_NONE, ACT_INRIA = 0, 1
 
 
 class TargetC(C.Structure):
@@ -68,7 +69,7 @@ class TargetC(C.Structure):
 class RawAttributesC(C.Structure):
     _fields_ = [("count", C.c_int64), ("P", C.c_void_p), ("Cd", C.c_void_p), ("opacity", C.c_void_p), ("Alpha", C.c_void_p),
                 ("scale", C.c_void_p), ("orient", C.c_void_p), ("sh_coefficients", C.c_void_p),
-                ("sh_coefficients_len", C.c_int32), ("reserved0", C.c_int32),
+                ("sh_coefficients_len", C.c_int32), ("activation", C.c_int32),
                 ("sh", C.c_void_p * 15), ("f_rest", C.c_void_p * 45),
                 ("has_sh_order", C.c_int32), ("sh_order", C.c_int32), ("has_explicit_camera", C.c_int32),
                 ("explicit_camera", C.c_float * 3)]
@@ -196,7 +197,7 @@ class GSplatRenderer:
                                                *[_ptr(a) for a in arrs], out), "gsb_register_update")
         return out.value.decode()
 
-    def update(self, gdp: int, gversion, gvtx: int, attrs: dict) -> dict:
+    def update(self, gdp: int, gversion, gvtx: int, attrs: dict, activation: int = 0) -> dict:
         """GR_PrimGsplat::update (GR_GSplat.C:191-458) on the GPU: ``attrs`` maps Houdini attribute names to fp32 numpy
         arrays (P, Cd, opacity, Alpha, scale, orient, sh_coefficients | sh1..sh15 | f_rest_0..f_rest_44) plus the detail
         attributes gsplat__sh_order (int) and gsplat__explicit_camera_pos (3 floats).  Returns what update() leaves
@@ -216,6 +217,7 @@ class GSplatRenderer:
         P = np.ascontiguousarray(attrs["P"], np.float32); keep.append(P)
         ra = RawAttributesC()
         ra.count = P.shape[0]; ra.P = P.ctypes.data
+        ra.activation = int(activation)                  # ACT_INRIA: attrs are raw INRIA PLY columns (ply.inria_raw_attributes)
         ra.Cd = arr("Cd", (3,)); ra.opacity = arr("opacity", ()); ra.Alpha = arr("Alpha", ())
         ra.scale = arr("scale", (3,)); ra.orient = arr("orient", (4,))
         shc = attrs.get("sh_coefficients")

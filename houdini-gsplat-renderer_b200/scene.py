@@ -150,3 +150,36 @@ WORKLOADS = {
     "20M_sh3_4k":    dict(n=20_000_000, sh=True, width=3840, height=2160, seed=1004, orbit=False),
     "20M_sh3_8k":    dict(n=20_000_000, sh=True, width=7680, height=4320, seed=1004, orbit=False),
 }
+
+
+def make_inria_shell_columns(n: int, seed: int, shells: int = 3) -> dict:
+    """Raw INRIA-PLY columns of a SURFACE-like capture: points on a few nested, bumpy spherical shells
+    (a real capture is mostly surfaces, unlike the filled cube of §8d), flat splats lying in the tangent plane, opacities
+    as logits, scales as logs, quaternions w-first and un-normalised, SH degree 3 in f_dc / f_rest.  Feed it through
+    ply.write_ply / ply.load_inria / GSplatRenderer.update(..., activation=ACT_INRIA)."""
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    shell = rng.integers(0, shells, n)
+    radius = (0.45 + 0.25 * shell + 0.03 * np.sin(7.0 * d[:, 0]) * np.cos(5.0 * d[:, 1])).astype(np.float32)
+    pos = d * radius[:, None]
+    # tangent frame -> quaternion (x, y, z, w) of the rotation taking +z to the normal d
+    z = np.array([0.0, 0.0, 1.0], np.float32)
+    axis = np.cross(np.broadcast_to(z, d.shape), d)
+    s = np.linalg.norm(axis, axis=1, keepdims=True)
+    axis = np.where(s > 1e-6, axis / np.maximum(s, 1e-12), np.array([1.0, 0.0, 0.0], np.float32))
+    ang = np.arccos(np.clip(d[:, 2], -1, 1))
+    qxyz = axis * np.sin(ang / 2)[:, None]
+    qw = np.cos(ang / 2)
+    gain = (0.5 + rng.random(n)).astype(np.float32)                       # INRIA checkpoints do not store unit quaternions
+    s0 = 0.5 * (4.0 * np.pi * 0.7 ** 2 * shells / max(n, 1)) ** 0.5       # surface density -> splat size
+    ls = np.log(s0) + 0.4 * rng.standard_normal((n, 3))
+    ls[:, 2] -= 2.0                                                       # thin along the normal
+    cols = {"x": pos[:, 0], "y": pos[:, 1], "z": pos[:, 2],
+            "opacity": rng.normal(1.5, 2.0, n), "scale_0": ls[:, 0], "scale_1": ls[:, 1], "scale_2": ls[:, 2],
+            "rot_0": qw * gain, "rot_1": qxyz[:, 0] * gain, "rot_2": qxyz[:, 1] * gain, "rot_3": qxyz[:, 2] * gain}
+    for c in range(3):
+        cols[f"f_dc_{c}"] = rng.normal(0.3, 1.0, n)
+    for j in range(45):
+        cols[f"f_rest_{j}"] = rng.normal(0.0, 0.08, n)
+    return {k: np.ascontiguousarray(v, np.float32) for k, v in cols.items()}

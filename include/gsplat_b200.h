@@ -221,7 +221,11 @@ typedef struct gsb_raw_attributes {
     const float* orient;               /* [count][4]  (x,y,z,w), absent -> (0,0,0,1)  GR.C:312 */
     const float* sh_coefficients;      /* [count][sh_coefficients_len][3]  vec3-array attribute, tried first  GR.C:93-113 */
     int32_t      sh_coefficients_len;  /* vec3 entries per point; entries >= 15 are ignored */
-    int32_t      reserved0;
+    int32_t      activation;           /* enum gsb_activation.  GSB_ACT_INRIA: the arrays are the RAW columns of an INRIA 3DGS .ply
+                                           — Cd = f_dc_0..2, opacity = the logit, scale = log scales, orient =
+                                          (rot_0, rot_1, rot_2, rot_3) = (w, x, y, z), f_rest as is — and the conversion of the
+                                          example scene's wrangles (Cd = SH_C0 f_dc + 0.5, sigmoid, exp, quaternion reorder +
+                                          normalise) runs on the GPU inside the ingestion kernel */
     const float* sh[15];               /* sh1..sh15, each [count][3]; used if sh_coefficients is absent and all 15 exist  GR.C:115-128,160-171 */
     const float* f_rest[45];           /* f_rest_0..44, each [count]; used last, all 45 must exist; coefficient j = (f_rest_j, f_rest_j+15, f_rest_j+30)  GR.C:130-143,173-184,357-366 */
     int32_t      has_sh_order;         /* detail attribute gsplat__sh_order present  GR.C:284-289 */
@@ -229,6 +233,8 @@ typedef struct gsb_raw_attributes {
     int32_t      has_explicit_camera;  /* detail attribute gsplat__explicit_camera_pos present  GR.C:277-282 */
     float        explicit_camera[3];
 } gsb_raw_attributes;
+
+enum gsb_activation { GSB_ACT_NONE = 0, GSB_ACT_INRIA = 1 };
 
 /* What update() leaves in the GR primitive for its render() to push every pass (GR.C:438-457, 485-492). */
 typedef struct gsb_update_result {

@@ -10,6 +10,48 @@ from __future__ import annotations
 import numpy as np
 
 
+SH_C0 = np.float32(0.28209479177387814)
+
+
+def det_exp(x):
+    """exp(x) in float64 with + - * and rint only — the operation sequence of csrc/ingest.cu det_exp(), same bits."""
+    x = np.asarray(x, np.float64)
+    xc = np.clip(x, -745.0, 709.0)
+    k = np.rint(xc * 1.4426950408889634)
+    r = (xc - k * 6.93147180369123816490e-01) - k * 1.90821492927058770002e-10
+    p = np.full_like(r, 1.0 / 6227020800.0)
+    for c in (1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+              1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0):
+        p = p * r + c
+    ki = k.astype(np.int64)
+    k1 = np.where(ki >= 0, ki // 2, -((-ki) // 2))          # C integer division truncates toward zero
+    k2 = ki - k1
+    s1 = ((k1 + 1023) << 52).view(np.float64); s2 = ((k2 + 1023) << 52).view(np.float64)
+    out = (p * s1) * s2
+    out = np.where(x > 709.0, np.inf, np.where(x < -745.0, 0.0, out))
+    return np.where(np.isnan(x), x, out)
+
+
+def activate_inria(raw: dict) -> dict:
+    """The example scene's wrangles (SURVEY 8a note N1) on the raw INRIA columns, fp32 results — the restatement of what
+    csrc/ingest.cu does for activation = GSB_ACT_INRIA (same operations, same order)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    out = {k: v for k, v in raw.items() if k not in ("Cd", "opacity", "scale", "orient")}
+    if raw.get("Cd") is not None:
+        out["Cd"] = (SH_C0 * f32(raw["Cd"]) + np.float32(0.5)).astype(np.float32)
+    if raw.get("opacity") is not None:
+        out["opacity"] = (1.0 / (1.0 + det_exp(-f32(raw["opacity"]).astype(np.float64)))).astype(np.float32)
+    if raw.get("scale") is not None:
+        out["scale"] = det_exp(f32(raw["scale"]).astype(np.float64)).astype(np.float32)
+    if raw.get("orient") is not None:
+        q = f32(raw["orient"])
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        nn = np.sqrt(((x * x + y * y) + z * z) + w * w).astype(np.float32)
+        d = np.where(nn > 0, nn, np.float32(1)).astype(np.float32)
+        out["orient"] = np.stack([x / d, y / d, z / d, w / d], axis=1).astype(np.float32)
+    return out
+
+
 def update(attrs: dict) -> dict:
     P = np.ascontiguousarray(attrs["P"], np.float32)
     n = P.shape[0]

@@ -102,6 +102,45 @@ def test_ingested_prim_renders_like_a_registered_one(scene):
     r.close()
 
 
+def test_inria_ply_activation_on_the_gpu(tmp_path, oracle, scene):
+    """a raw INRIA .ply goes to the GPU as is; the wrangle conversion (SH_C0 f_dc + 0.5, sigmoid, exp,
+    quaternion reorder + normalise) and the half cast run in the ingestion kernel and equal the numpy restatement bit for
+    bit (deterministic exp on both sides).  The scene is surface-like (nested shells), unlike the benchmark's cube; the
+    production frame equals the oracle's frame of the activated attributes and the exact-K1 frame."""
+    from houdini_gsplat_renderer_b200 import ply, renderer as R
+    O, S = oracle, scene
+    cols = S.make_inria_shell_columns(200_000, 5)
+    cols["opacity"][:5] = [-200.0, 200.0, 0.0, -9.0, 40.0]           # saturating logits
+    cols["scale_0"][:3] = [-30.0, 12.0, 0.0]                         # half underflow / overflow of exp(scale)
+    cols["rot_0"][7] = cols["rot_1"][7] = cols["rot_2"][7] = cols["rot_3"][7] = 0.0   # zero quaternion: left as is
+    path = tmp_path / "shells.ply"
+    ply.write_ply(path, cols)
+    raw = ply.load_inria(path)
+    ref = I.update(I.activate_inria(raw))
+    r = R.GSplatRenderer(0)
+    res = r.update(0x9A, (1, 0, 0, 0), 0, raw, activation=R.ACT_INRIA)
+    assert res["sh_data_found"]
+    for which, name in ((0, "pos"), (1, "cd_h"), (2, "alpha"), (3, "scale_h"), (4, "orient_h"), (5, "shx_h"), (6, "shy_h"), (7, "shz_h")):
+        got = r.fetch_entry(res["id"], which)
+        want = np.ascontiguousarray(ref[name]).view(np.uint16 if which not in (0, 2) else np.float32).reshape(-1)
+        assert np.array_equal(got.view(want.dtype), want), name
+    # render it: production path == exact-K1 path == oracle (surface-like scene, camera outside the shells)
+    cl = S.SplatCloud(ref["pos"], ref["cd_h"], ref["alpha"], ref["scale_h"], ref["orient_h"], ref["shx_h"], ref["shy_h"], ref["shz_h"])
+    fr = S.orbit_frame(640, 360, 30.0)
+    r.setSphericalHarmonicsOrder(3)
+    f1 = np.zeros((360, 640, 4), np.float32)
+    r.draw([res["id"]], fr, host_rgba=f1)
+    st = r.stats()
+    r.set_option(R.OPT_LAZY_PROJECT, 0)
+    f2 = np.zeros_like(f1); r.draw([res["id"]], fr, host_rgba=f2)
+    assert np.array_equal(f1, f2)
+    F = O.make_frame(fr, O.camera_from_view(fr.view), np.asarray(res["barycentre"], np.float32), 3)
+    o = O.pipeline(F, cl)
+    assert np.abs(f1 - o["rgba"]).max() <= 2e-5 and st["n_consumed"] == o["n_consumed"]
+    assert f1[..., 3].max() > 0.9
+    r.close()
+
+
 def test_config1_simple_scene_cook(oracle, scene):
     """BASELINE config 1 (hip/GSplatPlugin_simpleScene_v001.hip: GSplatSOP builds prims from 10 k synthetic points, no
     render), SURVEY.md §8d: the 10 000-point seed-1001 SH-3 cloud -> HDK-free model of cookMySop/build (one prim, vertex i
