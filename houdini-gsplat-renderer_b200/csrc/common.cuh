@@ -226,6 +226,14 @@ void launch_ingest_sh_vec3(const float* src, int64_t n, int len, int planar, uin
 // rest = [45][n] (`f_rest_0`..`f_rest_44`)
 void launch_ingest_sh_rest(const float* rest, int64_t n, uint16_t* shx, uint16_t* shy, uint16_t* shz, cudaStream_t s);
 
+// wire.cu: the reference's wireframe vertex shader, once per splat: verts[8 n] = gl_Position of the outline's
+// 8 line vertices, colors[8 n][3] = Cd (may be NULL); and an overlay of the outlines into an RGBA32F frame (owner: width x
+// height u64 scratch; the nearest splat wins per pixel)
+void launch_wire_vertices(const FrameConsts& fc, const float* pos, const uint16_t* cd, const uint16_t* scale,
+                          const uint16_t* orient, int64_t n, float4* verts, float* colors, cudaStream_t s);
+void launch_wire_overlay(const float4* verts, const uint16_t* cd, int64_t n, int width, int height,
+                         unsigned long long* owner, float4* rgba, cudaStream_t s);
+
 // blend.cu
 // One depth chunk.  first: pixel state starts at (0,0,0,T=1), otherwise it is reloaded from fb, which between
 // chunks holds (C, T).  A tile whose pixels are all saturated is finalised to (C, 1-T) and flagged in tile_done (bit map);

@@ -208,6 +208,7 @@ struct gsb_context {
     struct cudaGraphicsResource* gl_res = nullptr;  // registered viewport texture (CUDA<->GL interop hand-back)
     uint32_t gl_tex = 0; int gl_w = 0, gl_h = 0;
     Stager stager;                                   // pinned double-buffered staging of the cold-path uploads
+    DevBuf wire_verts, wire_cols, wire_owner;         // wireframe overlay (gsb_render_wireframe)
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf scan_scratch;
     unsigned long long* counters_h = nullptr;        // pinned mirror: [0..8) frame counters, [8..16) the current chunk's, [16..) every chunk's at frame end
@@ -1200,6 +1201,47 @@ try {
     memcpy(st.camera, fc.cam, 12); memcpy(st.origin, fc.origin, 12);
     return GSB_OK;
 } GSB_CATCH_ALL
+
+// ------------------------------------------------------------------ wire pass of GR_PrimGsplat::render, GR.C:474-483 (SURVEY f-4)
+int gsb_render_wireframe(gsb_context* ctx, const char* id, const gsb_frame* fr, const gsb_wire_target* target)
+try {
+    if (!ctx || !id || !fr) return fail(GSB_ERR_INVALID, "gsb_render_wireframe: NULL argument");
+    if (fr->width < 1 || fr->height < 1 || fr->width > 65535 || fr->height > 65535)
+        return fail(GSB_ERR_LIMIT, "gsb_render_wireframe: screen size must be 1..65535");
+    auto it = ctx->registry.find(id);
+    if (it == ctx->registry.end()) return fail(GSB_ERR_NOT_FOUND, "gsb_render_wireframe: unknown id");
+    const Entry& e = *it->second;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)e.count;
+    FrameConsts fc{};
+    memcpy(fc.view, fr->view, 64); memcpy(fc.proj, fr->proj, 64); memcpy(fc.object, fr->object, 64);
+    memcpy(fc.inv_object, fr->inv_object, 64); memcpy(fc.obj_view, fr->obj_view, 64);
+    fc.width = fr->width; fc.height = fr->height; fc.W = (float)fr->width; fc.H = (float)fr->height;
+    float4* verts = target && target->device_vertices ? static_cast<float4*>(target->device_vertices) : nullptr;
+    if (!verts) { CU(ctx->wire_verts.ensure(n * 8 * 16 + 16)); verts = ctx->wire_verts.as<float4>(); }
+    float* cols = target && target->device_colors ? static_cast<float*>(target->device_colors) : nullptr;
+    if (!cols && target && target->host_colors) { CU(ctx->wire_cols.ensure(n * 8 * 12 + 16)); cols = ctx->wire_cols.as<float>(); }
+    launch_wire_vertices(fc, e.pos.as<float>(), e.cd.as<uint16_t>(), e.scale.as<uint16_t>(), e.orient.as<uint16_t>(), (int64_t)n,
+                         verts, cols, s);
+    if (target && target->overlay_rgba) {
+        CU(ctx->wire_owner.ensure((size_t)fr->width * fr->height * 8));
+        launch_wire_overlay(verts, e.cd.as<uint16_t>(), (int64_t)n, fr->width, fr->height, ctx->wire_owner.as<unsigned long long>(),
+                            static_cast<float4*>(target->overlay_rgba), s);
+    }
+    CU(cudaGetLastError());
+    bool sync = false;
+    if (target && target->host_vertices && n) { CU(cudaMemcpyAsync(target->host_vertices, verts, n * 8 * 16, cudaMemcpyDeviceToHost, s)); sync = true; }
+    if (target && target->host_colors && n) { CU(cudaMemcpyAsync(target->host_colors, cols, n * 8 * 12, cudaMemcpyDeviceToHost, s)); sync = true; }
+    if (target && target->overlay_host_rgba && target->overlay_rgba) {
+        CU(cudaMemcpyAsync(target->overlay_host_rgba, target->overlay_rgba, (size_t)fr->width * fr->height * 16, cudaMemcpyDeviceToHost, s));
+        sync = true;
+    }
+    if (sync) CU(cudaStreamSynchronize(s));
+    return GSB_OK;
+} GSB_CATCH_ALL
+
+void* gsb_wire_device_vertices(gsb_context* ctx) { return ctx ? ctx->wire_verts.p : nullptr; }
 
 // ------------------------------------------------------------------ postRender, R.C:660-678
 int gsb_post_render(gsb_context* ctx)

@@ -36,7 +36,8 @@ EXPORTS = ["gsb_abi_version", "gsb_create", "gsb_destroy", "gsb_last_error", "gs
            "gsb_get_stats", "gsb_set_stream", "gsb_synchronize", "gsb_device_framebuffer",
            "gsb_registry_size", "gsb_debug_fetch", "gsb_debug_sort_pairs", "gsb_debug_exclusive_scan",
            "gsb_ipc_export_frame", "gsb_ipc_open", "gsb_ipc_close", "gsb_copy_to_host",
-           "gsb_update_from_attributes", "gsb_debug_fetch_entry", "gsb_host_register", "gsb_host_unregister"]
+           "gsb_update_from_attributes", "gsb_debug_fetch_entry", "gsb_host_register", "gsb_host_unregister",
+           "gsb_render_wireframe", "gsb_wire_device_vertices"]
 
 
 class GsbError(RuntimeError):
@@ -64,6 +65,11 @@ ACT_NONE, ACT_INRIA = 0, 1
 class TargetC(C.Structure):
     _fields_ = [("device_rgba", C.c_void_p), ("host_rgba", C.c_void_p),
                 ("gl_texture", C.c_uint32), ("flags", C.c_uint32), ("final_rgba", C.c_void_p)]
+
+
+class WireTargetC(C.Structure):
+    _fields_ = [("device_vertices", C.c_void_p), ("device_colors", C.c_void_p), ("host_vertices", C.c_void_p),
+                ("host_colors", C.c_void_p), ("overlay_rgba", C.c_void_p), ("overlay_host_rgba", C.c_void_p)]
 
 
 class RawAttributesC(C.Structure):
@@ -130,6 +136,9 @@ def load_library() -> C.CDLL:
         lib.gsb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.gsb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.gsb_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
+        lib.gsb_render_wireframe.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(FrameC), C.POINTER(WireTargetC)]
+        lib.gsb_wire_device_vertices.restype = C.c_void_p
+        lib.gsb_wire_device_vertices.argtypes = [C.c_void_p]
         lib.gsb_update_from_attributes.argtypes = [C.c_void_p, C.POINTER(PrimKey), C.POINTER(RawAttributesC), C.POINTER(UpdateResultC)]
         lib.gsb_debug_fetch_entry.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = lib
@@ -273,6 +282,17 @@ class GSplatRenderer:
                                                                 depth_func, depth_range)
         t = TargetC(device_rgba, None if host_rgba is None else host_rgba.ctypes.data, 0, 0, final_rgba)
         self._ck(self._lib.gsb_render(self._h, C.byref(fc), C.byref(t)), "gsb_render")
+
+    def renderWireframe(self, registry_id: str, frame, count: int, overlay_rgba: int | None = None,
+                        overlay_host: np.ndarray | None = None):
+        """The wire pass of GR_PrimGsplat::render (GR_GSplat.C:474-483): returns ([8n,4] gl_Position, [8n,3] colour) of the
+        outline's line vertices; overlay_rgba (CUDA pointer): the outlines are also drawn into that frame."""
+        fc = frame if isinstance(frame, FrameC) else frame_to_c(frame)
+        verts = np.zeros((8 * count, 4), np.float32); cols = np.zeros((8 * count, 3), np.float32)
+        t = WireTargetC(None, None, verts.ctypes.data, cols.ctypes.data, overlay_rgba,
+                        None if overlay_host is None else overlay_host.ctypes.data)
+        self._ck(self._lib.gsb_render_wireframe(self._h, registry_id.encode(), C.byref(fc), C.byref(t)), "gsb_render_wireframe")
+        return verts, cols
 
     def postRender(self):
         self._ck(self._lib.gsb_post_render(self._h), "gsb_post_render")

@@ -251,6 +251,26 @@ typedef struct gsb_update_result {
 GSB_API int gsb_update_from_attributes(gsb_context* ctx, const gsb_prim_key* key, const gsb_raw_attributes* attrs,
                                        gsb_update_result* out);
 
+/* ---- wireframe / selection overlay: GR_PrimGsplat::render's wire pass (src/GR_GSplat.C:474-483), SURVEY.md §8 f-4 ------- */
+
+/* The reference keeps a VBO with 8 copies of every splat attribute (GR_GSplat.C:376-421) and runs its wire vertex shader
+ * (shaders/GSplatShaderSource.h:22-90) on all of them, drawn as RE_PRIM_LINES: the outline of each splat's +-2 sigma quad,
+ * colour = Cd.  Here the vertex shader runs once per splat on the GPU: vertices[8 count][4] = gl_Position of line vertices
+ * 0..7 (edges (0,1) (2,3) (4,5) (6,7)), colors[8 count][3] = Cd.  Everything optional; with all pointers NULL the vertices
+ * stay in a library buffer (gsb_wire_device_vertices).  overlay_rgba: the outlines are also rasterised into that RGBA32F
+ * device frame (frame.width x frame.height, row 0 = bottom): per pixel the nearest splat wins, colour (Cd, 1), pixels no
+ * line touches are left as they are. */
+typedef struct gsb_wire_target {
+    void* device_vertices;   /* caller-owned device buffer, 8 * count * 16 bytes (e.g. a mapped GL buffer); NULL = library buffer */
+    void* device_colors;     /* caller-owned device buffer, 8 * count * 12 bytes; NULL = not produced unless host_colors is set */
+    void* host_vertices;     /* optional host copies (the call returns when they are there) */
+    void* host_colors;
+    void* overlay_rgba;      /* optional device frame the outlines are drawn into */
+    void* overlay_host_rgba; /* optional host copy of overlay_rgba after the overlay */
+} gsb_wire_target;
+GSB_API int   gsb_render_wireframe(gsb_context* ctx, const char* id, const gsb_frame* frame, const gsb_wire_target* target);
+GSB_API void* gsb_wire_device_vertices(gsb_context* ctx);
+
 /* ---- additions the reference has no equivalent for -------------------------------------- */
 GSB_API int   gsb_set_option(gsb_context* ctx, int option, double value);
 GSB_API int   gsb_get_stats(gsb_context* ctx, gsb_stats* out);

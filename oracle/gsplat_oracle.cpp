@@ -644,6 +644,131 @@ int orc_render(const orc_frame* F, int64_t n,
     return 0;
 }
 
+/* ---------------------------------------------------------------- wireframe overlay
+ * The reference's wire vertex shader (SRC.h:22-90) for all 8 vertices of every splat: raw position (no origin round
+ * trip), covariance WITHOUT the object matrix (SRC.h:74), no culling.  verts[8 n][4] = gl_Position, colors[8 n][3] = Cd.
+ * Same fp32 operation order as csrc/wire.cu (bit-exact). */
+void orc_wire_vertices(const orc_frame* F, int64_t n, const float* pos, const uint16_t* cd_h, const uint16_t* scale_h,
+                       const uint16_t* orient_h, float* verts, float* colors)
+{
+    const float W = (float)F->width, H = (float)F->height;
+    const float* OV = F->obj_view; const float* P = F->proj; const float* V = F->view;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = pos + 3 * i;
+        float vc[3];
+        for (int r = 0; r < 3; ++r)
+            vc[r] = ((MAT(OV, r, 0) * p[0] + MAT(OV, r, 1) * p[1]) + MAT(OV, r, 2) * p[2]) + MAT(OV, r, 3);
+        float fy = -vc[1];
+        float clip[4];
+        for (int r = 0; r < 4; ++r)
+            clip[r] = ((MAT(P, r, 0) * vc[0] + MAT(P, r, 1) * fy) + MAT(P, r, 2) * vc[2]) + MAT(P, r, 3);
+        float sx = h2f(scale_h[3 * i]), sy = h2f(scale_h[3 * i + 1]), sz = h2f(scale_h[3 * i + 2]);
+        float qx = h2f(orient_h[4 * i]), qy = h2f(orient_h[4 * i + 1]), qz = h2f(orient_h[4 * i + 2]), qr = h2f(orient_h[4 * i + 3]);
+        float Rt[3][3];
+        Rt[0][0] = 1.0f - 2.0f * (qy * qy + qz * qz); Rt[0][1] = 2.0f * (qx * qy + qr * qz); Rt[0][2] = 2.0f * (qx * qz - qr * qy);
+        Rt[1][0] = 2.0f * (qx * qy - qr * qz); Rt[1][1] = 1.0f - 2.0f * (qx * qx + qz * qz); Rt[1][2] = 2.0f * (qy * qz + qr * qx);
+        Rt[2][0] = 2.0f * (qx * qz + qr * qy); Rt[2][1] = 2.0f * (qy * qz - qr * qx); Rt[2][2] = 1.0f - 2.0f * (qx * qx + qy * qy);
+        const float sc[3] = { sx, sy, sz };
+        float Mm[3][3], S[3][3];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) Mm[a][b] = sc[a] * Rt[a][b];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[a][b] = (Mm[0][a] * Mm[0][b] + Mm[1][a] * Mm[1][b]) + Mm[2][a] * Mm[2][b];
+        float t[3];
+        for (int r = 0; r < 3; ++r)
+            t[r] = ((MAT(V, r, 0) * p[0] + MAT(V, r, 1) * p[1]) + MAT(V, r, 2) * p[2]) + MAT(V, r, 3);
+        float aspect = MAT(P, 0, 0) / MAT(P, 1, 1);
+        float tanFovX = 1.0f / MAT(P, 0, 0);
+        float tanFovY = 1.0f / (MAT(P, 1, 1) * aspect);
+        float limX = 1.3f * tanFovX, limY = 1.3f * tanFovY;
+        float tz = t[2];
+        float rx = t[0] / tz; rx = fminf(fmaxf(rx, -limX), limX);
+        float ry = t[1] / tz; ry = fminf(fmaxf(ry, -limY), limY);
+        float tx = rx * tz, ty = ry * tz;
+        float focal = (W * MAT(P, 0, 0)) / 2.0f;
+        float j0 = focal / tz;
+        float tz2 = tz * tz;
+        float j2x = -((focal * tx) / tz2);
+        float j2y = -((focal * ty) / tz2);
+        float A0[3], A1[3], B0[3], B1[3];
+        for (int k = 0; k < 3; ++k) {
+            A0[k] = j0 * MAT(V, 0, k) + j2x * MAT(V, 2, k);
+            A1[k] = j0 * MAT(V, 1, k) + j2y * MAT(V, 2, k);
+        }
+        for (int k = 0; k < 3; ++k) {
+            B0[k] = (A0[0] * S[0][k] + A0[1] * S[1][k]) + A0[2] * S[2][k];
+            B1[k] = (A1[0] * S[0][k] + A1[1] * S[1][k]) + A1[2] * S[2][k];
+        }
+        float c00 = (B0[0] * A0[0] + B0[1] * A0[1]) + B0[2] * A0[2];
+        float c01 = (B0[0] * A1[0] + B0[1] * A1[1]) + B0[2] * A1[2];
+        float c11 = (B1[0] * A1[0] + B1[1] * A1[1]) + B1[2] * A1[2];
+        float a = c00 + 0.3f, b = c01, c = c11 + 0.3f;
+        float mid = 0.5f * (a + c);
+        float hd = (a - c) / 2.0f;
+        float radius = sqrtf(hd * hd + b * b);
+        float l1 = mid + radius;
+        float l2 = fmaxf(mid - radius, 0.1f);
+        float dvx = b, dvy = l1 - a;
+        float len = sqrtf(dvx * dvx + dvy * dvy);
+        float ex = dvx / len, ey = dvy / len;
+        float s1 = fminf(sqrtf(2.0f * l1), 4096.0f);
+        float s2 = fminf(sqrtf(2.0f * l2), 4096.0f);
+        float v1x = s1 * ex, v1y = s1 * (-ey);
+        float v2x = s2 * (-ey), v2y = s2 * (-ex);
+        static const float qcx[8] = { -2.f, 2.f, 2.f, 2.f, 2.f, -2.f, -2.f, -2.f };
+        static const float qcy[8] = { -2.f, -2.f, -2.f, 2.f, 2.f, 2.f, 2.f, -2.f };
+        for (int v = 0; v < 8; ++v) {
+            float dx = ((qcx[v] * v1x + qcy[v] * v2x) * 2.0f) / W;
+            float dy = ((qcx[v] * v1y + qcy[v] * v2y) * 2.0f) / H;
+            float* o = verts + (8 * i + v) * 4;
+            o[0] = clip[0] + dx * clip[3]; o[1] = -(clip[1] + dy * clip[3]); o[2] = clip[2]; o[3] = clip[3];
+            if (colors) { float* c3 = colors + (8 * i + v) * 3; c3[0] = h2f(cd_h[3 * i]); c3[1] = h2f(cd_h[3 * i + 1]); c3[2] = h2f(cd_h[3 * i + 2]); }
+        }
+    }
+}
+
+/* the outlines rasterised into rgba (H x W x 4, left as is where no line passes): per pixel the nearest splat wins (ties: the
+ * lower index), colour (Cd, 1).  Segment rule of csrc/wire.cu: n = ceil(max(|dx|, |dy|)) steps, samples a + (b - a)(i / n),
+ * pixel = floor; splats whose centre is outside GL's clip volume are skipped. */
+void orc_wire_overlay(int64_t n, const float* verts, const uint16_t* cd_h, int width, int height, float* rgba)
+{
+    std::vector<uint64_t> owner((size_t)width * height, ~0ull);
+    const float W = (float)width, H = (float)height;
+    for (int64_t seg = 0; seg < n * 4; ++seg) {
+        const int64_t i = seg >> 2;
+        const float* va = verts + (8 * i + 2 * (seg & 3)) * 4; const float* vb = va + 4;
+        const float w = va[3], z = va[2];
+        if (!(w > 0.0f) || !(z >= -w && z <= w)) continue;
+        const float ax = ((va[0] / w + 1.0f) * 0.5f) * W, ay = ((va[1] / w + 1.0f) * 0.5f) * H;
+        const float bx = ((vb[0] / w + 1.0f) * 0.5f) * W, by = ((vb[1] / w + 1.0f) * 0.5f) * H;
+        if (!(ax == ax) || !(ay == ay) || !(bx == bx) || !(by == by)) continue;
+        const float ddx = bx - ax, ddy = by - ay;
+        const float m = fmaxf(fabsf(ddx), fabsf(ddy));
+        if (!(m <= 1.0e9f)) continue;
+        int steps = (int)ceilf(m);
+        steps = steps < 1 ? 1 : (steps > 65536 ? 65536 : steps);
+        const float depth = z / w;
+        const float dk = depth * 0.5f + 0.5f;
+        uint32_t db; memcpy(&db, &dk, 4);
+        const uint64_t key = ((uint64_t)db << 32) | (uint64_t)(uint32_t)i;
+        const float fn = (float)steps;
+        for (int k = 0; k <= steps; ++k) {
+            const float tpar = (float)k / fn;
+            const float x = ax + ddx * tpar, y = ay + ddy * tpar;
+            const float fx = floorf(x), fyy = floorf(y);
+            if (fx >= 0.0f && fyy >= 0.0f && fx < W && fyy < H) {
+                uint64_t& o = owner[(size_t)fyy * width + (size_t)fx];
+                if (key < o) o = key;
+            }
+        }
+    }
+    for (size_t k = 0; k < owner.size(); ++k) {
+        if (owner[k] == ~0ull) continue;
+        const uint32_t i = (uint32_t)owner[k];
+        rgba[4 * k] = h2f(cd_h[3 * (size_t)i]); rgba[4 * k + 1] = h2f(cd_h[3 * (size_t)i + 1]); rgba[4 * k + 2] = h2f(cd_h[3 * (size_t)i + 2]);
+        rgba[4 * k + 3] = 1.0f;
+    }
+}
+
 int orc_num_threads(void) { return omp_get_max_threads(); }
 /* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline sets its thread count explicitly */
 void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -213,6 +213,26 @@ def pipeline(F: OrcFrame, cloud, scene_depth=None, depth_func=DEPTH_NONE, depth_
     return dict(pr, order=order, tile_start=ts, inst=inst, rgba=rgba, consumed=consumed, n_consumed=total)
 
 
+def wire_vertices(F: OrcFrame, cloud):
+    """the reference's wire vertex shader for the 8 outline vertices of every splat: ([8n,4] gl_Position, [8n,3] Cd)."""
+    pos = _c(cloud.pos, np.float32)
+    cd = _c(cloud.cd_h.view(np.uint16), np.uint16); sc = _c(cloud.scale_h.view(np.uint16), np.uint16)
+    orr = _c(cloud.orient_h.view(np.uint16), np.uint16)
+    n = pos.shape[0]
+    verts = np.zeros((8 * n, 4), np.float32); cols = np.zeros((8 * n, 3), np.float32)
+    lib().orc_wire_vertices(C.byref(F), C.c_int64(n), _p(pos), _p(cd), _p(sc), _p(orr), _p(verts), _p(cols))
+    return verts, cols
+
+
+def wire_overlay(verts: np.ndarray, cloud, width: int, height: int, rgba=None):
+    cd = _c(cloud.cd_h.view(np.uint16), np.uint16)
+    if rgba is None:
+        rgba = np.zeros((height, width, 4), np.float32)
+    v = _c(verts, np.float32)
+    lib().orc_wire_overlay(C.c_int64(v.shape[0] // 8), _p(v), _p(cd), C.c_int(width), C.c_int(height), _p(rgba))
+    return rgba
+
+
 def build_prim(pos: np.ndarray):
     pos = _c(pos, np.float32); n = pos.shape[0]
     v2p = np.empty(n, np.int32); bary = np.zeros(3, np.float32); bbox = np.zeros(6, np.float32)
