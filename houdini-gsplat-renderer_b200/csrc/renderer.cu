@@ -8,6 +8,7 @@
 //   tile ranges -> blend (finished tiles straight to the device / pinned host / peer-GPU frame) | optional D2H, GL interop.
 // No CPU fallback exists: every entry point fails with GSB_ERR_CUDA if the device is unusable.
 #include "common.cuh"
+#include "host_pool.h"
 #include "../../include/gsplat_b200.h"
 
 #include <algorithm>
@@ -15,8 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <string>
@@ -86,40 +90,24 @@ struct Entry {
 
 // ---- cold path (geometry change): host -> device through pinned, double-buffered staging.  A cudaMemcpyAsync from
 // pageable memory is staged by the driver through one small bounce buffer (r01: 2.64 GB in 0.64 s, 4 GB/s); here a few
-// host threads fill one pinned slot while the DMA engine drains the other, so the rate is min(host memcpy, PCIe).
-int host_threads()
-{
-    static int n = 0;
-    if (!n) { unsigned h = std::thread::hardware_concurrency(); n = (int)std::min(16u, std::max(1u, h)); }
-    return n;
-}
-
-template <class F> void parallel_ranges(size_t n, size_t grain, F&& f)      // f(begin, end) on disjoint ranges
-{
-    int t = (int)std::min<size_t>((size_t)host_threads(), (n + grain - 1) / std::max<size_t>(grain, 1));
-    if (t <= 1) { f((size_t)0, n); return; }
-    std::vector<std::thread> th;
-    th.reserve((size_t)t);
-    for (int k = 0; k < t; ++k) {
-        const size_t a = n * (size_t)k / (size_t)t, b = n * (size_t)(k + 1) / (size_t)t;
-        th.emplace_back([&f, a, b] { f(a, b); });
-    }
-    for (auto& x : th) x.join();
-}
+// host threads (a persistent pool, host_pool.h) fill one pinned slot while the DMA engine drains the others, so the rate is
+// min(host memcpy, PCIe).
+template <class F> void parallel_ranges(size_t n, size_t grain, F&& f) { HostPool::get().ranges(n, grain, std::forward<F>(f)); }
 
 struct Stager {
-    static constexpr size_t SLOT = (size_t)32 << 20;
-    char* slot[2] = { nullptr, nullptr };
-    cudaEvent_t done[2] = { nullptr, nullptr };
-    bool busy[2] = { false, false };
+    static constexpr size_t SLOT = (size_t)64 << 20;
+    static constexpr int NSLOT = 3;
+    char* slot[NSLOT] = { nullptr, nullptr, nullptr };
+    cudaEvent_t done[NSLOT] = { nullptr, nullptr, nullptr };
+    bool busy[NSLOT] = { false, false, false };
     int next = 0;
     ~Stager()
     {
-        for (int i = 0; i < 2; ++i) { if (slot[i]) cudaFreeHost(slot[i]); if (done[i]) cudaEventDestroy(done[i]); }
+        for (int i = 0; i < NSLOT; ++i) { if (slot[i]) cudaFreeHost(slot[i]); if (done[i]) cudaEventDestroy(done[i]); }
     }
     cudaError_t init()
     {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NSLOT; ++i) {
             if (!slot[i]) { cudaError_t e = cudaMallocHost(&slot[i], SLOT); if (e != cudaSuccess) return e; }
             if (!done[i]) { cudaError_t e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
         }
@@ -134,7 +122,7 @@ struct Stager {
         char* dp = static_cast<char*>(dst);
         for (size_t off = 0; off < bytes; off += SLOT) {
             const size_t len = std::min(SLOT, bytes - off);
-            const int k = next; next ^= 1;
+            const int k = next; next = (next + 1) % NSLOT;
             if (busy[k]) { e = cudaEventSynchronize(done[k]); if (e != cudaSuccess) return e; busy[k] = false; }
             char* buf = slot[k];
             parallel_ranges(len, (size_t)1 << 20, [&](size_t a, size_t b) { memcpy(buf + a, sp + off + a, b - a); });
