@@ -179,11 +179,13 @@ struct gsb_context {
     DevBuf geomA_p, lam_p, orig, cells, cell_views, sel_cells;
     DevBuf arena;                                    // per-frame counters, histograms, sort headers, tile flags: ONE memset per frame
     DevBuf lookback;                                 // radix-sort look-back table (epoch tagged, cleared on allocation only)
+    DevBuf emit_status;                              // look-back state of the emit's count scan (same tagging)
     uint32_t sort_epoch = 0;
     cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
     std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
     FrameConsts last_fc{}; bool last_lazy = false;   // for the on-demand debug view of the bound
     bool obj_level_warned = false;                   // _justPrintedOBJLevelRenderingWarning (R.h:127)
+    int auto_shift = 4; long long auto_key[4] = { -1, -1, -1, -1 };   // adaptive first-chunk size (gsb_render)
     uint32_t* last_tile_consumed = nullptr;
 
     // per-frame device buffers.  keys/trects: K1 output in submission order (never moved).
@@ -849,9 +851,12 @@ try {
 
     // depth chunks: the frame is binned and blended front to back in nchunks ranges of the depth order
     int nchunks = ctx->depth_chunks;
-    // auto (r01 sweeps on B200): a small first chunk that saturates most tiles + one chunk for the rest
-    // (20 M: 2 chunks, first = V/16: 2.36 ms vs 2.53 for 3 geometric chunks; 5 M: first = V/8; 1 M: one chunk)
-    if (nchunks <= 0) nchunks = (n >= (int64_t)2000000) ? 2 : 1;
+    // auto: a first chunk that saturates most tiles + the rest.  A chunk costs ~80 us of fixed work (selection, two sorts
+    // of small lists, launches) and every instance it avoids ~33 ns, so a third chunk pays when the instance count is large:
+    // at 4K and beyond (r02 sweeps, 20 M splats: 8K 5.57 ms with 3 chunks vs 5.78 with 2; 1080p 1.415 vs 1.403).
+    // The SIZE of the first chunk is not a constant: it follows the previous frame's outcome (auto_shift, below).
+    const bool auto_chunks = nchunks <= 0;
+    if (auto_chunks) nchunks = (n >= (int64_t)500000) ? (((int64_t)fr->width * fr->height >= (int64_t)3840 * 2160) ? 3 : 2) : 1;
     nchunks = std::min(nchunks, (int)MAX_CHUNKS);
 
     // Every depth key is the fp32 bit pattern of a squared distance from the camera to a point inside the packed set's
@@ -1007,8 +1012,14 @@ try {
     const ChunkPlan* chunk_plan = nullptr;
     if (nchunks > 1) {
         ChunkPlan* plan = ctx->plan.as<ChunkPlan>();
-        const int shift = ctx->chunk_shift > 0 ? ctx->chunk_shift
-                        : (ctx->depth_chunks > 0 ? nchunks : (n >= (int64_t)10000000 ? 4 : 3));   // explicit chunk count: geometric
+        // first chunk = V / 2^shift.  Explicit chunk count: geometric (shift = count).  Auto: the shift that the feedback
+        // below settled on for this (cloud, screen, chunk count); the starting guess only matters for the first frames
+        const long long akey[4] = { (long long)n, fr->width, fr->height, nchunks };
+        if (memcmp(akey, ctx->auto_key, sizeof akey) != 0) {
+            memcpy(ctx->auto_key, akey, sizeof akey);
+            ctx->auto_shift = nchunks + 1 + (n >= (int64_t)10000000 ? 1 : 0);
+        }
+        const int shift = ctx->chunk_shift > 0 ? ctx->chunk_shift : (ctx->depth_chunks > 0 ? nchunks : ctx->auto_shift);
         launch_choose_chunks(bucket_hist, nchunks, shift, db, plan, s);
         st.launches += 1;
         chunk_plan = plan;
@@ -1032,6 +1043,7 @@ try {
     for (int ty = 0; ty < fc.tiles_y; ++ty) n_owned_rows += owns_row(ty, fc.row_rank, fc.row_world, fc.row_group) ? 1 : 0;
     const uint64_t owned_tiles = (uint64_t)n_owned_rows * (uint64_t)fc.tiles_x;
     uint64_t L_total = 0, V = 0, D = 0, L = 0;
+    uint64_t L_chunk[MAX_CHUNKS] = {};
     int chunks_run = 0;
     // the live buffers are sized once for the cloud, so no size has to come back from the device before the selection
     // (exact K1: the second halves double as the selection's staging area: CTA-local runs, dead before the sort ping-pongs)
@@ -1081,6 +1093,7 @@ try {
         // the one host wait of the chunk: V, this chunk's L and bound of D, the tiles finished by the previous chunks
         CU(cudaEventSynchronize(ctx->ev_sel));
         V = ctx->counters_h[0]; L = ctx->counters_h[8]; D = ctx->counters_h[9];
+        L_chunk[c] = L;
         const bool all_done = ctx->counters_h[3] >= owned_tiles;        // implies L == 0
         // the last chunk that has work, or the last chunk at all, finalises the un-saturated tiles
         const bool last = (c == nchunks - 1) || all_done;
@@ -1101,22 +1114,27 @@ try {
             if (rc2) return rc2;
         }
         uint32_t* counts = ctx->counts.as<uint32_t>();
-        // ties of the depth sort in index order (the live list arrives in cell order): the final order
+        // the final order (ties of the depth sort in index order: the live list arrives in cell order) is settled by K2
         ctx->order_vals_buf = ctx->order_buf ^ 1;
-        launch_tie_fix(ctx->lkeys[ctx->order_buf].as<uint32_t>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), L, nullptr,
-                       ctx->lvals[ctx->order_vals_buf].as<uint32_t>(), s);
-        st.launches += (L ? 1 : 0);
-        const uint32_t* order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
+        uint32_t* const order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
-        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
+        launch_records(fc, ps, ctx->lkeys[ctx->order_buf].as<uint32_t>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), order, (int64_t)L, sat,
+                       ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device, cc + 3) -> instances (the emit also
-        // builds the digit histograms of the tile partition) -> stable partition by tile -> tile ranges
+        // K4: live-tile counts (K2) -> emit (scans them on the fly, leaves the exact total D on the device at cc + 3, builds the
+        // digit histograms of the tile partition) -> stable partition by tile -> tile ranges
         const SortPlan tile_plan = sort_plan(0, tile_bits);
-        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
-        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
+        {
+            const size_t need = emit_status_bytes((int64_t)L);
+            if (need > ctx->emit_status.cap) {
+                CU(ctx->emit_status.ensure(need + need / 2));
+                CU(cudaMemsetAsync(ctx->emit_status.p, 0, ctx->emit_status.cap, s));
+            }
+        }
+        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, ctx->emit_status.as<unsigned long long>(), next_epoch(ctx),
+                    reinterpret_cast<uint32_t*>(cc + 4), err_flag, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
         st.launches += (L ? 1 : 0);
         // stable partition of the instances by tile -> tile ranges
@@ -1132,6 +1150,18 @@ try {
                      zdepth, scene_depth, s);
         st.launches += 1;
         if (tm) CU(cudaEventRecord(ctx->evc[c][4], s));
+    }
+    // Feedback on the first chunk's size (auto mode).  Too small a first chunk leaves most tiles unsaturated and the LAST
+    // chunk then selects a large part of the cloud (20 M / 1080p: first = V/32 -> 6.2 M live splats instead of 2.8 M); too
+    // large a first chunk sorts, shades and bins splats nobody sees.  Balance: the last chunk's live count should stay
+    // between a quarter and twice the earlier chunks' sum; outside that band the shift moves by one for the next frame.
+    // Any value gives the same frame, so this only steers cost, never pixels.
+    if (auto_chunks && ctx->chunk_shift == 0 && nchunks > 1) {
+        uint64_t early = 0;
+        for (int c = 0; c + 1 < nchunks; ++c) early += L_chunk[c];
+        const uint64_t lastL = chunks_run == nchunks ? L_chunk[nchunks - 1] : 0;     // stopped early: every tile saturated
+        if (lastL > 2 * early && ctx->auto_shift > 1) --ctx->auto_shift;
+        else if (early > 4 * lastL && ctx->auto_shift < 10) ++ctx->auto_shift;
     }
     nchunks = chunks_run;
     CU(cudaGetLastError());
