@@ -198,86 +198,32 @@ select_gather_kernel(const uint32_t* __restrict__ stage_k, const uint32_t* __res
     }
 }
 
-// K4 emit: instance (tile id, live rank) pairs of live rank k at the exclusive prefix of the live-tile counts, rows ascending
-// then columns ascending, live tiles only.  The prefix is computed HERE: every CTA scans its 256 counts and obtains the sum
-// of all preceding slices with one decoupled look-back (status[t] = epoch << 32 | flag << 30 | count; slices are taken from a
-// ticket, so a CTA only waits for slices that already started; bounded spin + error flag) — r02: replaces a 3-kernel scan.
-// The exact instance total is left at *total by the last slice, and the digit histograms of the tile partition that
-// follows are built on the way (shared-memory bins, one flush per CTA), so the partition needs no pass of its own.
-constexpr uint32_t ST_AGG = 0x40000000u, ST_INCL = 0x80000000u, ST_MASK = 0x3FFFFFFFu;
+// instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only; the digit
+// histograms of the tile partition that follows are built on the way (shared-memory bins, one flush per CTA), so the
+// partition needs no pass of its own over the instance keys
 struct EmitSort { int shift[SORT_MAX_PASSES]; int bits[SORT_MAX_PASSES]; int passes; };
 __global__ void __launch_bounds__(256)
-emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ counts,
-            unsigned long long* __restrict__ total, unsigned long long* __restrict__ status, const uint32_t epoch,
-            uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag,
+emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ offsets,
+            const unsigned long long* __restrict__ total,
             int64_t n, int tiles_x, int row_rank, int row_world, int row_group,
             const uint32_t* __restrict__ tile_done, uint32_t* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals,
             const EmitSort es, uint32_t* __restrict__ tile_hist)
 {
     __shared__ uint32_t sh_hist[SORT_MAX_PASSES][SORT_RADIX];
-    __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_tile, s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) (&sh_hist[0][0])[i] = 0u;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t k = (int64_t)tile * 256 + threadIdx.x;
-    const uint32_t cnt = (k < n) ? __ldg(counts + k) : 0u;
-    // exclusive scan of the slice
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) s_wsum[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0, slice_total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { woff += (w < warp) ? s_wsum[w] : 0u; slice_total += s_wsum[w]; }
-    // decoupled look-back over the preceding slices (warp 0: 32 predecessors per step, independent loads)
-    if (warp == 0) {
-        const unsigned long long etag = (unsigned long long)epoch << 32;
-        if (lane == 0)
-            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | (tile == 0 ? ST_INCL : ST_AGG) | (slice_total & ST_MASK)) : "memory");
-        uint32_t excl = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            uint32_t spins = 0;
-            bool done = false;
-            while (!done) {
-                unsigned long long v = etag | ST_INCL;                   // before the first slice: an inclusive zero
-                if (t - lane >= 0) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(status + (t - lane)) : "memory");
-                const uint32_t lo = (uint32_t)v;
-                const bool pub = (uint32_t)(v >> 32) == epoch && (lo & (ST_AGG | ST_INCL)) != 0u;
-                const unsigned not_pub = __ballot_sync(0xffffffffu, !pub);
-                const unsigned incl = __ballot_sync(0xffffffffu, pub && (lo & ST_INCL) != 0u);
-                // usable part of the window: the lanes before the first unpublished entry, up to and including the first inclusive one
-                const int first_bad = not_pub ? (__ffs(not_pub) - 1) : 32;
-                const unsigned incl_ok = incl & ((first_bad >= 32) ? 0xffffffffu : ((1u << first_bad) - 1u));
-                const int first_incl = incl_ok ? (__ffs(incl_ok) - 1) : -1;
-                const int use = first_incl >= 0 ? first_incl + 1 : first_bad;
-                uint32_t part = (lane < use) ? (lo & ST_MASK) : 0u;
-                part = __reduce_add_sync(0xffffffffu, part);
-                excl += part;
-                t -= use;
-                if (first_incl >= 0) done = true;
-                else if (use == 0) {
-                    if (++spins > (1u << 22)) { if (lane == 0) atomicExch(error_flag, 1u); done = true; }
-                    __nanosleep(20);
-                }
-            }
-            if (lane == 0)
-                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(status + tile), "l"(etag | ST_INCL | ((excl + slice_total) & ST_MASK)) : "memory");
-        }
-        if (lane == 0) {
-            s_base = excl;
-            if ((int64_t)(tile + 1) * 256 >= n) *total = (unsigned long long)excl + slice_total;     // the last slice knows D
-        }
+    if (tile_hist) {
+        for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) (&sh_hist[0][0])[i] = 0u;
+        __syncthreads();
     }
-    __syncthreads();
-    if (cnt != 0u) {                                              // else: culled by K2, or every tile it touches is saturated
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t o0 = 0, o1 = 0;
+    if (k < n) {
+        o0 = offsets[k];
+        o1 = (k + 1 < n) ? offsets[k + 1] : (uint32_t)(*total);
+    }
+    if (o1 != o0) {                                              // else: every tile it touches is saturated
         const uint2 tr = __ldg(tile_rects + k);
         const int tx0 = (int)(tr.x & 0xffffu), tx1 = (int)(tr.x >> 16), ty0 = (int)(tr.y & 0xffffu), ty1 = (int)(tr.y >> 16);
-        size_t o = (size_t)s_base + woff + (inc - cnt);
+        size_t o = o0;
         const int wpr = done_words_per_row(tiles_x);
         for (int ty = ty0; ty <= ty1; ++ty) {
             if (!owns_row(ty, row_rank, row_world, row_group)) continue;
@@ -294,17 +240,21 @@ emit_kernel(const uint2* __restrict__ tile_rects, const uint32_t* __restrict__ c
                     live &= live - 1;
                     const uint32_t id = (uint32_t)(ty * tiles_x + w * 32 + b);
                     inst_keys[o] = id; inst_vals[o] = (uint32_t)k; ++o;
+                    if (tile_hist) {
 #pragma unroll
-                    for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
-                        if (ps < es.passes) atomicAdd(&sh_hist[ps][(id >> es.shift[ps]) & ((1u << es.bits[ps]) - 1u)], 1u);
+                        for (int ps = 0; ps < SORT_MAX_PASSES; ++ps)
+                            if (ps < es.passes) atomicAdd(&sh_hist[ps][(id >> es.shift[ps]) & ((1u << es.bits[ps]) - 1u)], 1u);
+                    }
                 }
             }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) {
-        const uint32_t v = (&sh_hist[0][0])[i];
-        if (v) atomicAdd(tile_hist + i, v);
+    if (tile_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < es.passes * SORT_RADIX; i += 256) {
+            const uint32_t v = (&sh_hist[0][0])[i];
+            if (v) atomicAdd(tile_hist + i, v);
+        }
     }
 }
 
@@ -335,6 +285,31 @@ tile_range_kernel(const uint32_t* __restrict__ ids, const uint64_t d_max, const 
         if (v[k] != t) ranges[t].x = (uint32_t)j;
         if (v[2 + k] != t) ranges[t].y = (uint32_t)(j + 1);
     }
+}
+
+// The spec's depth order is ascending key, ties by ascending splat index.  The live list reaches the depth
+// sort in cell order, not index order, so after the sort every run of equal keys is put in index order: element j of a run
+// [a, b) goes to a + (number of run members with a smaller index).  Runs are short (two or three splats at equal fp32
+// distance); the scan for the run's ends is bounded at TIE_MAX on either side — a run of more than TIE_MAX bit-identical
+// distances keeps the order the sort left it in (the reference's own sort leaves ties unspecified).
+constexpr int TIE_MAX = 1024;
+__global__ void __launch_bounds__(256)
+tie_fix_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint64_t l_max,
+               const unsigned long long* __restrict__ l_dev, uint32_t* __restrict__ vals_out)
+{
+    const uint64_t l = l_dev ? min((unsigned long long)l_max, *l_dev) : l_max;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= l) return;
+    const uint32_t k = __ldg(keys + j), v = __ldg(vals + j);
+    const bool tie_l = j > 0 && __ldg(keys + j - 1) == k, tie_r = j + 1 < l && __ldg(keys + j + 1) == k;
+    if (!tie_l && !tie_r) { vals_out[j] = v; return; }
+    uint64_t a = j, b = j + 1;
+    uint32_t smaller = 0;
+    for (int t = 0; t < TIE_MAX && a > 0 && __ldg(keys + a - 1) == k; ++t) { --a; smaller += (__ldg(vals + a) < v) ? 1u : 0u; }
+    for (int t = 0; t < TIE_MAX && b < l && __ldg(keys + b) == k; ++t) { smaller += (__ldg(vals + b) < v) ? 1u : 0u; ++b; }
+    // b - a <= TIE_MAX: neither scan hit its bound, [a, b) is the whole run and every member sees the same run, so the
+    // destinations are a permutation of it.  Otherwise the run is longer than TIE_MAX for every member: all stay put.
+    vals_out[(b - a <= (uint64_t)TIE_MAX) ? a + smaller : j] = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -384,17 +359,15 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
         stage_k, stage_v, tile_l, tile_base, nt, keys_out, vals_out);
 }
 
-size_t emit_status_bytes(int64_t n) { return (size_t)((n + 255) / 256 + 1) * sizeof(unsigned long long); }
-
-void launch_emit(const uint2* tile_rects, const uint32_t* counts, unsigned long long* total, unsigned long long* status,
-                 uint32_t epoch, uint32_t* ticket, uint32_t* error_flag, int64_t n, FrameConsts fc, const uint32_t* tile_done,
+void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
+                 const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, const SortPlan& tile_plan, uint32_t* tile_hist, cudaStream_t s)
 {
     if (n <= 0) return;
     EmitSort es{};
     es.passes = tile_plan.passes;
     for (int p = 0; p < tile_plan.passes; ++p) { es.shift[p] = tile_plan.shift[p]; es.bits[p] = tile_plan.bits[p]; }
-    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tile_rects, counts, total, status, epoch, ticket, error_flag, n, fc.tiles_x,
+    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tile_rects, offsets, total, n, fc.tiles_x,
                                                            fc.row_rank, fc.row_world, fc.row_group, tile_done, inst_keys, inst_vals,
                                                            es, tile_hist);
 }
@@ -405,6 +378,13 @@ void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const u
     cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s);
     if (d_max == 0) return;
     tile_range_kernel<<<(unsigned)((d_max + 1023) / 1024), 256, 0, s>>>(sorted_tile_ids, d_max, d_dev, ranges);
+}
+
+void launch_tie_fix(const uint32_t* keys_sorted, const uint32_t* vals_sorted, uint64_t l_max, const unsigned long long* l_dev,
+                    uint32_t* vals_out, cudaStream_t s)
+{
+    if (l_max == 0) return;
+    tie_fix_kernel<<<(unsigned)((l_max + 255) / 256), 256, 0, s>>>(keys_sorted, vals_sorted, l_max, l_dev, vals_out);
 }
 
 void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,

@@ -171,14 +171,10 @@ void launch_project_bound_debug(const FrameConsts& fc, const float4* geomA_p, co
 // and the bucket boundaries are turned into key boundaries (plan->key_lo: the smallest key whose bucket belongs to the
 // chunk, found by bisection over the monotone map key -> bucket -> chunk), so membership is two integer compares
 void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, DepthBuckets db, ChunkPlan* plan, cudaStream_t s);
-// K2 (only splats that reach a live tile, in depth order): (keys_sorted, vals_sorted) is the depth-sorted live list; the
-// kernel first settles ties (runs of equal keys go in ascending index order) and writes the final order to order_out, then
-// gathers the splat's 128-byte line, redoes the projection, evaluates SH, writes the 48-byte record of live rank j to
-// recs[j], its tile rectangle (tx0 | tx1 << 16, ty0 | ty1 << 16) to tile_rects[j] and the number of live tiles it touches to
-// counts[j] (sat: launch_live_sat, NULL = every tile live)
-constexpr int TIE_MAX = 1024;
-void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* keys_sorted, const uint32_t* vals_sorted,
-                    uint32_t* order_out, int64_t n_live,
+// K2 (only splats that reach a live tile, in depth order): gather the splat's 128-byte line, redo the projection,
+// evaluate SH, write the 48-byte record of live rank j to recs[j], its tile rectangle (tx0 | tx1 << 16, ty0 | ty1 << 16)
+// to tile_rects[j] and the number of live tiles it touches to counts[j] (sat: launch_live_sat, NULL = every tile live)
+void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
                     const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
                     const uint32_t* owned_rows, cudaStream_t s);
 // zdepth (may be NULL): window depth of live rank j (scene-depth occlusion)
@@ -205,17 +201,16 @@ void launch_select_live(const uint32_t* keys, const uint32_t* trects, const uint
                         cudaStream_t s);
 // instance (tile id, live rank) pairs at offsets[k] .., rows ascending then columns ascending, live tiles only;
 // tile_rects = K2's rectangles by live rank; offsets = exclusive scan of K2's counts, *total = its grand total (device)
-// K4 emit with the count scan inside: counts = K2's live-tile counts by live rank (NOT scanned); status =
-// emit_status_bytes(n) bytes of look-back state, epoch tagged like the sort's table (zero once after allocation, a fresh
-// epoch per call); *ticket zero before; *total receives the exact instance count; tile_hist (zero before) receives the digit
-// histograms of the tile partition described by tile_plan; *error_flag is set if the bounded look-back spin times out
-size_t emit_status_bytes(int64_t n);
-void launch_emit(const uint2* tile_rects, const uint32_t* counts, unsigned long long* total, unsigned long long* status,
-                 uint32_t epoch, uint32_t* ticket, uint32_t* error_flag, int64_t n, FrameConsts fc, const uint32_t* tile_done,
+// tile_hist (may be NULL; zero before): receives the digit histograms of the tile partition described by tile_plan
+void launch_emit(const uint2* tile_rects, const uint32_t* offsets,
+                 const unsigned long long* total, int64_t n, FrameConsts fc, const uint32_t* tile_done,
                  uint32_t* inst_keys, uint32_t* inst_vals, const SortPlan& tile_plan, uint32_t* tile_hist, cudaStream_t s);
 // d_max: host-side upper bound (grid size), d_dev: the exact count on the device (NULL: d_max is exact)
 void launch_tile_ranges(const uint32_t* sorted_tile_ids, uint64_t d_max, const unsigned long long* d_dev, uint2* ranges,
                         int num_tiles, cudaStream_t s);
+// after the depth sort: runs of equal keys are put in ascending value (= splat index) order; keys stay where they are
+void launch_tie_fix(const uint32_t* keys_sorted, const uint32_t* vals_sorted, uint64_t l_max, const unsigned long long* l_dev,
+                    uint32_t* vals_out, cudaStream_t s);
 // debug views (GSB_OPT_KEEP_INTERMEDIATES): records by splat index, instances as splat indices
 void launch_debug_views(const Record* recs, const uint32_t* live_splats, int64_t n_live, Record* recs_by_splat,
                         const uint32_t* inst_refs, uint64_t d, uint32_t* inst_splats, cudaStream_t s);

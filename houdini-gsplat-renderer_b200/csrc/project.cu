@@ -927,37 +927,10 @@ __device__ __forceinline__ uint32_t record_one(const FrameConsts& F, const uint4
     return count;
 }
 
-// The spec's depth order is ascending key, ties by ascending splat index.  The live list reaches the depth
-// sort in cell order, not index order, so every run of equal keys has to be put in index order afterwards: rank j of a run
-// [a, b) takes the run member that has exactly j - a smaller indices in the run.  Runs are short (two or three splats at
-// equal fp32 distance); the scan for the run's ends is bounded at TIE_MAX on either side — a run of more than TIE_MAX
-// bit-identical distances keeps the order the sort left it in (the reference's own sort leaves ties unspecified).
-// (r02 first did this in a kernel of its own, 11 us per chunk; K2 reads the sorted list anyway.)
-__device__ __forceinline__ uint32_t depth_rank_owner(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                     const int64_t j, const int64_t l)
-{
-    const uint32_t k = __ldg(keys + j), v = __ldg(vals + j);
-    const bool tie_l = j > 0 && __ldg(keys + j - 1) == k, tie_r = j + 1 < l && __ldg(keys + j + 1) == k;
-    if (!tie_l && !tie_r) return v;
-    int64_t a = j, b = j + 1;
-    for (int t = 0; t < TIE_MAX && a > 0 && __ldg(keys + a - 1) == k; ++t) --a;
-    for (int t = 0; t < TIE_MAX && b < l && __ldg(keys + b) == k; ++t) ++b;
-    if (b - a > (int64_t)TIE_MAX) return v;              // longer than TIE_MAX for every member: all stay put
-    const uint32_t want = (uint32_t)(j - a);
-    for (int64_t i = a; i < b; ++i) {
-        const uint32_t vi = __ldg(vals + i);
-        uint32_t smaller = 0;
-        for (int64_t m = a; m < b; ++m) smaller += (__ldg(vals + m) < vi) ? 1u : 0u;
-        if (smaller == want) return vi;
-    }
-    return v;                                            // (unreachable: indices are distinct)
-}
-
 template <int ORDER>
 __global__ void __launch_bounds__(K2_THREADS)
 records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ rows,
-               const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ vals_sorted, uint32_t* __restrict__ order_out,
-               const int64_t n_live, const uint32_t* __restrict__ sat,
+               const uint32_t* __restrict__ live_splats, const int64_t n_live, const uint32_t* __restrict__ sat,
                Record* __restrict__ recs, uint2* __restrict__ tile_rects, uint32_t* __restrict__ counts,
                float* __restrict__ zdepth, const uint32_t* __restrict__ owned_rows)
 {
@@ -965,8 +938,7 @@ records_kernel(const __grid_constant__ FrameConsts F, const uint4* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t j = (int64_t)blockIdx.x * K2_THREADS + threadIdx.x;
     const bool valid = j < n_live;
-    const uint32_t my = valid ? depth_rank_owner(keys_sorted, vals_sorted, j, n_live) : 0u;
-    if (valid) order_out[j] = my;                            // the final depth order (debug views, GSB_DBG_ORDER)
+    const uint32_t my = valid ? __ldg(live_splats + j) : 0u;
     uint2 tr;
     const uint32_t cnt = record_one<ORDER>(F, rows, srow[warp], lane, my, valid, j, sat, recs, zdepth, owned_rows, tr);
     if (valid) { tile_rects[j] = tr; counts[j] = cnt; }
@@ -1090,22 +1062,18 @@ void launch_choose_chunks(const uint32_t* bucket_hist, int nchunks, int shift, D
     choose_chunks_kernel<<<1, DEPTH_BUCKETS, 0, s>>>(bucket_hist, nchunks, shift, db, plan);
 }
 
-void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* keys_sorted, const uint32_t* vals_sorted,
-                    uint32_t* order_out, int64_t n_live,
+void launch_records(const FrameConsts& fc, const PackedSplats& ps, const uint32_t* live_splats, int64_t n_live,
                     const uint32_t* sat, Record* recs, uint2* tile_rects, uint32_t* counts, float* zdepth,
                     const uint32_t* owned_rows, cudaStream_t s)
 {
     if (n_live <= 0) return;
     const unsigned grid = (unsigned)((n_live + K2_THREADS - 1) / K2_THREADS);
-#define GSB_K2(O) records_kernel<O><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, keys_sorted, vals_sorted, order_out, n_live, sat, recs, tile_rects, \
-                      counts, zdepth, owned_rows)
     switch (fc.sh_order) {
-    case 0:  GSB_K2(0); break;
-    case 1:  GSB_K2(1); break;
-    case 2:  GSB_K2(2); break;
-    default: GSB_K2(3); break;
+    case 0:  records_kernel<0><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    case 1:  records_kernel<1><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    case 2:  records_kernel<2><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
+    default: records_kernel<3><<<grid, K2_THREADS, 0, s>>>(fc, ps.rows, live_splats, n_live, sat, recs, tile_rects, counts, zdepth, owned_rows); break;
     }
-#undef GSB_K2
 }
 
 }  // namespace gsb

@@ -179,7 +179,6 @@ struct gsb_context {
     DevBuf geomA_p, lam_p, orig, cells, cell_views, sel_cells;
     DevBuf arena;                                    // per-frame counters, histograms, sort headers, tile flags: ONE memset per frame
     DevBuf lookback;                                 // radix-sort look-back table (epoch tagged, cleared on allocation only)
-    DevBuf emit_status;                              // look-back state of the emit's count scan (same tagging)
     uint32_t sort_epoch = 0;
     cudaEvent_t ev_sel = nullptr;                    // "the chunk's selection counters are in pinned memory"
     std::vector<uint32_t> owned_rows_h; int owned_key[4] = { -1, -1, -1, -1 };
@@ -1114,27 +1113,24 @@ try {
             if (rc2) return rc2;
         }
         uint32_t* counts = ctx->counts.as<uint32_t>();
-        // the final order (ties of the depth sort in index order: the live list arrives in cell order) is settled by K2
+        // ties of the depth sort in index order (the live list arrives in cell order): the final order.  (r02 also measured
+        // this inside K2: the divergent tie loops cost the gather-bound kernel 32 us per frame, the separate kernel 23.)
         ctx->order_vals_buf = ctx->order_buf ^ 1;
-        uint32_t* const order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
+        launch_tie_fix(ctx->lkeys[ctx->order_buf].as<uint32_t>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), L, nullptr,
+                       ctx->lvals[ctx->order_vals_buf].as<uint32_t>(), s);
+        st.launches += (L ? 1 : 0);
+        const uint32_t* order = ctx->lvals[ctx->order_vals_buf].as<uint32_t>();
         if (tm) CU(cudaEventRecord(ctx->evc[c][1], s));
         // K2: records of the live splats, in depth order, plus their tile rectangles and live-tile counts
-        launch_records(fc, ps, ctx->lkeys[ctx->order_buf].as<uint32_t>(), ctx->lvals[ctx->order_buf].as<uint32_t>(), order, (int64_t)L, sat,
-                       ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
+        launch_records(fc, ps, order, (int64_t)L, sat, ctx->recs.as<Record>(), ctx->ltiles.as<uint2>(), counts, zdepth, owned_rows, s);
         st.launches += (L ? 1 : 0);
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
-        // K4: live-tile counts (K2) -> emit (scans them on the fly, leaves the exact total D on the device at cc + 3, builds the
-        // digit histograms of the tile partition) -> stable partition by tile -> tile ranges
+        // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device, cc + 3) -> instances (the emit also
+        // builds the digit histograms of the tile partition; r02 measured the scan INSIDE the emit, one decoupled look-back
+        // per CTA: 16 us slower per frame than the three small scan kernels) -> stable partition by tile -> tile ranges
         const SortPlan tile_plan = sort_plan(0, tile_bits);
-        {
-            const size_t need = emit_status_bytes((int64_t)L);
-            if (need > ctx->emit_status.cap) {
-                CU(ctx->emit_status.ensure(need + need / 2));
-                CU(cudaMemsetAsync(ctx->emit_status.p, 0, ctx->emit_status.cap, s));
-            }
-        }
-        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, ctx->emit_status.as<unsigned long long>(), next_epoch(ctx),
-                    reinterpret_cast<uint32_t*>(cc + 4), err_flag, (int64_t)L, fc,
+        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+        launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
         st.launches += (L ? 1 : 0);
         // stable partition of the instances by tile -> tile ranges
