@@ -49,7 +49,8 @@ constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096: the granularity the
 constexpr int RS_MAXBITS = 9;
 constexpr int RS_RADIX   = 1 << RS_MAXBITS;         // up to 512 bins per pass
 constexpr int RS_MAX_PASSES = 4;
-constexpr int LB_WIN     = 16;                      // predecessors inspected per look-back step (independent loads)
+constexpr int LB_WIN     = 16;                      // entries inspected per look-back step (independent loads)
+constexpr int LB_BLOCK   = 16;                      // tiles per look-back block (two-level look-back)
 
 constexpr uint32_t LB_AGG  = 0x40000000u;   // tile aggregate available
 constexpr uint32_t LB_INCL = 0x80000000u;   // inclusive prefix available
@@ -159,7 +160,7 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const size_t n_max,
                const unsigned long long* __restrict__ n_dev,
                const DigitFn dig, const uint32_t* __restrict__ hist,
-               unsigned long long* __restrict__ lookback, uint32_t* __restrict__ ticket,
+               unsigned long long* __restrict__ lookback, const unsigned tiles_max, uint32_t* __restrict__ ticket,
                uint32_t* __restrict__ error_flag, const uint32_t epoch,
                const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ aux_out)
 {
@@ -232,8 +233,7 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
 #pragma unroll
             for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = sm.cnt[w][threadIdx.x]; sm.cnt[w][threadIdx.x] = (uint16_t)total; total += c; }
             sm.tot[threadIdx.x] = total;
-            st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, etag | total | (tile == 0 ? LB_INCL : LB_AGG));
-            if (tile == 0) sm.excl[threadIdx.x] = 0u;
+            st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, etag | total | LB_AGG);
         }
         // exclusive scan of the digit totals across the block
         uint32_t inc = total;
@@ -260,21 +260,49 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
             }
         }
 
-        // Decoupled look-back, one thread per digit, LB_WIN predecessors per step: the LB_WIN volatile loads of a step are
-        // independent (one L2 round trip), rows of the [tile][digit] table are read coalesced across the warp.  With a window
-        // this wide the chain of not-yet-inclusive predecessors stays shorter than one window (equilibrium: resident tiles x
-        // round trip / (window x tile time) < 1); a narrow or serial walk lets it grow to the number of resident tiles.
-        // An entry whose epoch word is not this sort's is a leftover of an earlier sort: not published yet.
-        if (tile > 0 && (int)threadIdx.x < nbins) {
-            const unsigned long long* col = lookback + threadIdx.x;
-            uint32_t excl = 0, spins = 0;
-            int t = (int)tile - 1;
-            bool done = false;
+        // Decoupled look-back in TWO LEVELS (r02), one thread per digit.  A single-level walk over tile aggregates needs
+        // tile / LB_WIN dependent L2 round trips when no predecessor has an inclusive prefix yet — exactly the one-wave case
+        // of the depth sorts (342 tiles in flight at once: 19 round trips = 13 us of a 22 us pass).  Here tiles form blocks
+        // of LB_BLOCK; the last tile of a block also publishes the block's aggregate (as soon as its 15 predecessors in the
+        // block have published theirs) and later the inclusive prefix at the block's end.  A tile sums (1) the aggregates of
+        // the tiles before it in its own block: one batch of independent loads, and (2) block entries backwards in windows of
+        // LB_WIN until it meets an inclusive one: ceil(tile / 256) more round trips.  Rows of both tables are read coalesced
+        // across the warp; entries carry the sort's epoch (anything else = not published yet); every spin is bounded.
+        if ((int)threadIdx.x < nbins) {
+            const unsigned long long* agg_col = lookback + threadIdx.x;                 // [tile][nbins]: tile aggregates
+            unsigned long long* blk_col = lookback + (size_t)tiles_max * nbins + threadIdx.x;   // [block][nbins]
+            const int blk = (int)tile / LB_BLOCK, first = blk * LB_BLOCK, cnt_in = (int)tile - first;
+            const bool block_last = ((int)tile % LB_BLOCK) == LB_BLOCK - 1;
+            uint32_t excl_in = 0, excl_blk = 0, spins = 0;
+            bool failed = false;
+            // (1) tiles [first, tile) of this block
+            if (cnt_in > 0) {
+                for (;;) {
+                    unsigned long long val[LB_BLOCK - 1];
+#pragma unroll
+                    for (int j = 0; j < LB_BLOCK - 1; ++j)
+                        val[j] = (j < cnt_in) ? ld_volatile(agg_col + (size_t)(first + j) * nbins) : (etag | LB_AGG);
+                    bool all = true; uint32_t sum = 0;
+#pragma unroll
+                    for (int j = 0; j < LB_BLOCK - 1; ++j) {
+                        const uint32_t lo = (uint32_t)val[j];
+                        all = all && (uint32_t)(val[j] >> 32) == epoch && (lo & LB_AGG) != 0u;
+                        sum += lo & LB_MASK;
+                    }
+                    if (all) { excl_in = sum; break; }
+                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); failed = true; break; }
+                    __nanosleep(20);
+                }
+            }
+            if (block_last && !failed) st_volatile(blk_col + (size_t)blk * nbins, etag | ((excl_in + total) & LB_MASK) | LB_AGG);
+            // (2) the blocks before this one, nearest first, until an inclusive entry
+            int bq = blk - 1;
+            bool done = bq < 0 || failed;
             while (!done) {
                 unsigned long long val[LB_WIN];
 #pragma unroll
                 for (int j = 0; j < LB_WIN; ++j)
-                    val[j] = (t - j >= 0) ? ld_volatile(col + (size_t)(t - j) * nbins) : (etag | LB_INCL);
+                    val[j] = (bq - j >= 0) ? ld_volatile(blk_col + (size_t)(bq - j) * nbins) : (etag | LB_INCL);
                 int used = 0;
                 bool blocked = false;
 #pragma unroll
@@ -282,17 +310,18 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                     if (!done && !blocked) {
                         const uint32_t lo = (uint32_t)val[j];
                         if ((uint32_t)(val[j] >> 32) != epoch || (lo & (LB_AGG | LB_INCL)) == 0u) blocked = true;   // not published yet: retry from here
-                        else { excl += lo & LB_MASK; ++used; done = (lo & LB_INCL) != 0u; }
+                        else { excl_blk += lo & LB_MASK; ++used; done = (lo & LB_INCL) != 0u; }
                     }
                 }
-                t -= used;
+                bq -= used;
                 if (blocked) {
                     if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1u); break; }
                     __nanosleep(20);
                 }
             }
+            const uint32_t excl = excl_in + excl_blk;
             sm.excl[threadIdx.x] = excl;
-            st_volatile(lookback + (size_t)tile * nbins + threadIdx.x, etag | ((excl + total) & LB_MASK) | LB_INCL);
+            if (block_last) st_volatile(blk_col + (size_t)blk * nbins, etag | ((excl + total) & LB_MASK) | LB_INCL);
         }
         __syncthreads();
         if ((int)threadIdx.x < nbins)
@@ -323,7 +352,8 @@ size_t sort_header_bytes() { return ((RS_MAX_PASSES * RS_RADIX + 8) * sizeof(uin
 // look-back table for sorts of up to n_max elements: passes x tiles x 512 bins x 8 bytes (never cleared: epoch tagged)
 size_t sort_lookback_bytes(size_t n_max)
 {
-    return (size_t)RS_MAX_PASSES * (rs_blocks(n_max) + 1) * RS_RADIX * sizeof(unsigned long long) + 256;
+    const size_t nb = rs_blocks(n_max);
+    return (size_t)RS_MAX_PASSES * (nb + nb / LB_BLOCK + 2) * RS_RADIX * sizeof(unsigned long long) + 256;
 }
 
 int sort_key_bits(uint32_t key_span)
@@ -374,7 +404,7 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     uint32_t* tickets = hist + RS_MAX_PASSES * RS_RADIX;
     if (!error_flag) error_flag = tickets + RS_MAX_PASSES;      // nobody looks: still a valid sink
     size_t lb_off[RS_MAX_PASSES + 1]; lb_off[0] = 0;
-    for (int p = 0; p < plan.passes; ++p) lb_off[p + 1] = lb_off[p] + ((size_t)nb << plan.bits[p]);
+    for (int p = 0; p < plan.passes; ++p) lb_off[p + 1] = lb_off[p] + ((size_t)(nb + nb / LB_BLOCK + 2) << plan.bits[p]);   // tile rows + block rows
     if (!header_is_zero) cudaMemsetAsync(header, 0, sort_header_bytes(), s);
     if (!hist_ready) {
         const unsigned hist_grid = nb < (unsigned)(NUM_SMS * 4) ? nb : (unsigned)(NUM_SMS * 4);
@@ -388,7 +418,7 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
 #define GSB_PASS(B) case B: os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n_max, n_dev, \
-                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], \
+                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], nb, \
                         tickets + p, error_flag, epoch, ain, aout); break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
