@@ -98,7 +98,6 @@ void     exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* s
 //              never again: entries carry the epoch of the sort that wrote them.  epoch must differ from every epoch
 //              the table has seen (a counter)
 //   error_flag device word (may be NULL), set to 1 if a bounded look-back spin ever times out
-//   aux0/aux1  optional second 32-bit payload that rides along, ping-ponging like the values
 // The sort orders by min(key - key_min, key_span) (order-preserving for keys in [key_min, key_min + key_span),
 // everything above collapses onto key_span); pass end_bit = sort_key_bits(key_span) to sort only the bits that vary.
 constexpr int SORT_MAX_PASSES = 4;
@@ -111,7 +110,6 @@ int      radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1
                           const unsigned long long* n_dev, int begin_bit, int end_bit,
                           uint32_t* header, bool header_is_zero, bool hist_ready, unsigned long long* lookback, uint32_t epoch,
                           uint32_t* error_flag, cudaStream_t s, int* launches,
-                          uint32_t* aux0 = nullptr, uint32_t* aux1 = nullptr,
                           uint32_t key_min = 0u, uint32_t key_span = 0xFFFFFFFFu);
 int      sort_key_bits(uint32_t key_span);
 __host__ __device__ __forceinline__ uint32_t sort_squeeze(uint32_t key, uint32_t key_min, uint32_t key_span)

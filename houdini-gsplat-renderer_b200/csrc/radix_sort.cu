@@ -39,7 +39,7 @@ namespace {
 #define GSB_RS_ITEMS 8
 #endif
 #ifndef GSB_RS_MINB
-#define GSB_RS_MINB 2
+#define GSB_RS_MINB 3
 #endif
 constexpr int RS_THREADS = GSB_RS_THREADS;          // the wide shape: 512 threads x 8 keys (9-bit digits need 512 threads)
 constexpr int RS_ITEMS   = GSB_RS_ITEMS;
@@ -75,7 +75,6 @@ struct PassSmemT {
     uint32_t tile;
     uint32_t sk[RS_TILE];
     uint32_t sv[RS_TILE];
-    uint32_t sa[RS_TILE];               // auxiliary payload (optional)
 };
 using PassSmem = PassSmemT<RS_THREADS>;
 
@@ -161,8 +160,7 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                const unsigned long long* __restrict__ n_dev,
                const DigitFn dig, const uint32_t* __restrict__ hist,
                unsigned long long* __restrict__ lookback, const unsigned tiles_max, uint32_t* __restrict__ ticket,
-               uint32_t* __restrict__ error_flag, const uint32_t epoch,
-               const uint32_t* __restrict__ aux_in, uint32_t* __restrict__ aux_out)
+               uint32_t* __restrict__ error_flag, const uint32_t epoch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = PassSmemT<THREADS>;
@@ -176,7 +174,6 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     const size_t n = n_dev ? (size_t)min((unsigned long long)n_max, *n_dev) : n_max;
     const unsigned num_tiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
     const unsigned long long etag = (unsigned long long)epoch << 32;
-    const bool has_aux = aux_in != nullptr;
 
     // global digit offsets of this pass: exclusive scan of the histogram, once per CTA
     {
@@ -202,14 +199,12 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
 
         const size_t base = (size_t)tile * RS_TILE;
         const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
-        uint32_t k[RS_ITEMS], v[RS_ITEMS];
+        uint32_t k[RS_ITEMS];
         uint16_t rank[RS_ITEMS];
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) {
             size_t idx = item_index(base, warp, lane, j);
-            bool valid = idx < n;
-            k[j] = valid ? __ldg(keys_in + idx) : 0u;
-            v[j] = valid ? __ldg(vals_in + idx) : 0u;
+            k[j] = (idx < n) ? __ldg(keys_in + idx) : 0u;
         }
 
         // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
@@ -226,6 +221,15 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
             rank[j] = (uint16_t)(pre + __popc(peers & lt));
         }
         __syncthreads();
+
+        // the values are only needed for the reorder below: loading them here (not with the keys) keeps 8 registers free
+        // during the ranking (the kernel runs at 40 registers for 3 CTAs per SM) and their latency hides behind the scans
+        uint32_t v[RS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            size_t idx = item_index(base, warp, lane, j);
+            v[j] = (idx < n) ? __ldg(vals_in + idx) : 0u;
+        }
 
         // thread d: exclusive prefix over warps for digit d, tile total for d; publish the aggregate
         uint32_t total = 0;
@@ -256,7 +260,6 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                 uint32_t d = dig(k[j]);
                 uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
                 sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
-                if (has_aux) sm.sa[lp] = __ldg(aux_in + idx);       // the payload rides along (loaded late: short live range)
             }
         }
 
@@ -336,7 +339,6 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                 uint32_t d = dig(key);
                 size_t o = (size_t)(sm.global_delta[d] + i);
                 keys_out[o] = key; vals_out[o] = sm.sv[i];
-                if (has_aux) aux_out[o] = sm.sa[i];
             }
         }
         __syncthreads();                                                // smem is reused by the next ticket
@@ -379,8 +381,7 @@ SortPlan sort_plan(int begin_bit, int end_bit)
 int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, size_t n_max,
                      const unsigned long long* n_dev, int begin_bit, int end_bit,
                      uint32_t* header, bool header_is_zero, bool hist_ready, unsigned long long* lookback, uint32_t epoch,
-                     uint32_t* error_flag, cudaStream_t s, int* launches,
-                     uint32_t* aux0, uint32_t* aux1, uint32_t key_min, uint32_t key_span)
+                     uint32_t* error_flag, cudaStream_t s, int* launches, uint32_t key_min, uint32_t key_span)
 {
     if (n_max == 0 || end_bit <= begin_bit) return 0;
     static bool attr_set = false;
@@ -414,12 +415,11 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
     const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
-    uint32_t* ain = aux0; uint32_t* aout = aux1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
 #define GSB_PASS(B) case B: os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n_max, n_dev, \
                         BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], nb, \
-                        tickets + p, error_flag, epoch, ain, aout); break
+                        tickets + p, error_flag, epoch); break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
         }
@@ -427,7 +427,6 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
-        t = ain; ain = aout; aout = t;
         cur ^= 1;
     }
     if (launches) *launches += plan.passes;

@@ -1088,7 +1088,7 @@ try {
         ctx->order_buf = radix_sort_pairs(ctx->lkeys[0].as<uint32_t>(), ctx->lvals[0].as<uint32_t>(),
                                           ctx->lkeys[1].as<uint32_t>(), ctx->lvals[1].as<uint32_t>(), N, cc + 0, 0, key_bits,
                                           hdr_depth, true, lazy, ctx->lookback.as<unsigned long long>(), next_epoch(ctx), err_flag, s, &st.launches,
-                                          nullptr, nullptr, key_min, key_span);
+                                          key_min, key_span);
         // the one host wait of the chunk: V, this chunk's L and bound of D, the tiles finished by the previous chunks
         CU(cudaEventSynchronize(ctx->ev_sel));
         V = ctx->counters_h[0]; L = ctx->counters_h[8]; D = ctx->counters_h[9];
