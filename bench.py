@@ -275,10 +275,20 @@ def run_ours(args):
     r.set_stream(stream.cuda_stream)
     r.setSphericalHarmonicsOrder(sh_order)
 
-    # cold path: H2D of the prim's arrays + pack, timed once (geometry-change cost, GR_GSplat.C:302-372 + R.C:448-530)
+    # cold path: H2D of the prim's arrays + pack (geometry-change cost, GR_GSplat.C:302-372 + R.C:448-530).  The prim's
+    # barycentre is an INPUT of registerUpdate (the prim computes it when it cooks, GEO_GSplat.C:338-351), so it is taken
+    # before the clock starts.  Timed twice: the first registration of the process (device allocations of 7 GB, kernel
+    # module load) and a re-registration of the same prim under a new version (what a recook costs; the old entry is erased
+    # by registerUpdate like R.C:246-265) — the steady-state number.
+    origin = cloud.barycentre()
     torch.cuda.synchronize()
     t0 = time.time()
-    rid = r.registerUpdate(0xB200, (1, 0, 0, 0), 0, cloud)
+    rid = r.registerUpdate(0xB200, (1, 0, 0, 0), 0, cloud, origin)
+    r.includeInRenderPass(rid); r.generateRenderGeometry(); r.synchronize()
+    cold_first_ms = (time.time() - t0) * 1e3
+    r.postRender()
+    t0 = time.time()
+    rid = r.registerUpdate(0xB200, (2, 0, 0, 0), 0, cloud, origin)
     r.includeInRenderPass(rid); r.generateRenderGeometry(); r.synchronize()
     cold_upload_ms = (time.time() - t0) * 1e3
     h2d_cold = N * (132 if w["sh"] else 36)
@@ -461,6 +471,9 @@ def run_ours(args):
                         "returns when the frame is there; geometry resident (the reference also re-uploads only on active-set change)"},
         "e2e_cold_ms": cold_upload_ms, "e2e_cold_h2d_bytes": h2d_cold,
         "e2e_cold_GBps": h2d_cold / (cold_upload_ms * 1e-3) / 1e9,
+        "e2e_cold_first_ms": cold_first_ms, "e2e_cold_first_GBps": h2d_cold / (cold_first_ms * 1e-3) / 1e9,
+        "e2e_cold_note": "registerUpdate (pageable host arrays -> HBM) + generateRenderGeometry (pack, Morton cells): first call of "
+                         "the process, and a re-registration under a new version (steady state)",
         "gpu_launches": cnt["launches"],
         "roofline": {"kernel": "blend_kernel", "bound": "hbm", "achieved": blend_ach, "peak": peak, "unit": "GB/s",
                      "frac": blend_ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

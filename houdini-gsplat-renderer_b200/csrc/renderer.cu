@@ -18,6 +18,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <functional>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -92,6 +93,24 @@ struct Entry {
 // pageable memory is staged by the driver through one small bounce buffer (r01: 2.64 GB in 0.64 s, 4 GB/s); here a few
 // host threads (a persistent pool, host_pool.h) fill one pinned slot while the DMA engine drains the others, so the rate is
 // min(host memcpy, PCIe).
+// GSB_TRACE_COLD=1 in the environment: wall-clock phases of the cold path on stderr (a diagnostic, not an interface)
+struct ColdTrace {
+    const char* what; bool on; std::chrono::steady_clock::time_point t0, tl; std::string line;
+    explicit ColdTrace(const char* w) : what(w), on(getenv("GSB_TRACE_COLD") != nullptr), t0(std::chrono::steady_clock::now()), tl(t0) {}
+    void mark(const char* phase)
+    {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        char b[96]; snprintf(b, sizeof b, " %s=%.1f", phase, std::chrono::duration<double, std::milli>(t - tl).count());
+        line += b; tl = t;
+    }
+    ~ColdTrace()
+    {
+        if (!on) return;
+        fprintf(stderr, "[gsb cold] %s total=%.1f ms:%s\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), line.c_str());
+    }
+};
 template <class F> void parallel_ranges(size_t n, size_t grain, F&& f) { HostPool::get().ranges(n, grain, std::forward<F>(f)); }
 
 struct Stager {
@@ -385,6 +404,9 @@ try {
     CU(cudaMallocHost(&c->counters_h, (16 + MAX_CHUNKS * 8) * 8));
     memset(c->counters_h, 0, (16 + MAX_CHUNKS * 8) * 8);
     CU(c->plan.ensure(sizeof(ChunkPlan)));
+    // the cold path's pinned slots and host threads exist from here on: the first registration does not pay for them
+    CU(c->stager.init());
+    (void)HostPool::get();
     *out = c.release();
     return GSB_OK;
 } GSB_CATCH_ALL
@@ -479,7 +501,9 @@ try {
     const size_t n = (size_t)splat_count;
     cudaStream_t s = ctx->stream;
     int rc;
+    ColdTrace tr("gsb_register_update");
     if ((rc = upload(ctx->stager, e.pos, pos, n * 12, s))) return rc;
+    tr.mark("pos");
     // bounding box of the prim (bounds the depth keys, see gsb_render): host threads, while the first DMA runs
     e.bbox_valid = n > 0;
     if (n > 0) {
@@ -488,16 +512,20 @@ try {
         e.bbox_valid = finite;
         for (int k = 0; k < 3; ++k) { e.bbox[k] = lo[k]; e.bbox[3 + k] = hi[k]; }
     }
+    tr.mark("bbox");
     if ((rc = upload(ctx->stager, e.cd, cd_h, n * 6, s))) return rc;
     if ((rc = upload(ctx->stager, e.alpha, alpha, n * 4, s))) return rc;
     if ((rc = upload(ctx->stager, e.scale, scale_h, n * 6, s))) return rc;
     if ((rc = upload(ctx->stager, e.orient, orient_h, n * 8, s))) return rc;
+    tr.mark("cd_alpha_scale_orient");
     if (e.has_sh) {
         if ((rc = upload(ctx->stager, e.shx, shx_h, n * 32, s))) return rc;
         if ((rc = upload(ctx->stager, e.shy, shy_h, n * 32, s))) return rc;
         if ((rc = upload(ctx->stager, e.shz, shz_h, n * 32, s))) return rc;
+        tr.mark("sh");
     }
     CU(cudaStreamSynchronize(s));      // the caller's arrays are not borrowed past this call
+    tr.mark("sync");
 
     // same gdp, different version -> erase (R.C:246-265); then the entry replaces any older one under the same id
     for (auto it = ctx->registry.begin(); it != ctx->registry.end();) {
@@ -741,7 +769,9 @@ try {
     }
 
     const size_t n = (size_t)ctx->splat_count;
+    ColdTrace tr("gsb_generate_render_geometry");
     CU(ctx->geomA.ensure(n * 16)); CU(ctx->geomB.ensure(n * 16)); CU(ctx->rows.ensure(n * ROW_U4 * 16));
+    tr.mark("alloc_packed");
     int64_t offset = 0;
     for (auto& id : ctx->active_set) {                     // R.C:420-511
         const Entry& e = *ctx->registry[id];
@@ -767,6 +797,7 @@ try {
         CU(hdr.ensure(sort_header_bytes()));
         int rc2 = ensure_lookback(ctx, n);
         if (rc2) return rc2;
+        tr.mark("alloc_cells");
         float bb[6] = { 0, 0, 0, 0, 0, 0 };
         if (ctx->bbox_valid) memcpy(bb, ctx->bbox, sizeof bb);          // invalid box: every key 0, the order stays the index order
         launch_morton(ctx->geomA.as<float4>(), (int64_t)n, bb, mk[0].as<uint32_t>(), mi[0].as<uint32_t>(), ctx->stream);
@@ -777,6 +808,7 @@ try {
         launch_gather_geom(ctx->orig.as<uint32_t>(), ctx->geomA.as<float4>(), (int64_t)n, ctx->geomA_p.as<float4>(), ctx->stream);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(ctx->stream));                          // the temporaries die here
+        tr.mark("pack_morton_gather");
     }
     ctx->sigma_valid = false; ctx->sigma_planes_valid = false;
     ctx->can_render = true;

@@ -41,11 +41,19 @@ class SplatCloud:
 
     def barycentre(self) -> np.ndarray:
         """GEO_PrimGsplat::baryCenter (GEO_GSplat.C:338-351): sequential fp32 sum / N."""
+        cached = getattr(self, "_bary", None)           # (id of the position array, value): a replaced array recomputes
+        if cached is not None and cached[0] == id(self.pos):
+            return cached[1]
         s = np.zeros(3, dtype=np.float32)
         # sequential fp32 accumulation, done per axis with cumsum (which is sequential in numpy)
         for k in range(3):
             s[k] = np.cumsum(self.pos[:, k], dtype=np.float32)[-1] if self.n else 0.0
-        return (s / np.float32(self.n)).astype(np.float32)
+        b = (s / np.float32(self.n)).astype(np.float32)
+        try:
+            object.__setattr__(self, "_bary", (id(self.pos), b))   # the prim computes it at cook time too (GEO_GSplat.C:338)
+        except Exception:
+            pass
+        return b
 
     def subset(self, idx) -> "SplatCloud":
         f = lambda a: None if a is None else np.ascontiguousarray(a[idx])
