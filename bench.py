@@ -523,8 +523,10 @@ def run_ours(args):
                 "pixels_over_1e-3": int(over.sum()), "pixels_over_1e-3_not_flagged": int((over & ~unsafe).sum()),
                 "flagged_pixels": int(unsafe.sum()), "pixels": int(unsafe.size),
                 "note": "reference semantics has no early termination (GPU stops a pixel at T < 1e-5: error <= 1e-5 * max rgb); "
-                        "flagged = a support edge or the 1/255 discard ring of a still-visible splat passes within 2e-5 of the "
-                        "pixel centre, where one ulp of evaluation order decides coverage"}
+                        "flagged = a support edge or the 1/255 discard ring of a still-visible splat passes within tol_q of the "
+                        "pixel centre, tol_q = 2e-5 + 2 ulp_fp32(screen extent) x |grad q| in the splat's own q units (a 2 px "
+                        "splat at x = 1900 has a q uncertainty of 1e-4 under ANY fp32 evaluation), where one ulp of evaluation "
+                        "order decides coverage (oracle/ref_harness.cpp ref_draw_ex)"}
             ok = ok and bool(d2[~unsafe].max() <= 1e-3) and int((over & ~unsafe).sum()) == 0
             baseline = {"value": ns2 / t2 / 1e6, "unit": "Msplats/s", "cores": rcores, "kind": "reference",
                         "sample": "one whole frame (incl. the edge-pixel diagnostic): " + ref_sample_note(st2, ns2, N, args.workload, w, rcores),

@@ -290,7 +290,8 @@ void ref_draw(float* rgba, const float* scene_depth, int depth_func, int64_t* st
 }
 
 /* unsafe (H x W bytes, may be NULL): set to 1 where some splat's support edge (|q.x| = 2, |q.y| = 2) or discard threshold
- * (alpha = 1/255) passes within tol of the pixel centre — there a last-bit difference in the evaluation order of the
+ * (alpha = 1/255) passes within tol_q of the pixel centre (tol_q = tol + the splat's own fp32 position uncertainty in q
+ * units, see below) — there a last-bit difference in the evaluation order of the
  * reference's formulas decides coverage, so two valid evaluations of the same GLSL may differ by up to alpha there
  * (SURVEY.md §7 "discontinuous support") — provided the fragment could still change the pixel by more than 1e-4 (its
  * opacity times the transmittance left at that point).  Diagnostic only; the frame itself does not depend on it. */
@@ -352,6 +353,18 @@ void ref_draw_ex(float* rgba, const float* scene_depth, int depth_func, int64_t*
                             const double yw = ((double)o[v].p[1] / (double)o[v].p[3] * 0.5 + 0.5) * H;
                             xmn = std::min(xmn, xw); xmx = std::max(xmx, xw); ymn = std::min(ymn, yw); ymx = std::max(ymx, yw);
                         }
+                        /* tolerance of THIS splat in q units.  Any fp32 evaluation of the reference's formulas carries the
+                         * window position to one ulp of the screen extent (delta_px: the reference's NDC vertices are fp32, one
+                         * ulp of 1.0 is W / 2 * 2^-23 px; a pixel-space evaluation subtracts fp32 centres with ulp 2^-23 * W),
+                         * and q changes by |grad q|_1 per pixel — so a 2 px splat at x = 1900 has a q uncertainty of ~1e-4,
+                         * five times the floor `tol`.  tol_q = tol + 2 * delta_px * |grad q|_1. */
+                        const double gx0 = ((Y[2] - Y[0]) * (o[1].pos[0] - o[0].pos[0]) - (Y[1] - Y[0]) * (o[2].pos[0] - o[0].pos[0])) / area;
+                        const double gy0 = (-(X[2] - X[0]) * (o[1].pos[0] - o[0].pos[0]) + (X[1] - X[0]) * (o[2].pos[0] - o[0].pos[0])) / area;
+                        const double gx1 = ((Y[2] - Y[0]) * (o[1].pos[1] - o[0].pos[1]) - (Y[1] - Y[0]) * (o[2].pos[1] - o[0].pos[1])) / area;
+                        const double gy1 = (-(X[2] - X[0]) * (o[1].pos[1] - o[0].pos[1]) + (X[1] - X[0]) * (o[2].pos[1] - o[0].pos[1])) / area;
+                        const double grad = std::max(std::fabs(gx0) + std::fabs(gy0), std::fabs(gx1) + std::fabs(gy1));
+                        const double delta_px = std::ldexp((double)std::max(W, H), -23);
+                        const double tq = (double)tol + 2.0 * delta_px * grad;
                         const int ux0 = (int)std::max(0.0, std::floor(xmn - 1.5)), ux1 = (int)std::min((double)(W - 1), std::ceil(xmx + 0.5));
                         const int uy0 = std::max(by0, (int)std::max(0.0, std::floor(ymn - 1.5)));
                         const int uy1 = std::min(by1, (int)std::min((double)(H - 1), std::ceil(ymx + 0.5)));
@@ -364,10 +377,10 @@ void ref_draw_ex(float* rgba, const float* scene_depth, int depth_func, int64_t*
                                 const double qx = l0 * o[0].pos[0] + l1 * o[1].pos[0] + l2 * o[2].pos[0];
                                 const double qy = l0 * o[0].pos[1] + l1 * o[1].pos[1] + l2 * o[2].pos[1];
                                 const double ax = std::fabs(qx), ay = std::fabs(qy);
-                                bool u = (std::fabs(ax - 2.0) < tol && ay < 2.0 + tol) || (std::fabs(ay - 2.0) < tol && ax < 2.0 + tol);
-                                if (!u && ax <= 2.0 + tol && ay <= 2.0 + tol) {
+                                bool u = (std::fabs(ax - 2.0) < tq && ay < 2.0 + tq) || (std::fabs(ay - 2.0) < tq && ax < 2.0 + tq);
+                                if (!u && ax <= 2.0 + tq && ay <= 2.0 + tq) {
                                     const double a = std::exp(-(qx * qx + qy * qy)) * (double)o[0].opacity;
-                                    u = std::fabs(a - 1.0 / 255.0) < (double)tol * 0.05;
+                                    u = std::fabs(a - 1.0 / 255.0) < tq * 0.05;      /* |da/dq| = 2 |q| a <= 0.02 on the ring */
                                 }
                                 /* a flip of this fragment moves the pixel by at most (1 - dst.a) * opacity: deep layers behind an
                                  * (almost) opaque pixel cannot matter and are not flagged */
