@@ -7,7 +7,8 @@ per-frame DRAM-traffic / warp-instruction JSON that bench.py reads for `roofline
            --csv profiles/r02_ncu_full_summary.csv --json profiles/r02_ncu_traffic.json --frame-kernel cell_project_kernel
 
 --frame-kernel: a kernel that runs once per frame; the launches between two of its occurrences are taken as ONE frame for the
-per-frame sums (without it every captured launch is summed).  Runs on the CPU container: needs only `ncu -i`."""
+per-frame sums (without it every captured launch is summed).  --periodic: for a static camera, find the period of the launch
+sequence and sum its last full period (the capture need not start on a frame boundary).  Runs on the CPU container: needs only `ncu -i`."""
 import argparse
 import csv
 import io
@@ -44,6 +45,8 @@ def main():
     ap.add_argument("--json", required=True)
     ap.add_argument("--frame-kernel", default="")
     ap.add_argument("--note", default="")
+    ap.add_argument("--periodic", action="store_true",
+                    help="static camera: the per-frame sums are taken over the last full period of the launch sequence")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -69,6 +72,20 @@ def main():
         idx = [i for i, (n, _) in enumerate(launches) if a.frame_kernel in n]
         if len(idx) >= 2:
             frame = launches[idx[0]:idx[1]]
+        elif len(idx) == 1:                       # one frame start in the capture: the frame ends with its last blend launch
+            end, blends = idx[0], 0
+            for i in range(idx[0], len(launches)):
+                if "blend_kernel" in launches[i][0]:
+                    blends += 1; end = i + 1
+                    if blends == a.chunks:
+                        break
+            frame = launches[idx[0]:end]
+    if a.periodic:
+        # static camera: every frame launches the same sequence, so ANY window of one period is one frame's set of launches
+        names = [n for n, _ in launches]
+        period = next((P for P in range(4, len(names)) if all(names[i] == names[i + P] for i in range(len(names) - P))), None)
+        if period:
+            frame = launches[len(launches) - period:]
     with open(a.csv, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on: {len(launches)} captured launches of bench.py, {a.workload}, "
                 f"{a.chunks} depth chunks; per launch.  {a.note}\n")
