@@ -27,6 +27,7 @@
 // instruction but runs on the ADU pipe at ~2 cycles per DISTINCT value (ncu r01: ADU 97 % busy, 62 cycles per
 // warp for random digits), so the mask is built from one vote.ballot per digit bit instead (<= 8 ballots + LOP3).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gsb {
 
@@ -112,7 +113,7 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid)
     unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < NBITS; ++b) {
-        const bool bit = (d >> b) & 1u;
+        const bool bit = (d & (1u << b)) != 0u;                  // one LOP3 with a predicate result, no shift
         const unsigned m = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? m : ~m;
     }
@@ -153,7 +154,10 @@ os_hist_kernel(const uint32_t* __restrict__ keys, size_t n_max, const unsigned l
 // ---- one pass ------------------------------------------------------------------------------------------------
 // lookback layout: [tile][nbins] 64-bit entries (epoch << 32 | flags | count): a tile publishes one coalesced row; a
 // look-back step reads LB_WIN rows.  Persistent: every CTA loops over ticketed tiles until the tickets run out.
-template <int NBITS, int THREADS, int MINB, class DigitFn>
+// ATOMIC_MATCH: the lanes of a warp that share a digit find each other through one shared-memory atomicOr per key on a
+// [warp][digit] mask table (aliased onto the reorder staging area, which is idle during the ranking) instead of NBITS
+// ballots with ~6 instructions each: the ranking loop was 49 % of the pass's instructions (r02 ncu source counters).
+template <int NBITS, int THREADS, int MINB, bool ATOMIC_MATCH, class DigitFn>
 __global__ void __launch_bounds__(THREADS, MINB)
 os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, const size_t n_max,
@@ -193,32 +197,51 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     for (;;) {
         if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
         for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
+        uint32_t* const masks = sm.sk;                                  // [warp][nbins]: <= 16 x 512 words = sk + sv
+        if (ATOMIC_MATCH) {
+            static_assert(sizeof(sm.sk) + sizeof(sm.sv) >= sizeof(uint32_t) * RS_WARPS * nbins, "mask table fits the staging area");
+            for (int i = threadIdx.x; i < RS_WARPS * nbins; i += RS_THREADS) masks[i] = 0u;
+        }
         __syncthreads();
         const uint32_t tile = sm.tile;
         if (tile >= num_tiles) break;                                   // CTA-uniform
 
         const size_t base = (size_t)tile * RS_TILE;
         const uint32_t tile_count = (uint32_t)((n - base < (size_t)RS_TILE) ? (n - base) : (size_t)RS_TILE);
+        // item j of this thread is local element li0 + 32 j of the tile (warp-striped inside the warp's 256-element chunk): one
+        // pointer per array and immediate offsets, validity as a 32-bit compare against the elements left from li0 on
+        const uint32_t li0 = (uint32_t)warp * (32u * RS_ITEMS) + (uint32_t)lane;
+        const int rem = (int)tile_count - (int)li0;                   // item j is valid iff 32 j < rem
+        const uint32_t* __restrict__ kp = keys_in + base + li0;
+        const uint32_t* __restrict__ vp = vals_in + base + li0;
         uint32_t k[RS_ITEMS];
-        uint16_t rank[RS_ITEMS];
+        uint32_t rd[RS_ITEMS];                                        // rank | digit << 16 (rank <= 4096, digit < 512)
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-            size_t idx = item_index(base, warp, lane, j);
-            k[j] = (idx < n) ? __ldg(keys_in + idx) : 0u;
-        }
+        for (int j = 0; j < RS_ITEMS; ++j) k[j] = (32 * j < rem) ? __ldg(kp + 32 * j) : 0u;
 
         // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) {
-            size_t idx = item_index(base, warp, lane, j);
-            bool valid = idx < n;
-            uint32_t d = dig(k[j]);
-            unsigned peers = match_digit<NBITS>(d, valid);
-            uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
-            __syncwarp();
-            if (valid && lane == (__ffs(peers) - 1)) sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers));
-            __syncwarp();
-            rank[j] = (uint16_t)(pre + __popc(peers & lt));
+            const bool valid = 32 * j < rem;
+            const uint32_t d = dig(k[j]);
+            if (ATOMIC_MATCH) {
+                uint32_t* const mp = masks + warp * nbins + d;
+                if (valid) atomicOr(mp, 1u << lane);
+                __syncwarp();
+                const unsigned peers = valid ? *reinterpret_cast<volatile uint32_t*>(mp) : 0u;
+                const uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
+                __syncwarp();                                           // everyone has read the mask and the count
+                if (valid && lane == (__ffs(peers) - 1)) { sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers)); *mp = 0u; }
+                __syncwarp();
+                rd[j] = (pre + __popc(peers & lt)) | (d << 16);
+            } else {
+                const unsigned peers = match_digit<NBITS>(d, valid);
+                const uint32_t pre = valid ? sm.cnt[warp][d] : 0u;
+                __syncwarp();
+                if (valid && lane == (__ffs(peers) - 1)) sm.cnt[warp][d] = (uint16_t)(pre + __popc(peers));
+                __syncwarp();
+                rd[j] = (pre + __popc(peers & lt)) | (d << 16);
+            }
         }
         __syncthreads();
 
@@ -226,10 +249,7 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
         // during the ranking (the kernel runs at 40 registers for 3 CTAs per SM) and their latency hides behind the scans
         uint32_t v[RS_ITEMS];
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-            size_t idx = item_index(base, warp, lane, j);
-            v[j] = (idx < n) ? __ldg(vals_in + idx) : 0u;
-        }
+        for (int j = 0; j < RS_ITEMS; ++j) v[j] = (32 * j < rem) ? __ldg(vp + 32 * j) : 0u;
 
         // thread d: exclusive prefix over warps for digit d, tile total for d; publish the aggregate
         uint32_t total = 0;
@@ -255,10 +275,9 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
         // key/value/rank registers die before the look-back)
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) {
-            size_t idx = item_index(base, warp, lane, j);
-            if (idx < n) {
-                uint32_t d = dig(k[j]);
-                uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + rank[j];
+            if (32 * j < rem) {
+                const uint32_t d = rd[j] >> 16;
+                const uint32_t lp = sm.local_base[d] + sm.cnt[warp][d] + (rd[j] & 0xffffu);
                 sm.sk[lp] = k[j]; sm.sv[lp] = v[j];
             }
         }
@@ -333,11 +352,10 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
 
 #pragma unroll
         for (int t = 0; t < RS_ITEMS; ++t) {
-            uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
+            const uint32_t i = (uint32_t)t * RS_THREADS + threadIdx.x;
             if (i < tile_count) {
-                uint32_t key = sm.sk[i];
-                uint32_t d = dig(key);
-                size_t o = (size_t)(sm.global_delta[d] + i);
+                const uint32_t key = sm.sk[i];
+                const uint32_t o = sm.global_delta[dig(key)] + i;          // < 2^30 elements: 32-bit offsets
                 keys_out[o] = key; vals_out[o] = sm.sv[i];
             }
         }
@@ -387,12 +405,13 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     static bool attr_set = false;
     static int pass_ctas_per_sm = GSB_RS_MINB;
     if (!attr_set) {
-#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
+#define GSB_SET_ATTR(B) cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, true, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)); \
+                        cudaFuncSetAttribute(os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, false, BitsDigit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem))
         GSB_SET_ATTR(1); GSB_SET_ATTR(2); GSB_SET_ATTR(3); GSB_SET_ATTR(4); GSB_SET_ATTR(5); GSB_SET_ATTR(6); GSB_SET_ATTR(7);
         GSB_SET_ATTR(8); GSB_SET_ATTR(9);
 #undef GSB_SET_ATTR
         int per = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, RS_THREADS, GSB_RS_MINB, BitsDigit>, RS_THREADS, sizeof(PassSmem)) == cudaSuccess && per >= 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, os_pass_kernel<8, RS_THREADS, GSB_RS_MINB, true, BitsDigit>, RS_THREADS, sizeof(PassSmem)) == cudaSuccess && per >= 1)
             pass_ctas_per_sm = per;
         attr_set = true;
     }
@@ -412,18 +431,24 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
         os_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(k0, n_max, n_dev, plan, hist);
         if (launches) *launches += 1;
     }
+    // GSB_RS_MATCH=ballot in the environment selects the ballot ranking (A/B runs); default: shared-memory atomicOr
+    static const bool atomic_match = [] { const char* e = getenv("GSB_RS_MATCH"); return !(e && e[0] == 'b'); }();
     const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
     const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
-#define GSB_PASS(B) case B: os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(kin, vin, kout, vout, n_max, n_dev, \
-                        BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, hist + p * RS_RADIX, lookback + lb_off[p], nb, \
-                        tickets + p, error_flag, epoch); break
+#define GSB_PASS_ARGS(B) kin, vin, kout, vout, n_max, n_dev, BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, \
+                        hist + p * RS_RADIX, lookback + lb_off[p], nb, tickets + p, error_flag, epoch
+#define GSB_PASS(B) case B: \
+            if (atomic_match) os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, true, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(GSB_PASS_ARGS(B)); \
+            else os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, false, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(GSB_PASS_ARGS(B)); \
+            break
         switch (plan.bits[p]) {
             GSB_PASS(1); GSB_PASS(2); GSB_PASS(3); GSB_PASS(4); GSB_PASS(5); GSB_PASS(6); GSB_PASS(7); GSB_PASS(8); GSB_PASS(9);
         }
 #undef GSB_PASS
+#undef GSB_PASS_ARGS
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
