@@ -164,7 +164,7 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
                const unsigned long long* __restrict__ n_dev,
                const DigitFn dig, const uint32_t* __restrict__ hist,
                unsigned long long* __restrict__ lookback, const unsigned tiles_max, uint32_t* __restrict__ ticket,
-               uint32_t* __restrict__ error_flag, const uint32_t epoch)
+               uint32_t* __restrict__ error_flag, const uint32_t epoch, const int static_first)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = PassSmemT<THREADS>;
@@ -179,31 +179,26 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     const unsigned num_tiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
     const unsigned long long etag = (unsigned long long)epoch << 32;
 
-    // global digit offsets of this pass: exclusive scan of the histogram, once per CTA
-    {
-        const uint32_t hv = ((int)threadIdx.x < nbins) ? __ldg(hist + threadIdx.x) : 0u;
-        uint32_t inc = hv;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
-        if (lane == 31) sm.wtot[warp] = inc;
-        __syncthreads();
-        uint32_t woff = 0;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
-        if ((int)threadIdx.x < nbins) sm.digit_base[threadIdx.x] = woff + inc - hv;
-        __syncthreads();
-    }
-
+    // static_first: the first tile of a CTA is its block index and later ones come from the ticket counter (which then
+    // starts at gridDim.x), so the first key loads wait neither for the ticket's round trip nor for the histogram: the three
+    // global latencies of a short pass (ticket, histogram, keys) overlap.  The grid never exceeds the resident capacity, so
+    // every statically assigned tile is running and the look-back cannot starve.
+    uint32_t tile = blockIdx.x;
+    bool first_tile = true;
+    const uint32_t ticket_base = static_first ? gridDim.x : 0u;
     for (;;) {
-        if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
+        const bool draw = !first_tile || !static_first;                 // CTA-uniform
+        if (draw && threadIdx.x == 0) sm.tile = ticket_base + atomicAdd(ticket, 1u);
         for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&sm.cnt[0][0])[i] = 0u;
         uint32_t* const masks = sm.sk;                                  // [warp][nbins]: <= 16 x 512 words = sk + sv
         if (ATOMIC_MATCH) {
             static_assert(sizeof(sm.sk) + sizeof(sm.sv) >= sizeof(uint32_t) * RS_WARPS * nbins, "mask table fits the staging area");
             for (int i = threadIdx.x; i < RS_WARPS * nbins; i += RS_THREADS) masks[i] = 0u;
         }
-        __syncthreads();
-        const uint32_t tile = sm.tile;
+        if (draw) {
+            __syncthreads();
+            tile = sm.tile;
+        }
         if (tile >= num_tiles) break;                                   // CTA-uniform
 
         const size_t base = (size_t)tile * RS_TILE;
@@ -218,6 +213,22 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
         uint32_t rd[RS_ITEMS];                                        // rank | digit << 16 (rank <= 4096, digit < 512)
 #pragma unroll
         for (int j = 0; j < RS_ITEMS; ++j) k[j] = (32 * j < rem) ? __ldg(kp + 32 * j) : 0u;
+        if (first_tile) {
+            // global digit offsets of this pass: exclusive scan of the histogram, once per CTA, behind the first key loads
+            // (its barriers also order the clearing of cnt / masks above when no ticket was drawn)
+            const uint32_t hv = ((int)threadIdx.x < nbins) ? __ldg(hist + threadIdx.x) : 0u;
+            uint32_t inc = hv;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
+            if (lane == 31) sm.wtot[warp] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) woff += (w < warp) ? sm.wtot[w] : 0u;
+            if ((int)threadIdx.x < nbins) sm.digit_base[threadIdx.x] = woff + inc - hv;
+            __syncthreads();
+            first_tile = false;
+        }
 
         // stable rank of every item among equal digits of its warp, items visited in (j, lane) order
 #pragma unroll
@@ -433,13 +444,14 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     }
     // GSB_RS_MATCH=ballot in the environment selects the ballot ranking (A/B runs); default: shared-memory atomicOr
     static const bool atomic_match = [] { const char* e = getenv("GSB_RS_MATCH"); return !(e && e[0] == 'b'); }();
+    static const int static_first = [] { const char* e = getenv("GSB_RS_STATIC"); return (e && atoi(e) == 0) ? 0 : 1; }();
     const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
     const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     int cur = 0;
     for (int p = 0; p < plan.passes; ++p) {
 #define GSB_PASS_ARGS(B) kin, vin, kout, vout, n_max, n_dev, BitsDigit{ plan.shift[p], (1u << B) - 1u, key_min, key_span }, \
-                        hist + p * RS_RADIX, lookback + lb_off[p], nb, tickets + p, error_flag, epoch
+                        hist + p * RS_RADIX, lookback + lb_off[p], nb, tickets + p, error_flag, epoch, static_first
 #define GSB_PASS(B) case B: \
             if (atomic_match) os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, true, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(GSB_PASS_ARGS(B)); \
             else os_pass_kernel<B, RS_THREADS, GSB_RS_MINB, false, BitsDigit><<<grid, RS_THREADS, sizeof(PassSmem), s>>>(GSB_PASS_ARGS(B)); \
