@@ -86,6 +86,9 @@ size_t   scan_scratch_bytes(size_t n);
 // exclusive scan of n uint32; out may alias in.  If total_dev != nullptr the 64-bit grand total is stored there.
 void     exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scratch,
                             unsigned long long* total_dev, cudaStream_t s, int* launches);
+size_t   scan_status_bytes(size_t n);
+void     exclusive_scan_u32_onepass(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* status, uint32_t epoch,
+                                    unsigned long long* total_dev, uint32_t* error_flag, cudaStream_t s, int* launches);
 // Stable LSD radix sort of (key,val) pairs on key bits [begin_bit, end_bit) of the squeezed key (see below).
 // Ping-pongs between (k0,v0) and (k1,v1); returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
 //   n_max      host-side upper bound of the element count (< 2^30): sizes the grid cap and the look-back table

@@ -219,6 +219,7 @@ struct gsb_context {
     DevBuf wire_verts, wire_cols, wire_owner;         // wireframe overlay (gsb_render_wireframe)
     DevBuf shared_frame;                             // exported through CUDA IPC to the other ranks (display rank only)
     DevBuf scan_scratch;
+    DevBuf scan_status;                               // single-pass count scan: epoch-tagged tile states (zeroed when allocated)
     unsigned long long* counters_h = nullptr;        // pinned mirror: [0..8) frame counters, [8..16) the current chunk's, [16..) every chunk's at frame end
     int order_buf = 0, order_vals_buf = 0, inst_buf = 0;
     int chunks_last = 0;
@@ -368,6 +369,7 @@ static uint32_t next_epoch(gsb_context* ctx)
 {
     if (ctx->sort_epoch >= 0xFFFFFFF0u) {
         if (ctx->lookback.p) cudaMemsetAsync(ctx->lookback.p, 0, ctx->lookback.cap, ctx->stream);
+        if (ctx->scan_status.p) cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.cap, ctx->stream);
         ctx->sort_epoch = 0;
     }
     return ++ctx->sort_epoch;
@@ -933,6 +935,10 @@ try {
         CU(ctx->rects.ensure(N * 8));
     }
     CU(ctx->scan_scratch.ensure(std::max(scan_scratch_bytes(N), select_scratch_bytes(n))));
+    if (scan_status_bytes(N) > ctx->scan_status.cap) {
+        CU(ctx->scan_status.ensure(scan_status_bytes(N)));
+        CU(cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.cap, s));
+    }
     CU(ctx->ranges.ensure((size_t)num_tiles * 8));
     const size_t done_bytes = (size_t)done_words_per_row(fc.tiles_x) * (size_t)fc.tiles_y * 4;      // one bit per tile
     CU(ctx->live_sat.ensure((size_t)(fc.tiles_x + 1) * (size_t)(fc.tiles_y + 1) * 4));
@@ -1161,7 +1167,12 @@ try {
         // builds the digit histograms of the tile partition; r02 measured the scan INSIDE the emit, one decoupled look-back
         // per CTA: 16 us slower per frame than the three small scan kernels) -> stable partition by tile -> tile ranges
         const SortPlan tile_plan = sort_plan(0, tile_bits);
-        exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+        // (one launch: reduce, decoupled look-back over epoch-tagged tile states and apply; GSB_SCAN=3 in the environment keeps
+        // the three-launch scan for A/B runs.  Every partial sum is below the 2^30 - 1 instance limit checked above.)
+        static const bool scan3 = [] { const char* e = getenv("GSB_SCAN"); return e && atoi(e) == 3; }();
+        if (scan3) exclusive_scan_u32(counts, counts, (size_t)L, ctx->scan_scratch.p, cc + 3, s, &st.launches);
+        else exclusive_scan_u32_onepass(counts, counts, (size_t)L, ctx->scan_status.as<unsigned long long>(), next_epoch(ctx), cc + 3,
+                                        err_flag, s, &st.launches);
         launch_emit(ctx->ltiles.as<uint2>(), counts, cc + 3, (int64_t)L, fc,
                     first ? nullptr : tile_done, ctx->ikeys[0].as<uint32_t>(), ctx->ivals[0].as<uint32_t>(), tile_plan, hdr_tile, s);
         st.launches += (L ? 1 : 0);
@@ -1466,12 +1477,21 @@ int gsb_debug_exclusive_scan(gsb_context* ctx, const uint32_t* in, uint64_t n, u
 try {
     if (!ctx || (n && (!in || !out))) return fail(GSB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(ctx->device));
-    DevBuf a, b, scr, tot;
+    DevBuf a, b, scr, tot, status;
     CU(a.ensure(n * 4 + 16)); CU(b.ensure(n * 4 + 16)); CU(scr.ensure(scan_scratch_bytes(n))); CU(tot.ensure(16));
+    CU(status.ensure(scan_status_bytes(n)));
     cudaStream_t s = ctx->stream;
     CU(cudaMemcpyAsync(a.p, in, n * 4, cudaMemcpyHostToDevice, s));
     int launches = 0;
-    exclusive_scan_u32(a.as<uint32_t>(), b.as<uint32_t>(), n, scr.p, tot.as<unsigned long long>(), s, &launches);
+    // inputs whose total stays below 2^30 go through the single-pass scan the frame uses, anything larger through the
+    // three-launch scan (64-bit prefixes)
+    unsigned long long sum = 0;
+    for (uint64_t i = 0; i < n; ++i) sum += in[i];
+    if (sum < (1ull << 30)) {
+        CU(cudaMemsetAsync(status.p, 0, status.cap, s));
+        exclusive_scan_u32_onepass(a.as<uint32_t>(), b.as<uint32_t>(), n, status.as<unsigned long long>(), 1u, tot.as<unsigned long long>(),
+                                   nullptr, s, &launches);
+    } else exclusive_scan_u32(a.as<uint32_t>(), b.as<uint32_t>(), n, scr.p, tot.as<unsigned long long>(), s, &launches);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, b.p, n * 4, cudaMemcpyDeviceToHost, s));
     unsigned long long t = 0;

@@ -132,6 +132,93 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
         for (int k = 0; k < SCAN_ITEMS; ++k) if (first + k < n) out[first + k] = y[k];
     }
 }
+
+// ---- single pass (r02): reduce, decoupled look-back and apply in ONE launch ---------------------------------------------
+// status[tile] = epoch << 32 | flag | value (value < 2^30).  Entries of another epoch mean "not published yet", so the table
+// is never cleared between scans (it is zeroed once when allocated; the caller's epoch counter never repeats within 2^32
+// scans).  Tile t = blockIdx.x: like CUB's scan this relies on CTAs being dispatched in index order, so every predecessor
+// of a running tile is running or done; the spins are bounded all the same and a time-out raises *error_flag.
+constexpr uint32_t ST_AGG = 0x40000000u, ST_INCL = 0x80000000u, ST_MASK = 0x3FFFFFFFu, ST_SPIN_LIMIT = 1u << 22;
+__device__ __forceinline__ unsigned long long st_ld(const unsigned long long* p)
+{
+    unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_st(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                    size_t n, unsigned long long* __restrict__ status,
+                                                                    const uint32_t epoch, unsigned long long* __restrict__ total,
+                                                                    uint32_t* __restrict__ error_flag)
+{
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    __shared__ uint32_t s_excl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    const size_t base = (size_t)tile * SCAN_CHUNK;
+    const unsigned long long etag = (unsigned long long)epoch << 32;
+    uint32_t x[SCAN_ITEMS];
+    load_items(in, base, n, x);
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) tsum += x[k];
+    const uint32_t inc = warp_incl_scan(tsum, lane);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) { woff += (w < warp) ? wsum[w] : 0u; tile_total += wsum[w]; }
+    if (warp == 0) {
+        // publish the aggregate (tile 0: already inclusive), then walk back over the predecessors, 32 at a time
+        if (lane == 0) st_st(status + tile, etag | (tile_total & ST_MASK) | (tile == 0 ? ST_INCL : ST_AGG));
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t q = (int64_t)tile - 1;               // nearest predecessor not summed yet
+            uint32_t spins = 0;
+            for (;;) {
+                const int64_t mine = q - lane;
+                unsigned long long v = (mine >= 0) ? st_ld(status + mine) : (etag | ST_INCL);
+                const bool ready = (uint32_t)(v >> 32) == epoch && ((uint32_t)v & (ST_AGG | ST_INCL)) != 0u;
+                const unsigned not_ready = __ballot_sync(0xffffffffu, !ready);
+                const unsigned incl = __ballot_sync(0xffffffffu, ready && ((uint32_t)v & ST_INCL) != 0u);
+                // lanes [0, stop) are usable: up to the first inclusive entry, and only below the first entry not ready
+                const int first_nr = not_ready ? (__ffs(not_ready) - 1) : 32;
+                const int first_in = incl ? (__ffs(incl) - 1) : 32;
+                const int stop = first_in < first_nr ? first_in + 1 : first_nr;
+                uint32_t part = (lane < stop) ? ((uint32_t)v & ST_MASK) : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                excl += part;
+                q -= stop;
+                if (first_in < first_nr) break;          // met an inclusive prefix
+                if (stop == 0) {
+                    if (++spins > ST_SPIN_LIMIT) { if (lane == 0 && error_flag) atomicExch(error_flag, 1u); break; }
+                    __nanosleep(20);
+                }
+            }
+            if (lane == 0) st_st(status + tile, etag | ((excl + tile_total) & ST_MASK) | ST_INCL);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (total && base + SCAN_CHUNK >= n) *total = (unsigned long long)excl + tile_total;     // the last tile
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_excl + woff + (inc - tsum);
+    const size_t first = base + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t y[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { y[k] = run; run += x[k]; }
+    if (first + SCAN_ITEMS <= n && ((reinterpret_cast<uintptr_t>(out + first) & 15u) == 0)) {
+        uint4* p = reinterpret_cast<uint4*>(out + first);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) p[k] = make_uint4(y[4 * k], y[4 * k + 1], y[4 * k + 2], y[4 * k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) if (first + k < n) out[first + k] = y[k];
+    }
+}
 }  // namespace
 
 static inline size_t scan_chunks(size_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK; }
@@ -157,6 +244,21 @@ void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* scrat
     scan_partials_kernel<<<1, 1024, 0, s>>>(partial, m, prefix, total_dev);
     scan_apply_kernel<<<(unsigned)m, SCAN_THREADS, 0, s>>>(in, out, n, prefix);
     if (launches) *launches += 3;
+}
+
+// single launch; status: scan_status_bytes(n) bytes, zeroed when allocated, never cleared afterwards; epoch: a value no
+// earlier scan on this table used; every partial sum must stay below 2^30
+size_t scan_status_bytes(size_t n) { return (scan_chunks(n) + 1) * sizeof(unsigned long long) + 256; }
+
+void exclusive_scan_u32_onepass(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* status, uint32_t epoch,
+                                unsigned long long* total_dev, uint32_t* error_flag, cudaStream_t s, int* launches)
+{
+    if (n == 0) {
+        if (total_dev) cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), s);
+        return;
+    }
+    scan_onepass_kernel<<<(unsigned)scan_chunks(n), SCAN_THREADS, 0, s>>>(in, out, n, status, epoch, total_dev, error_flag);
+    if (launches) *launches += 1;
 }
 
 }  // namespace gsb
