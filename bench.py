@@ -466,6 +466,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "Msplats/s", "fps": 1e3 / e2e_ms, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 368 * world, "d2h_bytes_per_step": frame_bytes,
                 "host_direct": True if world > 1 else bool(args.host_direct),
+                "host_frame_on_gpu_local_cpus": (len(mg.host_cpus) if getattr(mg, "host_cpus", None) else None),
                 "note": "gsb_render with a pinned host target: gsb_frame in, RGBA32F frame stored into host memory by the blend "
                         "kernels (every rank over its own PCIe link; N>1: one shared frame + a 4-byte all-reduce fence), the call "
                         "returns when the frame is there; geometry resident (the reference also re-uploads only on active-set change)"},

@@ -97,6 +97,46 @@ class SharedHostFrames:
                 pass
 
 
+class near_gpu:
+    """Context manager: run the enclosed host-side setup on the CPUs NVML reports as local to CUDA device ``device`` (its
+    NUMA node), then restore the previous affinity.  Page-locked host memory is placed where the thread that registers /
+    first touches it runs; a frame that the blend kernels store into over PCIe should live on the GPU's own node.  A no-op
+    when NVML, the device UUID or sched_setaffinity are unavailable (GSB_NUMA_AFFINITY=0 turns it off)."""
+
+    def __init__(self, device: int):
+        self.device, self.saved, self.cpus = device, None, None
+
+    def __enter__(self):
+        if os.environ.get("GSB_NUMA_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+            return self
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus)
+            self.cpus = sorted(cpus)
+        except Exception:                                     # noqa: BLE001 - placement is an optimisation, never an error
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:                                 # noqa: BLE001
+                pass
+        return False
+
+
 class RowPartitionedRenderer:
     """Per-rank driver of a row-partitioned frame: owns the shared frames, the per-frame fence and the hand-off.
 
@@ -136,14 +176,16 @@ class RowPartitionedRenderer:
         # host frames: one shared-memory file mapped by every rank, page-locked + device-mapped by each of them
         name = [None]
         self.shm = None
-        if rank == 0:
-            self.shm = SharedHostFrames(width, height, 2)
-            name[0] = self.shm.name
-        if world > 1:
-            dist.broadcast_object_list(name, src=0)
-        if rank != 0:
-            self.shm = SharedHostFrames(width, height, 2, name=name[0])
-        renderer.host_register(self.shm.buffer)
+        with near_gpu(torch.cuda.current_device()) as ng:     # the frame's pages go to the GPU's own NUMA node
+            self.host_cpus = ng.cpus
+            if rank == 0:
+                self.shm = SharedHostFrames(width, height, 2)
+                name[0] = self.shm.name
+            if world > 1:
+                dist.broadcast_object_list(name, src=0)
+            if rank != 0:
+                self.shm = SharedHostFrames(width, height, 2, name=name[0])
+            renderer.host_register(self.shm.buffer)
 
     def device_frame(self) -> int | None:
         """Display rank: device pointer of the frame the last render() completed (p2p / nccl modes)."""
