@@ -445,7 +445,14 @@ int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, siz
     // GSB_RS_MATCH=ballot in the environment selects the ballot ranking (A/B runs); default: shared-memory atomicOr
     static const bool atomic_match = [] { const char* e = getenv("GSB_RS_MATCH"); return !(e && e[0] == 'b'); }();
     static const int static_first = [] { const char* e = getenv("GSB_RS_STATIC"); return (e && atoi(e) == 0) ? 0 : 1; }();
-    const unsigned cap = (unsigned)(NUM_SMS * pass_ctas_per_sm);
+    // resident capacity from the SMs this device really has (the static first tile relies on every CTA of the grid being
+    // resident at once; NUM_SMS = 148 is the full B200, a partitioned or cut-down part reports fewer)
+    static const int sms = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = NUM_SMS;
+        return v;
+    }();
+    const unsigned cap = (unsigned)(sms * pass_ctas_per_sm);
     const unsigned grid = nb < cap ? nb : cap;
     uint32_t* kin = k0; uint32_t* vin = v0; uint32_t* kout = k1; uint32_t* vout = v1;
     int cur = 0;
