@@ -36,6 +36,12 @@ def short(name: str) -> str:
     return m.group(1) + (f"<{m.group(2)}>" if m.group(2) else "")
 
 
+def find_period(names, shortest=4):
+    """Smallest P >= shortest with names[i] == names[i + P] for every i (the launch sequence of a static-camera run repeats
+    frame by frame), or None if the capture holds less than two periods' worth of evidence."""
+    return next((P for P in range(shortest, len(names)) if all(names[i] == names[i + P] for i in range(len(names) - P))), None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("report")
@@ -82,8 +88,7 @@ def main():
             frame = launches[idx[0]:end]
     if a.periodic:
         # static camera: every frame launches the same sequence, so ANY window of one period is one frame's set of launches
-        names = [n for n, _ in launches]
-        period = next((P for P in range(4, len(names)) if all(names[i] == names[i + P] for i in range(len(names) - P))), None)
+        period = find_period([n for n, _ in launches])
         if period:
             frame = launches[len(launches) - period:]
     with open(a.csv, "w") as f:
