@@ -12,20 +12,23 @@
 // tile in shared memory and scatters it coalesced.  Per pass each element is read once and written once:
 // 16 B/element/pass + 4 B for the histogram (68 B per element for 4 passes).
 //
-// Safety: tiles take their index from an atomic ticket, so a tile only ever waits on tiles that already
+// Safety: a CTA's first tile is its block index (the grid never exceeds the device's resident capacity, so all of those
+// run at once), every further tile comes from an atomic ticket, so a tile only ever waits on tiles that already
 // started; every spin is bounded and raises an error flag instead of hanging the GPU.
 //
 // r02: the frame pipeline never learns element counts on the host in time, so (i) every kernel reads n from DEVICE memory
-// (n_dev; the host only supplies an upper bound for the scratch size), (ii) the pass kernel is PERSISTENT: <= 2 CTAs per SM
-// loop over ticketed tiles, so a loose upper bound costs no empty CTAs, (iii) look-back entries are 64-bit, tagged with a
+// (n_dev; the host only supplies an upper bound for the scratch size), (ii) the pass kernel is PERSISTENT: three CTAs per SM
+// (40 registers, 60 KB of shared memory) loop over ticketed tiles, so a loose upper bound costs no empty CTAs, (iii) look-back entries are 64-bit, tagged with a
 // per-sort EPOCH in the high word: entries of earlier sorts read as "not published" and the table is never cleared,
-// (iv) the exclusive scan of the digit histogram happens at the start of every pass CTA (one block scan of <= 512 bins)
-// instead of in a kernel of its own, and (v) the histogram itself may be supplied by the kernel that produced the keys
+// (iv) the exclusive scan of the digit histogram happens inside every pass CTA (one block scan of <= 512 bins, behind the
+// first tile's key loads) instead of in a kernel of its own, and (v) the histogram itself may be supplied by the kernel that produced the keys
 // (hist_ready), which removes the upfront pass over them.
 //
 // Ranking inside a warp needs, per key, the mask of lanes holding the same digit.  match.any does that in one
 // instruction but runs on the ADU pipe at ~2 cycles per DISTINCT value (ncu r01: ADU 97 % busy, 62 cycles per
-// warp for random digits), so the mask is built from one vote.ballot per digit bit instead (<= 8 ballots + LOP3).
+// warp for random digits).  r01 built the mask from one vote.ballot per digit bit (<= 9 ballots at ~6 SASS each: 49 % of the
+// pass's instructions, r02 ncu source counters); r02 uses ONE shared-memory atomicOr per key on a [warp][digit] mask table
+// aliased onto the reorder staging area (ATOMIC_MATCH; the ballot form stays selectable with GSB_RS_MATCH=ballot).
 #include "common.cuh"
 #include <cstdlib>
 
