@@ -1165,7 +1165,7 @@ try {
         if (tm) CU(cudaEventRecord(ctx->evc[c][2], s));
         // K4: live-tile counts (K2) -> offsets (their exact total D stays on the device, cc + 3) -> instances (the emit also
         // builds the digit histograms of the tile partition; r02 measured the scan INSIDE the emit, one decoupled look-back
-        // per CTA: 16 us slower per frame than the three small scan kernels) -> stable partition by tile -> tile ranges
+        // per CTA: 16 us slower per frame than a scan kernel of its own) -> stable partition by tile -> tile ranges
         const SortPlan tile_plan = sort_plan(0, tile_bits);
         // (one launch: reduce, decoupled look-back over epoch-tagged tile states and apply; GSB_SCAN=3 in the environment keeps
         // the three-launch scan for A/B runs.  Every partial sum is below the 2^30 - 1 instance limit checked above.)

@@ -1,6 +1,9 @@
-// scan.cu — exclusive prefix sum over uint32 (reduce -> scan partials -> apply), sm_100a.
-// HBM-bound: 12 bytes per element (read, read, write).  Used for tile counts (V entries) and for the
-// radix sort's digit tables.  No spin-waits: three ordinary launches, so it cannot hang.
+// scan.cu — exclusive prefix sum over uint32, sm_100a.  Two forms:
+//  * exclusive_scan_u32_onepass (the frame's count scan): ONE launch — every CTA reduces its 4096-element tile, publishes the
+//    aggregate, obtains its exclusive prefix by decoupled look-back over epoch-tagged 64-bit tile states (bounded spins,
+//    error flag on time-out, never cleared between scans) and writes its outputs.  8 bytes per element.  Partial sums < 2^30.
+//  * exclusive_scan_u32 (reduce -> scan partials -> apply): three ordinary launches, 64-bit prefixes, no spin-waits; kept for
+//    totals beyond 2^30 and as the A/B reference (GSB_SCAN=3).  12 bytes per element.
 #include "common.cuh"
 
 namespace gsb {
